@@ -1,0 +1,85 @@
+"""Generates tests/golden/*.json by running the UNMODIFIED reference (/root/reference)
+through its own Simulator entry on the third-party stand-ins of oracle/shims/
+(see oracle/run_reference.py).  Run from the repo root, in the build container only:
+
+    python tests/golden/make_golden.py [case ...]
+
+Each case runs in its own process (the reference's per-problem modules share the
+module names `simulator` / `coordinator`).  Wall-clock stopping is disabled
+(maxtime=1e9) and the run is capped by `maxiter` (SURVEY.md App. C protocol).
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+
+COMMON = {"solver_option.common.tolresid": 0, "solver_option.common.maxtime": 1e9}
+CASES = {
+    # name: (problem, overrides)
+    "nonnegpca_1_a_K40": ("NonnegPCA", {"solver_option.common.maxiter": 40}),
+    "rosenbrock_K6": ("Rosenbrock", {"solver_option.common.maxiter": 6}),
+    "stableid_1_a_K25": ("StableIdentification", {"solver_option.common.maxiter": 25, "problem_initialpoint": "a"}),
+    "stableid_1_b_K25": ("StableIdentification", {"solver_option.common.maxiter": 25, "problem_initialpoint": "b"}),
+    "stableid_1_t_K25": ("StableIdentification", {"solver_option.common.maxiter": 25, "problem_initialpoint": "t"}),
+}
+# columns whose values depend on the reference's unseeded RNG (Rosenbrock callback,
+# src/Rosenbrock/simulator.py:52-57) or on wall-clock
+SKIP_COLUMNS = ("time", "second_order_residual", "condition_number")
+
+
+def _jsonable(v):
+    if v is None or isinstance(v, (str, bool)):
+        return v
+    if isinstance(v, (np.bool_,)):
+        return bool(v)
+    if isinstance(v, (int, np.integer)):
+        return int(v)
+    if isinstance(v, (float, np.floating)):
+        return float(v)
+    if isinstance(v, np.ndarray):
+        return v.tolist()
+    if isinstance(v, (list, tuple)):
+        return [_jsonable(u) for u in v]
+    raise TypeError(type(v))
+
+
+def run_case(name):
+    sys.path.insert(0, REPO)
+    from oracle.run_reference import run_reference
+
+    problem, ov = CASES[name]
+    overrides = dict(COMMON)
+    overrides.update(ov)
+    out, tcg, _ = run_reference(problem, overrides)
+    log = {k: _jsonable(v) for k, v in out.log.items() if k not in SKIP_COLUMNS}
+    doc = {
+        "case": name,
+        "problem": problem,
+        "overrides": {k: v for k, v in overrides.items()},
+        "generator": "tests/golden/make_golden.py (unmodified reference on oracle/shims stand-ins)",
+        "solver_name": out.name,
+        "stoppingcriterion": out.option["stoppingcriterion"].split(" after ")[0],
+        "x": _jsonable(out.x),
+        "ineqLagmult": _jsonable(out.ineqLagmult),
+        "tcg_iters": tcg,
+        "log": log,
+    }
+    with open(os.path.join(HERE, f"{name}.json"), "w") as f:
+        json.dump(doc, f)
+    print(name, "rows", len(log["iteration"]), "tcg hessvecs", sum(tcg))
+
+
+if __name__ == "__main__":
+    if len(sys.argv) == 3 and sys.argv[1] == "--one":
+        run_case(sys.argv[2])
+    else:
+        names = sys.argv[1:] or list(CASES)
+        procs = [(n, subprocess.Popen([sys.executable, __file__, "--one", n], cwd=REPO)) for n in names]
+        for n, p in procs:
+            if p.wait() != 0:
+                raise SystemExit(f"case {n} failed")
