@@ -1,0 +1,12 @@
+"""riptrm_b200 -- B200-native (sm_100a CUDA) trust-region path of the Riemannian interior-point
+trust-region method, behind the reference's `RIPTRM(option).run(problem) -> Output` interface.
+
+The directory name carries the reference's name; import it as `riptrm_b200` (repo-root shim)."""
+from . import _lib, options, structure
+from ._lib import RiptrmError, load_library
+from .solver import RIPTRM, BatchSolver, Output, trace_to_log
+from .structure import (NonnegPCAStructure, RosenbrockStructure, StableIdStructure,
+                        structure_from_problem)
+
+__all__ = ["RIPTRM", "BatchSolver", "Output", "trace_to_log", "RiptrmError", "load_library",
+           "NonnegPCAStructure", "RosenbrockStructure", "StableIdStructure", "structure_from_problem"]

@@ -1,0 +1,186 @@
+// fam_sphere.cuh -- NonnegPCA on Sphere(n): min -x'Zx, s_i = x_i + eps > 0
+// (src/NonnegPCA/coordinator.py:37-95; closed forms SURVEY.md App. A.1).
+//
+// One warp owns one instance.  S = Z + Z' (n x n, symmetric) sits in shared memory for the
+// whole solve; vectors are WVec<K> (element e = k*32 + lane), n <= 32*K.
+//
+//   grad f      = P_x(-Sx),   P_x u = u - <x,u> x        (pymanopt Sphere.projection)
+//   Hess L[v]   = P_x(-Sv) + (x'Sx) v + (y'x) v           (RIPTRM.py:491-523 + Sphere.ehess2rhess)
+//   G_x(w)      = P_x(w) ;  G*_x[v]_i = v_i - x_i <x,v>   (:525-571)
+//   Hw[v]       = Hess L[v] + G_x((y/s) * G*_x[v])        (:729)
+//   c           = grad f - G_x(mu / s)                     (:730)
+#pragma once
+#include "solver_warp.cuh"
+
+namespace riptrm {
+
+template <int K_>
+struct SphereFam {
+    static constexpr int K = K_;
+    static constexpr int MK = K_;
+    using Vec = WVec<K>;
+    using CVec = WVec<K>;
+
+    struct Ctx {
+        const double* S;  // shared memory, row-major n x n (+ tail padding), symmetric
+        double* vbuf;     // shared memory, 32*K doubles, staging for the broadcast operand
+        int n;
+        double eps;
+        bool embedded;    // 'is_euclidean_embedded'
+    };
+    struct Pt {
+        Vec x;
+        CVec s;
+        double cost;
+        Vec Sx;
+        double xSx;
+    };
+    struct Step {
+        Vec c;
+        CVec ys;       // y / s
+        double kappa;  // x'Sx + y'x
+    };
+
+    static __device__ __forceinline__ bool active(const Ctx& c, int k) { return k * 32 + lane_id() < c.n; }
+    static __device__ __forceinline__ bool cactive(const Ctx& c, int k) { return active(c, k); }
+    static __device__ __forceinline__ int dim(const Ctx& c) { return c.n - 1; }
+    static __device__ __forceinline__ int num_constraints(const Ctx& c) { return c.n; }
+    static __device__ __forceinline__ double typical_dist(const Ctx&) { return 3.141592653589793; }
+    static __device__ __forceinline__ bool domain_ok(const Ctx&, const Pt&) { return true; }
+
+    // out = S v.  S symmetric, so (S v)_e = sum_j S[j][e] v_j: lane-contiguous (conflict-free)
+    // reads of row j, v_j broadcast from shared memory.  Two accumulators per element
+    // (even j / odd j) halve the dependent-FMA chain; their sum order is part of the spec.
+    static __device__ __forceinline__ Vec matvec(const Ctx& c, const Vec& v) {
+        const int lane = lane_id();
+        const int n = c.n;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (active(c, k)) c.vbuf[k * 32 + lane] = v.v[k];
+        __syncwarp();
+        double a0[K], a1[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) a0[k] = a1[k] = 0.0;
+        const double* row = c.S + lane;
+        int j = 0;
+        for (; j + 1 < n; j += 2) {
+            const double2 vj = *reinterpret_cast<const double2*>(c.vbuf + j);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                a0[k] = fma(row[k * 32], vj.x, a0[k]);
+                a1[k] = fma(row[n + k * 32], vj.y, a1[k]);
+            }
+            row += 2 * n;
+        }
+        if (j < n) {
+            const double vj = c.vbuf[j];
+#pragma unroll
+            for (int k = 0; k < K; ++k) a0[k] = fma(row[k * 32], vj, a0[k]);
+        }
+        __syncwarp();
+        Vec out;
+#pragma unroll
+        for (int k = 0; k < K; ++k) out.v[k] = active(c, k) ? (a0[k] + a1[k]) : 0.0;
+        return out;
+    }
+
+    static __device__ __forceinline__ void eval_point(const Ctx& c, const Vec& x, Pt& pt) {
+        pt.x = x;
+        pt.Sx = matvec(c, x);
+        pt.xSx = wdot(x, pt.Sx);
+        pt.cost = -0.5 * pt.xSx;  // -x'Zx = -x'Sx/2
+#pragma unroll
+        for (int k = 0; k < K; ++k) pt.s.v[k] = active(c, k) ? (x.v[k] + c.eps) : 0.0;
+    }
+
+    static __device__ __forceinline__ double inner(const Ctx&, const Pt&, const Vec& a, const Vec& b) {
+        return wdot(a, b);
+    }
+
+    static __device__ __forceinline__ Vec project(const Ctx&, const Pt& pt, const Vec& v) {
+        const double a = wdot(pt.x, v);
+        Vec r;
+#pragma unroll
+        for (int k = 0; k < K; ++k) r.v[k] = v.v[k] - a * pt.x.v[k];
+        return r;
+    }
+
+    static __device__ __forceinline__ void begin_step(const Ctx& c, const Pt& pt, const CVec& y, double mu, Step& st) {
+        Vec w;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const bool on = active(c, k);
+            w.v[k] = on ? mu * (1.0 / pt.s.v[k]) : 0.0;
+            st.ys.v[k] = on ? y.v[k] / pt.s.v[k] : 0.0;
+        }
+        double xw = wdot_partial(pt.x, w), yx = wdot_partial(y, pt.x);
+        wsum2(xw, yx);
+        st.kappa = pt.xSx + yx;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double gradf = -pt.Sx.v[k] + pt.xSx * pt.x.v[k];  // P_x(-Sx); <x,-Sx> = -x'Sx exactly
+            const double Gw = w.v[k] - xw * pt.x.v[k];             // G_x(mu/s) = P_x(mu/s)
+            st.c.v[k] = gradf - Gw;
+        }
+    }
+
+    static __device__ __forceinline__ CVec gadj(const Ctx& c, const Pt& pt, const Vec& v) {
+        if (c.embedded) return v;
+        const double b = wdot(pt.x, v);
+        CVec g;
+#pragma unroll
+        for (int k = 0; k < K; ++k) g.v[k] = v.v[k] - pt.x.v[k] * b;
+        return g;
+    }
+
+    static __device__ __forceinline__ Vec Hw(const Ctx& c, const Pt& pt, const CVec&, const Step& st, const Vec& v) {
+        const Vec Sv = matvec(c, v);
+        double a = wdot_partial(pt.x, Sv), b = wdot_partial(pt.x, v);
+        wsum2(a, b);
+        Vec t, out;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double ga = c.embedded ? v.v[k] : (v.v[k] - pt.x.v[k] * b);
+            t.v[k] = st.ys.v[k] * ga;
+        }
+        const double d = wdot(pt.x, t);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double hl = (-Sv.v[k] + a * pt.x.v[k]) + st.kappa * v.v[k];
+            const double g = t.v[k] - d * pt.x.v[k];
+            out.v[k] = hl + g;
+        }
+        return out;
+    }
+
+    static __device__ __forceinline__ Vec retract(const Ctx&, const Pt& pt, const Vec& dx) {
+        Vec a;
+#pragma unroll
+        for (int k = 0; k < K; ++k) a.v[k] = pt.x.v[k] + dx.v[k];
+        const double nrm = sqrt(wdot(a, a));
+#pragma unroll
+        for (int k = 0; k < K; ++k) a.v[k] = a.v[k] / nrm;
+        return a;
+    }
+
+    // || grad f(x) + sum_i y_i grad g_i(x) ||, grad g_i = -P_x(e_i)
+    static __device__ __forceinline__ double gradL_norm(const Ctx&, const Pt& pt, const CVec& y) {
+        const double xy = wdot(pt.x, y);
+        Vec g;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            g.v[k] = (-pt.Sx.v[k] + pt.xSx * pt.x.v[k]) - (y.v[k] - xy * pt.x.v[k]);
+        return sqrt(wdot(g, g));
+    }
+
+    static __device__ __forceinline__ double manvio(const Ctx&, const Pt& pt) {
+        return sqrt(wdot(pt.x, pt.x)) - 1.0;  // src/NonnegPCA/simulator.py:12-14
+    }
+
+    static __device__ __forceinline__ double dist(const Ctx&, const Vec& xPrev, const Pt& pt) {
+        const double ip = fmax(fmin(wdot(xPrev, pt.x), 1.0), -1.0);  // pymanopt Sphere.dist
+        return acos(ip);
+    }
+};
+
+}  // namespace riptrm

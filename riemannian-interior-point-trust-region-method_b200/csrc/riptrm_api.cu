@@ -1,0 +1,486 @@
+// riptrm_api.cu -- C-ABI entry points (include/riptrm_b200.h) and the warp-per-instance kernels.
+//
+// Kernel shape for the batched small families: ONE warp per CTA, one (instance, initialpoint)
+// pair per warp at a time, a persistent grid (SM count x resident CTAs per SM) that pulls
+// instances from an atomic queue because per-instance work varies 3-5x.
+// There is no inter-warp synchronisation anywhere on the solve path.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/riptrm_b200.h"
+#include "fam_sphere.cuh"
+
+using namespace riptrm;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                               \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return fail(RIPTRM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct riptrm_handle {
+    int family = 0, n = 0, p = 0, m = 0, batch = 0, device = 0;
+    int vec_len = 0;  // n*p doubles per point
+    int num_sms = 0;
+    // problem data
+    double* dZ = nullptr;  // [batch_z][n][n]
+    bool ownZ = false;
+    int batch_z = 0;
+    double eps = 0.0;
+    bool have_problem = false;
+    // options
+    riptrm_options opts{};
+    bool have_opts = false;
+    double* d_sched = nullptr;  // 3 * (maxiter + 1)
+    int sched_len = 0;
+    // staging for RIPTRM_HOST calls
+    double *d_x0 = nullptr, *d_y0 = nullptr, *d_x = nullptr, *d_y = nullptr, *d_summary = nullptr, *d_trace = nullptr;
+    double* d_v = nullptr;      // hook operand
+    double* d_info = nullptr;   // hook info
+    size_t trace_bytes = 0;
+    int* d_counter = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
+    double last_ms = 0.0;
+};
+
+struct SphereParams {
+    const double* Z;  // device [batch_z][n][n]
+    int batch_z;
+    int n;
+    int batch;
+    double eps;
+    const double* x0;
+    const double* y0;
+    double* x;
+    double* y;
+    double* summary;
+    double* trace;
+    // hooks
+    const double* v;
+    double mu;
+    double Delta;
+    double* out;
+    double* info;
+};
+
+// Loads Z of one instance into shared memory and symmetrises it in place: S = Z + Z'
+// (Z is not symmetric: src/NonnegPCA/generator.py:25-28; Hessian of -x'Zx is -(Z+Z')).
+__device__ __forceinline__ void load_S(const double* __restrict__ Zg, double* S, int n, int pad) {
+    const int lane = lane_id();
+    const int nn = n * n;
+    if ((nn & 1) == 0) {
+        const double2* src = reinterpret_cast<const double2*>(Zg);
+        double2* dst = reinterpret_cast<double2*>(S);
+        for (int i = lane; i < nn / 2; i += 32) dst[i] = __ldg(src + i);
+    } else {
+        for (int i = lane; i < nn; i += 32) S[i] = __ldg(Zg + i);
+    }
+    for (int i = lane; i < pad; i += 32) S[nn + i] = 0.0;
+    __syncwarp();
+    for (int idx = lane; idx < nn; idx += 32) {
+        const int i = idx / n, j = idx - i * n;
+        if (i <= j) {
+            const double s = S[i * n + j] + S[j * n + i];
+            S[i * n + j] = s;
+            S[j * n + i] = s;
+        }
+    }
+    __syncwarp();
+}
+
+template <int K>
+__device__ __forceinline__ WVec<K> load_vec(const double* __restrict__ g, int len) {
+    WVec<K> r;
+    const int lane = lane_id();
+#pragma unroll
+    for (int k = 0; k < K; ++k) r.v[k] = (k * 32 + lane < len) ? g[k * 32 + lane] : 0.0;
+    return r;
+}
+template <int K>
+__device__ __forceinline__ void store_vec(double* g, const WVec<K>& r, int len) {
+    const int lane = lane_id();
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+        if (k * 32 + lane < len) g[k * 32 + lane] = r.v[k];
+}
+
+// mode 0: whole solve; 1: one Hessian-vector product; 2: one tCG solve
+template <int K, int MODE>
+__global__ void __launch_bounds__(32) sphere_kernel(SphereParams P, DevOpts o, int* counter) {
+    using F = SphereFam<K>;
+    extern __shared__ __align__(16) double smem[];
+    const int n = P.n;
+    const int pad = 32 * K;
+    typename F::Ctx ctx;
+    ctx.S = smem;
+    ctx.vbuf = smem + ((n * n + pad + 1) & ~1);
+    ctx.n = n;
+    ctx.eps = P.eps;
+    ctx.embedded = o.is_euclidean_embedded != 0;
+    const int lane = lane_id();
+    int loaded_z = -1;
+    while (true) {
+        int inst = 0;
+        if (lane == 0) inst = atomicAdd(counter, 1);
+        inst = __shfl_sync(kFull, inst, 0);
+        if (inst >= P.batch) break;
+        const int zi = (P.batch_z == 1) ? 0 : inst;
+        if (zi != loaded_z) {
+            load_S(P.Z + (size_t)zi * n * n, smem, n, pad);
+            loaded_z = zi;
+        }
+        const typename F::Vec x0 = load_vec<K>(P.x0 + (size_t)inst * n, n);
+        const typename F::CVec y0 = load_vec<K>(P.y0 + (size_t)inst * n, n);
+        if (MODE == 0) {
+            typename F::Pt pt;
+            typename F::CVec y;
+            double* tr = (P.trace != nullptr && o.trace_mode != 0)
+                             ? P.trace + (size_t)inst * o.trace_capacity * RIPTRM_TRACE_FIELDS
+                             : nullptr;
+            solve_instance<F>(ctx, o, x0, y0, pt, y, P.summary ? P.summary + (size_t)inst * RIPTRM_SUMMARY_FIELDS : nullptr,
+                              tr);
+            if (P.x) store_vec<K>(P.x + (size_t)inst * n, pt.x, n);
+            if (P.y) store_vec<K>(P.y + (size_t)inst * n, y, n);
+        } else {
+            typename F::Pt pt;
+            F::eval_point(ctx, x0, pt);
+            typename F::Step st;
+            F::begin_step(ctx, pt, y0, P.mu, st);
+            if (MODE == 1) {
+                const typename F::Vec v = load_vec<K>(P.v + (size_t)inst * n, n);
+                const typename F::Vec hv = F::Hw(ctx, pt, y0, st, v);
+                store_vec<K>(P.out + (size_t)inst * n, hv, n);
+            } else {
+                typename F::Vec eta, Heta;
+                const TcgResult r = tcg<F>(ctx, o, pt, y0, st, P.Delta, eta, Heta);
+                store_vec<K>(P.out + (size_t)inst * n, eta, n);
+                const double nrm = sqrt(F::inner(ctx, pt, eta, eta));  // warp-collective: all lanes
+                if (P.info != nullptr && lane < 4) {
+                    const double val = (lane == 0) ? (double)r.iters : (lane == 1) ? (double)r.stop : (lane == 2) ? nrm : r.model_value;
+                    P.info[(size_t)inst * 4 + lane] = val;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+extern "C" int riptrm_abi_version(void) { return RIPTRM_ABI_VERSION; }
+extern "C" const char* riptrm_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int riptrm_create(int family, int n, int p, int m, int batch, int device, riptrm_handle** out) {
+    if (out == nullptr) return fail(RIPTRM_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n <= 0 || p <= 0 || m < 0 || batch <= 0) return fail(RIPTRM_E_INVALID, "n, p, batch must be positive");
+    if (family == RIPTRM_FAMILY_NONNEGPCA_SPHERE) {
+        if (p != 1 || m != n) return fail(RIPTRM_E_INVALID, "NonnegPCA/Sphere needs p == 1 and m == n");
+        if (n > 128) return fail(RIPTRM_E_UNSUPPORTED, "Sphere family: n <= 128 (use RIPTRM_FAMILY_NONNEGPCA_COLUMNS for large n)");
+    } else {
+        return fail(RIPTRM_E_UNSUPPORTED, "family not built into this library");
+    }
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(RIPTRM_E_INVALID, "no such CUDA device");
+    CUDA_TRY(cudaSetDevice(device));
+    riptrm_handle* h = new riptrm_handle();
+    h->family = family;
+    h->n = n;
+    h->p = p;
+    h->m = m;
+    h->batch = batch;
+    h->device = device;
+    h->vec_len = n * p;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaMalloc(&h->d_counter, sizeof(int)));
+    CUDA_TRY(cudaEventCreate(&h->ev0));
+    CUDA_TRY(cudaEventCreate(&h->ev1));
+    *out = h;
+    return RIPTRM_OK;
+}
+
+static void free_dev(double*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+extern "C" int riptrm_destroy(riptrm_handle* h) {
+    if (h == nullptr) return RIPTRM_OK;
+    cudaSetDevice(h->device);
+    if (h->ownZ) free_dev(h->dZ);
+    free_dev(h->d_sched);
+    free_dev(h->d_x0);
+    free_dev(h->d_y0);
+    free_dev(h->d_x);
+    free_dev(h->d_y);
+    free_dev(h->d_summary);
+    free_dev(h->d_trace);
+    free_dev(h->d_v);
+    free_dev(h->d_info);
+    if (h->d_counter) cudaFree(h->d_counter);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+    return RIPTRM_OK;
+}
+
+extern "C" int riptrm_set_nonnegpca(riptrm_handle* h, const double* Z, int batch_z, double eps, int where) {
+    if (h == nullptr || Z == nullptr) return fail(RIPTRM_E_INVALID, "NULL argument");
+    if (h->family != RIPTRM_FAMILY_NONNEGPCA_SPHERE && h->family != RIPTRM_FAMILY_NONNEGPCA_COLUMNS)
+        return fail(RIPTRM_E_INVALID, "handle is not a NonnegPCA family");
+    if (batch_z != 1 && batch_z != h->batch) return fail(RIPTRM_E_INVALID, "batch_z must be 1 or batch");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)batch_z * h->n * h->n * sizeof(double);
+    if (h->ownZ) free_dev(h->dZ);
+    if (where == RIPTRM_DEVICE) {
+        h->dZ = const_cast<double*>(Z);
+        h->ownZ = false;
+    } else {
+        CUDA_TRY(cudaMalloc(&h->dZ, bytes));
+        h->ownZ = true;
+        CUDA_TRY(cudaMemcpy(h->dZ, Z, bytes, cudaMemcpyHostToDevice));
+    }
+    h->batch_z = batch_z;
+    h->eps = eps;
+    h->have_problem = true;
+    return RIPTRM_OK;
+}
+
+extern "C" int riptrm_set_rosenbrock(riptrm_handle*, double, double) {
+    return fail(RIPTRM_E_UNSUPPORTED, "Rosenbrock family not built into this library");
+}
+extern "C" int riptrm_set_stableid(riptrm_handle*, const double*, const double*, int, double, const double*, int, int) {
+    return fail(RIPTRM_E_UNSUPPORTED, "StableIdentification family not built into this library");
+}
+
+extern "C" int riptrm_set_options(riptrm_handle* h, const riptrm_options* o) {
+    if (h == nullptr || o == nullptr) return fail(RIPTRM_E_INVALID, "NULL argument");
+    if (o->maxiter < 0) return fail(RIPTRM_E_INVALID, "maxiter < 0");
+    if (o->mu_sched == nullptr || o->tol_lagrangian_sched == nullptr || o->tol_complementarity_sched == nullptr)
+        return fail(RIPTRM_E_INVALID, "schedules are required (length maxiter + 1)");
+    if (o->trace_mode < 0 || o->trace_mode > 2) return fail(RIPTRM_E_INVALID, "trace_mode must be 0, 1 or 2");
+    if (o->trace_mode != 0 && o->trace_capacity <= 0) return fail(RIPTRM_E_INVALID, "trace_capacity must be positive");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int len = o->maxiter + 1;
+    free_dev(h->d_sched);
+    CUDA_TRY(cudaMalloc(&h->d_sched, (size_t)3 * len * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(h->d_sched, o->mu_sched, len * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d_sched + len, o->tol_lagrangian_sched, len * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d_sched + 2 * len, o->tol_complementarity_sched, len * sizeof(double), cudaMemcpyHostToDevice));
+    h->sched_len = len;
+    h->opts = *o;
+    h->opts.mu_sched = h->opts.tol_lagrangian_sched = h->opts.tol_complementarity_sched = nullptr;
+    h->have_opts = true;
+    return RIPTRM_OK;
+}
+
+static DevOpts make_devopts(const riptrm_handle* h) {
+    const riptrm_options& s = h->opts;
+    DevOpts o;
+    o.maxiter = s.maxiter;
+    o.inner_maxiter = s.inner_maxiter;
+    o.tcg_mininner = s.tcg_mininner;
+    o.tcg_maxinner = s.tcg_maxinner;
+    o.is_euclidean_embedded = s.is_euclidean_embedded;
+    o.trace_mode = s.trace_mode;
+    o.trace_capacity = s.trace_capacity;
+    o.tolresid = s.tolresid;
+    o.maxtime = s.maxtime;
+    o.inner_maxtime = s.inner_maxtime;
+    o.initial_tr_radius = s.initial_tr_radius;
+    o.minimal_initial_tr_radius = s.minimal_initial_tr_radius;
+    o.maximal_tr_radius = s.maximal_tr_radius;
+    o.rho = s.rho;
+    o.reduction_regularization = s.reduction_regularization;
+    o.gamma = s.gamma;
+    o.const_left = s.const_left;
+    o.const_right = s.const_right;
+    o.tcg_theta = s.tcg_theta;
+    o.tcg_kappa = s.tcg_kappa;
+    o.mu = h->d_sched;
+    o.tolL = h->d_sched + h->sched_len;
+    o.tolC = h->d_sched + 2 * h->sched_len;
+    return o;
+}
+
+static int ensure(double*& p, size_t bytes) {
+    if (p != nullptr) return RIPTRM_OK;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(RIPTRM_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return RIPTRM_OK;
+}
+
+template <int K, int MODE>
+static int launch_sphere(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
+    const int n = h->n;
+    const size_t smem = (size_t)(((n * n + 32 * K + 1) & ~1) + 32 * K) * sizeof(double);
+    auto kern = sphere_kernel<K, MODE>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+    if (per_sm < 1) return fail(RIPTRM_E_UNSUPPORTED, "instance does not fit in shared memory");
+    int grid = h->num_sms * per_sm;
+    if (grid > h->batch) grid = h->batch;
+    CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
+    CUDA_TRY(cudaEventRecord(h->ev0, st));
+    kern<<<grid, 32, smem, st>>>(P, o, h->d_counter);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->ev1, st));
+    h->launches += 1;
+    return RIPTRM_OK;
+}
+
+template <int MODE>
+static int dispatch_sphere(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
+    const int n = h->n;
+    if (n <= 32) return launch_sphere<1, MODE>(h, P, o, st);
+    if (n <= 64) return launch_sphere<2, MODE>(h, P, o, st);
+    if (n <= 96) return launch_sphere<3, MODE>(h, P, o, st);
+    return launch_sphere<4, MODE>(h, P, o, st);
+}
+
+static int finish_timing(riptrm_handle* h, bool sync) {
+    if (sync) {
+        CUDA_TRY(cudaEventSynchronize(h->ev1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->last_ms = ms;
+    }
+    return RIPTRM_OK;
+}
+
+extern "C" int riptrm_solve(riptrm_handle* h, const double* x0, const double* y0, double* x, double* y,
+                            double* summary, double* trace, int where, void* stream) {
+    if (h == nullptr || x0 == nullptr || y0 == nullptr) return fail(RIPTRM_E_INVALID, "NULL argument");
+    if (!h->have_problem) return fail(RIPTRM_E_STATE, "riptrm_set_<family> has not been called");
+    if (!h->have_opts) return fail(RIPTRM_E_STATE, "riptrm_set_options has not been called");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = h->batch;
+    const size_t xb = B * h->vec_len * sizeof(double), yb = B * h->m * sizeof(double);
+    const size_t sb = B * RIPTRM_SUMMARY_FIELDS * sizeof(double);
+    const size_t tb = (h->opts.trace_mode != 0) ? B * (size_t)h->opts.trace_capacity * RIPTRM_TRACE_FIELDS * sizeof(double) : 0;
+    SphereParams P{};
+    P.Z = h->dZ;
+    P.batch_z = h->batch_z;
+    P.n = h->n;
+    P.batch = h->batch;
+    P.eps = h->eps;
+    const DevOpts o = make_devopts(h);
+    if (where == RIPTRM_DEVICE) {
+        P.x0 = x0;
+        P.y0 = y0;
+        P.x = x;
+        P.y = y;
+        P.summary = summary;
+        P.trace = trace;
+        int rc = dispatch_sphere<0>(h, P, o, st);
+        return rc;
+    }
+    int rc;
+    if ((rc = ensure(h->d_x0, xb)) || (rc = ensure(h->d_y0, yb)) || (rc = ensure(h->d_x, xb)) ||
+        (rc = ensure(h->d_y, yb)) || (rc = ensure(h->d_summary, sb)))
+        return rc;
+    if (tb != 0 && trace != nullptr) {
+        if (h->d_trace != nullptr && h->trace_bytes != tb) free_dev(h->d_trace);
+        if ((rc = ensure(h->d_trace, tb))) return rc;
+        h->trace_bytes = tb;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_x0, x0, xb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->d_y0, y0, yb, cudaMemcpyHostToDevice, st));
+    P.x0 = h->d_x0;
+    P.y0 = h->d_y0;
+    P.x = h->d_x;
+    P.y = h->d_y;
+    P.summary = h->d_summary;
+    P.trace = (tb != 0 && trace != nullptr) ? h->d_trace : nullptr;
+    if ((rc = dispatch_sphere<0>(h, P, o, st))) return rc;
+    if (x) CUDA_TRY(cudaMemcpyAsync(x, h->d_x, xb, cudaMemcpyDeviceToHost, st));
+    if (y) CUDA_TRY(cudaMemcpyAsync(y, h->d_y, yb, cudaMemcpyDeviceToHost, st));
+    if (summary) CUDA_TRY(cudaMemcpyAsync(summary, h->d_summary, sb, cudaMemcpyDeviceToHost, st));
+    if (P.trace) CUDA_TRY(cudaMemcpyAsync(trace, h->d_trace, tb, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return finish_timing(h, true);
+}
+
+static int run_hook(riptrm_handle* h, int mode, const double* x, const double* y, double mu, double Delta,
+                    const double* v, double* out, double* info, int where, cudaStream_t st) {
+    if (h == nullptr || x == nullptr || y == nullptr || out == nullptr) return fail(RIPTRM_E_INVALID, "NULL argument");
+    if (!h->have_problem) return fail(RIPTRM_E_STATE, "riptrm_set_<family> has not been called");
+    if (mode == 2 && !h->have_opts) return fail(RIPTRM_E_STATE, "riptrm_set_options has not been called");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t B = h->batch;
+    const size_t xb = B * h->vec_len * sizeof(double), yb = B * h->m * sizeof(double), ib = B * 4 * sizeof(double);
+    SphereParams P{};
+    P.Z = h->dZ;
+    P.batch_z = h->batch_z;
+    P.n = h->n;
+    P.batch = h->batch;
+    P.eps = h->eps;
+    P.mu = mu;
+    P.Delta = Delta;
+    DevOpts o{};
+    if (h->have_opts) o = make_devopts(h);
+    else { o.tcg_maxinner = -1; o.tcg_theta = 1.0; o.tcg_kappa = 0.1; o.tcg_mininner = 1; }
+    int rc;
+    if (where == RIPTRM_DEVICE) {
+        P.x0 = x; P.y0 = y; P.v = v; P.out = out; P.info = info;
+        return mode == 1 ? dispatch_sphere<1>(h, P, o, st) : dispatch_sphere<2>(h, P, o, st);
+    }
+    if ((rc = ensure(h->d_x0, xb)) || (rc = ensure(h->d_y0, yb)) || (rc = ensure(h->d_x, xb)) ||
+        (rc = ensure(h->d_v, xb)) || (rc = ensure(h->d_info, ib)))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->d_x0, x, xb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->d_y0, y, yb, cudaMemcpyHostToDevice, st));
+    if (v) CUDA_TRY(cudaMemcpyAsync(h->d_v, v, xb, cudaMemcpyHostToDevice, st));
+    P.x0 = h->d_x0; P.y0 = h->d_y0; P.v = h->d_v; P.out = h->d_x; P.info = info ? h->d_info : nullptr;
+    rc = mode == 1 ? dispatch_sphere<1>(h, P, o, st) : dispatch_sphere<2>(h, P, o, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, h->d_x, xb, cudaMemcpyDeviceToHost, st));
+    if (info) CUDA_TRY(cudaMemcpyAsync(info, h->d_info, ib, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return finish_timing(h, true);
+}
+
+extern "C" int riptrm_hessvec(riptrm_handle* h, const double* x, const double* y, double mu, const double* v,
+                              double* out, int where, void* stream) {
+    if (v == nullptr) return fail(RIPTRM_E_INVALID, "NULL argument");
+    return run_hook(h, 1, x, y, mu, 0.0, v, out, nullptr, where, (cudaStream_t)stream);
+}
+
+extern "C" int riptrm_tcg(riptrm_handle* h, const double* x, const double* y, double mu, double Delta, double* eta,
+                          double* info, int where, void* stream) {
+    return run_hook(h, 2, x, y, mu, Delta, nullptr, eta, info, where, (cudaStream_t)stream);
+}
+
+extern "C" int64_t riptrm_launch_count(const riptrm_handle* h) { return h ? h->launches : 0; }
+extern "C" double riptrm_last_kernel_ms(riptrm_handle* h) {
+    if (h == nullptr || h->launches == 0) return 0.0;
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0;
+    h->last_ms = ms;
+    return h->last_ms;
+}

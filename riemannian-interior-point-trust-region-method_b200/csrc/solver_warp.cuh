@@ -1,0 +1,468 @@
+// solver_warp.cuh -- the whole RIPTRM solve for ONE (instance, initialpoint) pair, executed by
+// ONE warp, generic over a problem family F (fam_*.cuh).  Everything the reference does per
+// solve lives here: the outer barrier loop (RIPTRM.py:909-976, :866-896), the inner
+// trust-region loop (:785-847), one trust-region iteration (:707-783), the Steihaug-Toint
+// truncated CG with its boundary-crossing tau solve (:41-216), the stopping tests (:574-629),
+// the rho test / radius update / dual clipping (:631-705), and the observers that produce the
+// reference's log row (utils.py:237-368; RIPTRM.py:980-1024).
+//
+// A family F provides (all warp-collective, every lane calls):
+//   Vec / CVec           tangent-/constraint-space vectors (WVec<K> / WVec<MK>)
+//   Ctx, Pt, Step        per-instance data, per-point cache (x, s, cost, ...), per-step cache (c, y/s, ...)
+//   eval_point, begin_step, Hw, gadj, inner, project, retract, gradL_norm, manvio, dist,
+//   cactive(ctx,k), dim(ctx), typical_dist(ctx)
+#pragma once
+#include "common.cuh"
+#include "../../include/riptrm_b200.h"
+
+namespace riptrm {
+
+struct DevOpts {
+    int maxiter, inner_maxiter, tcg_mininner, tcg_maxinner, is_euclidean_embedded, trace_mode, trace_capacity;
+    double tolresid, maxtime, inner_maxtime, initial_tr_radius, minimal_initial_tr_radius, maximal_tr_radius;
+    double rho, reduction_regularization, gamma, const_left, const_right, tcg_theta, tcg_kappa;
+    const double* mu;    // device, length maxiter + 1
+    const double* tolL;  // device
+    const double* tolC;  // device
+};
+
+struct TcgResult {
+    int iters;  // j + 1
+    int stop;   // riptrm_tcg_stop
+    double model_value;
+};
+
+// ------------------------------------------------------------------------------------------
+// Steihaug-Toint truncated CG, eta0 = 0, identity preconditioner  (RIPTRM.py:41-216)
+// ------------------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ TcgResult tcg(const typename F::Ctx& ctx, const DevOpts& o, const typename F::Pt& pt,
+                                         const typename F::CVec& y, const typename F::Step& st, double Delta,
+                                         typename F::Vec& eta, typename F::Vec& Heta) {
+    using Vec = typename F::Vec;
+    constexpr int K = F::K;
+    eta = wzero<K>();
+    Heta = wzero<K>();                                     // :47
+    Vec r = st.c;                                          // :48
+    double e_Pe = 0.0;                                     // :49
+    double r_r = F::inner(ctx, pt, r, r);                  // :56
+    const double norm_r0 = sqrt(r_r);                      // :57-58
+    double z_r = r_r;                                      // :62,:67 (z = r: identity preconditioner)
+    double d_Pd = z_r;                                     // :68
+    Vec delta;
+#pragma unroll
+    for (int k = 0; k < K; ++k) delta.v[k] = -r.v[k];      // :71
+    double e_Pd = 0.0;                                     // :73
+    double model_value = 0.0;                              // :90
+    TcgResult res;
+    res.stop = RIPTRM_TCG_MAX_INNER_ITER;                  // :95
+    const int maxinner = o.tcg_maxinner < 0 ? F::dim(ctx) : o.tcg_maxinner;
+    const double Delta2 = Delta * Delta;
+    // min(norm_r0**theta, kappa)  (:183-185); pow only when theta != 1
+    const double nr_theta = (o.tcg_theta == 1.0) ? norm_r0 : pow(norm_r0, o.tcg_theta);
+    const double target = norm_r0 * fmin(nr_theta, o.tcg_kappa);
+    int j = 0;
+    for (; j < maxinner; ++j) {                            // :98
+        Vec Hd = F::Hw(ctx, pt, y, st, delta);             // :100
+        const double d_Hd = F::inner(ctx, pt, delta, Hd);  // :103
+        double alpha = 0.0, e_Pe_new = e_Pe;
+        if (d_Hd != 0.0) {                                 // :106-114
+            alpha = z_r / d_Hd;
+            e_Pe_new = (e_Pe + (2.0 * alpha) * e_Pd) + (alpha * alpha) * d_Pd;
+        }
+        if (d_Hd <= 0.0 || e_Pe_new >= Delta2) {           // :118
+            const double tau = (-e_Pd + sqrt(e_Pd * e_Pd + d_Pd * (Delta2 - e_Pe))) / d_Pd;  // :123-125
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                eta.v[k] = eta.v[k] + tau * delta.v[k];    // :127
+                Heta.v[k] = Heta.v[k] + tau * Hd.v[k];     // :132
+            }
+            res.stop = (d_Hd <= 0.0) ? RIPTRM_TCG_NEGATIVE_CURVATURE : RIPTRM_TCG_EXCEEDED_TR;  // :142-145
+            ++j;
+            break;
+        }
+        e_Pe = e_Pe_new;                                   // :149
+        Vec new_eta, new_Heta;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            new_eta.v[k] = eta.v[k] + alpha * delta.v[k];  // :150
+            new_Heta.v[k] = Heta.v[k] + alpha * Hd.v[k];   // :154
+        }
+        const double new_model =
+            F::inner(ctx, pt, new_eta, st.c) + 0.5 * F::inner(ctx, pt, new_eta, new_Heta);  // :86-87,:162
+        if (new_model >= model_value) {                    // :163
+            res.stop = RIPTRM_TCG_MODEL_INCREASED;
+            ++j;
+            break;
+        }
+        eta = new_eta;                                     // :167-169
+        Heta = new_Heta;
+        model_value = new_model;
+#pragma unroll
+        for (int k = 0; k < K; ++k) r.v[k] = r.v[k] + alpha * Hd.v[k];  // :172
+        r_r = F::inner(ctx, pt, r, r);                     // :175
+        const double norm_r = sqrt(r_r);
+        if (j >= o.tcg_mininner && norm_r <= target) {     // :183-191
+            res.stop = (o.tcg_kappa < nr_theta) ? RIPTRM_TCG_REACHED_TARGET_LINEAR
+                                                : RIPTRM_TCG_REACHED_TARGET_SUPERLINEAR;
+            ++j;
+            break;
+        }
+        const double zold_rold = z_r;                      // :200
+        z_r = r_r;                                         // :202
+        const double beta = z_r / zold_rold;               // :205
+#pragma unroll
+        for (int k = 0; k < K; ++k) delta.v[k] = -r.v[k] + beta * delta.v[k];  // :206
+        delta = F::project(ctx, pt, delta);                // :210
+        e_Pd = beta * (e_Pd + alpha * d_Pd);               // :213
+        d_Pd = z_r + (beta * beta) * d_Pd;                 // :214
+    }
+    res.iters = j;  // j + 1 of the reference (loop index of the last executed iteration, plus one)
+    res.model_value = model_value;
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------
+// Observers: utils.evaluation / compute_residual / compute_maxmeanviolations (utils.py:237-368)
+// ------------------------------------------------------------------------------------------
+struct EvalRow {
+    double cost, distance, residual, gradnorm, compl_v, dual_v, man_v, max_v, mean_v;
+};
+
+template <class F>
+__device__ __forceinline__ EvalRow evaluate(const typename F::Ctx& ctx, const typename F::Pt& pt,
+                                            const typename F::CVec& y, const typename F::Vec& xPrev) {
+    constexpr int MK = F::MK;
+    EvalRow ev;
+    ev.cost = pt.cost;
+    ev.distance = F::dist(ctx, xPrev, pt);
+    ev.gradnorm = F::gradL_norm(ctx, pt, y);
+    double p_compl = 0.0, p_nonneg = 0.0, p_ineq = 0.0, p_sum = 0.0, p_max = 0.0;
+#pragma unroll
+    for (int k = 0; k < MK; ++k) {
+        if (F::cactive(ctx, k)) {
+            const double g = -pt.s.v[k];
+            const double cv = y.v[k] * g;
+            p_compl = p_compl + cv * cv;                    // utils.py:297-301
+            const double nv = fmax(-y.v[k], 0.0);
+            p_nonneg = p_nonneg + nv * nv;                  // :305-309
+            const double iv = fmax(g, 0.0);
+            p_ineq = p_ineq + iv * iv;                      // :313-318
+            p_sum = p_sum + iv;                             // :250-255
+            p_max = fmax(p_max, iv);
+        }
+    }
+    wsum3(p_compl, p_nonneg, p_ineq);
+    p_sum = wsum(p_sum);
+    p_max = wmax(p_max);
+    ev.compl_v = sqrt(p_compl);
+    ev.dual_v = sqrt(p_nonneg);
+    ev.man_v = F::manvio(ctx, pt);
+    ev.residual = sqrt(((((ev.gradnorm * ev.gradnorm + p_compl) + p_nonneg) + p_ineq) + 0.0) +
+                       ev.man_v * ev.man_v);                // :332-338
+    ev.max_v = p_max;
+    ev.mean_v = p_sum / (double)F::num_constraints(ctx);   // :264-265
+    return ev;
+}
+
+struct InnerInfo {
+    double num_inner, radius, dxtype, tcg_iters, normdx, minxfeasi, minyfeasi, compl_v, ared_pred, radius_update,
+        inner_status, dual_clipping;
+};
+
+__device__ __forceinline__ InnerInfo empty_info() {
+    const double nan = CUDART_NAN;
+    InnerInfo i;
+    i.num_inner = i.radius = i.dxtype = i.tcg_iters = i.normdx = i.minxfeasi = i.minyfeasi = i.compl_v = nan;
+    i.ared_pred = i.radius_update = i.inner_status = i.dual_clipping = nan;
+    return i;
+}
+
+// One coalesced 200-byte store: lane f writes field f.
+__device__ __forceinline__ void write_trace_row(double* row, int iteration, double mu, const InnerInfo& in,
+                                                double maxabs, const EvalRow& ev, double time_s) {
+    const int l = lane_id();
+    double v = 0.0;
+    switch (l) {
+        case RIPTRM_TR_ITERATION: v = (double)iteration; break;
+        case RIPTRM_TR_NUM_INNER: v = in.num_inner; break;
+        case RIPTRM_TR_MU: v = mu; break;
+        case RIPTRM_TR_RADIUS: v = in.radius; break;
+        case RIPTRM_TR_DXTYPE: v = in.dxtype; break;
+        case RIPTRM_TR_TCG_ITERS: v = in.tcg_iters; break;
+        case RIPTRM_TR_NORMDX: v = in.normdx; break;
+        case RIPTRM_TR_MINXFEASI: v = in.minxfeasi; break;
+        case RIPTRM_TR_MINYFEASI: v = in.minyfeasi; break;
+        case RIPTRM_TR_COMPL: v = in.compl_v; break;
+        case RIPTRM_TR_ARED_PRED: v = in.ared_pred; break;
+        case RIPTRM_TR_RADIUS_UPDATE: v = in.radius_update; break;
+        case RIPTRM_TR_INNER_STATUS: v = in.inner_status; break;
+        case RIPTRM_TR_DUAL_CLIPPING: v = in.dual_clipping; break;
+        case RIPTRM_TR_MAXABSLAGMULT: v = maxabs; break;
+        case RIPTRM_TR_COST: v = ev.cost; break;
+        case RIPTRM_TR_DISTANCE: v = ev.distance; break;
+        case RIPTRM_TR_RESIDUAL: v = ev.residual; break;
+        case RIPTRM_TR_GRADNORM: v = ev.gradnorm; break;
+        case RIPTRM_TR_COMPLVIOLATION: v = ev.compl_v; break;
+        case RIPTRM_TR_DUALVIOLATION: v = ev.dual_v; break;
+        case RIPTRM_TR_MANVIOLATION: v = ev.man_v; break;
+        case RIPTRM_TR_MAXVIOLATION: v = ev.max_v; break;
+        case RIPTRM_TR_MEANVIOLATION: v = ev.mean_v; break;
+        case RIPTRM_TR_TIME: v = time_s; break;
+        default: break;
+    }
+    if (l < RIPTRM_TRACE_FIELDS) row[l] = v;
+}
+
+template <class F>
+__device__ __forceinline__ double max_abs_mult(const typename F::Ctx& ctx, const typename F::CVec& y) {
+    double m = -CUDART_INF;  // RIPTRM.py:1020-1022
+#pragma unroll
+    for (int k = 0; k < F::MK; ++k)
+        if (F::cactive(ctx, k)) m = fmax(m, fabs(y.v[k]));
+    return wmax(m);
+}
+
+// ------------------------------------------------------------------------------------------
+// One trust-region iteration (RIPTRM.py:707-783).  Updates (pt, y, Delta) in place.
+// Returns true when the inner loop converged.
+// ------------------------------------------------------------------------------------------
+struct Counters {
+    double inner, tcg, aux;
+};
+
+template <class F>
+__device__ __forceinline__ bool inner_step(const typename F::Ctx& ctx, const DevOpts& o, typename F::Pt& pt,
+                                           typename F::CVec& y, double mu, double& Delta, double tolL, double tolC,
+                                           int k_inner, InnerInfo& info, Counters& cnt) {
+    using Vec = typename F::Vec;
+    using CVec = typename F::CVec;
+    constexpr int MK = F::MK;
+    info = empty_info();
+    info.num_inner = (double)k_inner;
+    info.radius = Delta;                                            // :708, :394
+
+    typename F::Step st;
+    F::begin_step(ctx, pt, y, mu, st);                              // s, grad f, c  (:724-730)
+
+    Vec dx, Hdx_unused;
+    const TcgResult tr = tcg<F>(ctx, o, pt, y, st, Delta, dx, Hdx_unused);  // :733 -> :445-452
+    cnt.tcg += (double)tr.iters;
+    info.dxtype = (double)tr.stop;
+    info.tcg_iters = (double)tr.iters;
+    const double normdx = sqrt(F::inner(ctx, pt, dx, dx));          // :735
+    info.normdx = normdx;
+
+    // dy = -y + mu * (1/s) - y * G*[dx] / s ; yNew = y + dy        (:743, :745)
+    const CVec ga = F::gadj(ctx, pt, dx);
+    CVec yNew;
+#pragma unroll
+    for (int k = 0; k < MK; ++k) {
+        if (F::cactive(ctx, k)) {
+            const double dy = (-y.v[k] + mu * (1.0 / pt.s.v[k])) - (y.v[k] * ga.v[k]) / pt.s.v[k];
+            yNew.v[k] = y.v[k] + dy;
+        } else {
+            yNew.v[k] = 0.0;
+        }
+    }
+    typename F::Pt ptN;
+    F::eval_point(ctx, F::retract(ctx, pt, dx), ptN);               // :744 (+ cost, s at xNew)
+
+    // compute_inner_stoppingcriteria (:574-629)
+    bool xfe = true, yfe = true;
+    double mins = CUDART_INF, miny = CUDART_INF, p_c = 0.0;
+#pragma unroll
+    for (int k = 0; k < MK; ++k) {
+        if (F::cactive(ctx, k)) {
+            xfe = xfe && (ptN.s.v[k] > 0.0);                        // :591
+            yfe = yfe && (yNew.v[k] > 0.0);                         // :592
+            mins = fmin(mins, ptN.s.v[k]);
+            miny = fmin(miny, yNew.v[k]);
+            const double cv = yNew.v[k] * ptN.s.v[k] - mu;          // :595
+            p_c = p_c + cv * cv;
+        }
+    }
+    xfe = wall(xfe) && F::domain_ok(ctx, ptN);
+    yfe = wall(yfe);
+    const double compl_v = sqrt(wsum(p_c));
+    const double ngl = F::gradL_norm(ctx, ptN, yNew);               // :593
+    info.minxfeasi = wmin(mins);
+    info.minyfeasi = wmin(miny);
+    info.compl_v = compl_v;
+
+    if (xfe && yfe && ngl <= tolL && compl_v <= tolC) {             // :762-766
+        info.inner_status = (double)RIPTRM_INNER_CONVERGED;
+        pt = ptN;
+        y = yNew;
+        return true;
+    }
+    if (!xfe) {                                                     // :769-775
+        info.inner_status = (double)RIPTRM_INNER_PRIMAL_INFEASIBLE;
+        Delta = o.gamma * normdx;
+        return false;
+    }
+
+    // update_xy_TR_radius (:631-705)
+    double pl_cur = 0.0, pl_new = 0.0;
+#pragma unroll
+    for (int k = 0; k < MK; ++k) {
+        if (F::cactive(ctx, k)) {
+            pl_cur = pl_cur + det_log(pt.s.v[k]);
+            pl_new = pl_new + det_log(ptN.s.v[k]);
+        }
+    }
+    wsum2(pl_cur, pl_new);
+    const double phi_cur = pt.cost - mu * pl_cur;                   // :649
+    const double phi_new = ptN.cost - mu * pl_new;
+    double ared = phi_cur - phi_new;                                // :658
+    const Vec Hdx = F::Hw(ctx, pt, y, st, dx);                      // the extra Hessian-vector of :659
+    cnt.aux += 1.0;
+    double pred = (0.0 - 0.5 * F::inner(ctx, pt, Hdx, dx)) - F::inner(ctx, pt, st.c, dx);
+    const double reg = (fmax(1.0, fabs(phi_cur)) * 2.220446049250313e-16) * o.reduction_regularization;  // :660
+    ared = ared + reg;
+    pred = pred + reg;
+    info.ared_pred = ared / pred;                                   // :666
+    double DeltaNext;
+    if (ared < 0.25 * pred) {                                       // :667-675
+        info.radius_update = (double)RIPTRM_RADIUS_REDUCED;
+        DeltaNext = 0.25 * Delta;
+    } else if (ared >= 0.75 * pred && fabs(normdx - Delta) <= 1e-15) {
+        info.radius_update = (double)RIPTRM_RADIUS_EXPANDED;
+        DeltaNext = fmin(2.0 * Delta, o.maximal_tr_radius);
+    } else {
+        info.radius_update = (double)RIPTRM_RADIUS_UNCHANGED;
+        DeltaNext = Delta;
+    }
+    if (ared > o.rho * pred) {                                      // :677
+        info.inner_status = (double)RIPTRM_INNER_SUCCESSFUL;
+        // :681-684.  np.maximum(a, b, out) quirk: I_right = max(const_right, const_right / mu)
+        const double I_right = fmax(o.const_right, o.const_right / mu);
+        bool clipped_any = false;
+#pragma unroll
+        for (int k = 0; k < MK; ++k) {
+            if (F::cactive(ctx, k)) {
+                const double I_left = o.const_left * fmin(fmin(y.v[k], mu / ptN.s.v[k]), 1.0);
+                const double cl = fmin(fmax(yNew.v[k], I_left), I_right);
+                clipped_any = clipped_any || !(cl == yNew.v[k]);
+                yNew.v[k] = cl;
+            }
+        }
+        info.dual_clipping = wany(clipped_any) ? 1.0 : 0.0;         // :685-695
+        pt = ptN;
+        y = yNew;
+    } else {
+        info.inner_status = (double)RIPTRM_INNER_UNSUCCESSFUL;      // :697-702
+    }
+    Delta = DeltaNext;
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// Whole solve: RIPTRM.run (:909-976) with outer_step (:866-896) and inner_run (:785-847)
+// ------------------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ void solve_instance(const typename F::Ctx& ctx, const DevOpts& o,
+                                               const typename F::Vec& x0, const typename F::CVec& y0,
+                                               typename F::Pt& pt, typename F::CVec& y, double* summary,
+                                               double* trace /* this instance's rows or nullptr */) {
+    using Vec = typename F::Vec;
+    using CVec = typename F::CVec;
+    F::eval_point(ctx, x0, pt);                                     // outer_preprocess (:849-864)
+    y = y0;
+    double Delta = o.initial_tr_radius > 0.0 ? o.initial_tr_radius : F::typical_dist(ctx) / 8.0;
+    Vec xPrev = pt.x;
+    InnerInfo info = empty_info();
+    Counters cnt = {0.0, 0.0, 0.0};
+    int it = 0, rows = 0, stop_reason = RIPTRM_STOP_RUNNING;
+    double mu = o.mu[0];
+    const uint64_t t_start = global_timer_ns();
+    EvalRow ev;
+    while (true) {                                                  // :931
+        ev = evaluate<F>(ctx, pt, y, xPrev);                        // :933
+        if (o.trace_mode != 0 && (it == 0 || o.trace_mode == 2)) {  // :936-941
+            if (trace != nullptr && rows < o.trace_capacity)
+                write_trace_row(trace + (size_t)rows * RIPTRM_TRACE_FIELDS, it, mu, info, max_abs_mult<F>(ctx, y), ev,
+                                (double)(global_timer_ns() - t_start) * 1e-9);
+            ++rows;
+        }
+        xPrev = pt.x;                                               // :946
+        // base_solver.check_stoppingcriterion (:85-106) + residual criterion (:942-945)
+        const double run_time = (double)(global_timer_ns() - t_start) * 1e-9;
+        if (run_time >= o.maxtime) stop_reason = RIPTRM_STOP_MAXTIME;
+        else if (it >= o.maxiter) stop_reason = RIPTRM_STOP_MAXITER;
+        if (ev.residual <= o.tolresid) stop_reason = RIPTRM_STOP_TOLRESID;
+        if (stop_reason != RIPTRM_STOP_RUNNING) break;
+        it += 1;                                                    // :959
+        // ---- outer_step (:866-896)
+        mu = o.mu[it - 1];
+        const double tolL = o.tolL[it - 1], tolC = o.tolC[it - 1];  // :881-885
+        // ---- inner_run (:785-847)
+        const typename F::Pt pt_init = pt;
+        const CVec y_init = y;
+        const double Delta_init = Delta;
+        Vec xPrevInner = pt.x;
+        const uint64_t t_inner = global_timer_ns();
+        int k = 0;
+        while (true) {
+            k += 1;                                                 // :808
+            bool done = inner_step<F>(ctx, o, pt, y, mu, Delta, tolL, tolC, k, info, cnt);  // :810
+            cnt.inner += 1.0;
+            if (o.trace_mode == 1) {                                // :812-818
+                if (trace != nullptr && rows < o.trace_capacity) {
+                    const EvalRow evi = evaluate<F>(ctx, pt, y, xPrevInner);
+                    write_trace_row(trace + (size_t)rows * RIPTRM_TRACE_FIELDS, it, mu, info,
+                                    max_abs_mult<F>(ctx, y), evi, (double)(global_timer_ns() - t_start) * 1e-9);
+                }
+                ++rows;
+            }
+            xPrevInner = pt.x;                                      // :819
+            bool rollback = false;
+            const uint64_t now = global_timer_ns();                 // :822-834
+            const double rt = (o.inner_maxtime < 0.0) ? (double)(now - t_start) * 1e-9 : (double)(now - t_inner) * 1e-9;
+            const double lim = (o.inner_maxtime < 0.0) ? o.maxtime : o.inner_maxtime;
+            if (rt >= lim) {
+                info.inner_status = (double)RIPTRM_INNER_MAX_TIME;
+                rollback = true;
+            }
+            if (o.inner_maxiter >= 0 && k >= o.inner_maxiter) {     // :835-842
+                info.inner_status = (double)RIPTRM_INNER_MAX_ITER;
+                rollback = true;
+            }
+            if (rollback) {
+                done = true;
+                pt = pt_init;
+                y = y_init;
+                Delta = Delta_init;
+            }
+            if (done) break;                                        // :844-845
+        }
+        mu = o.mu[it];                                              // :890-893 (host-evaluated schedule)
+        Delta = fmax(Delta, o.minimal_initial_tr_radius);           // :894
+    }
+    if (summary != nullptr) {
+        const int l = lane_id();
+        double v = 0.0;
+        switch (l) {
+            case RIPTRM_SM_COST: v = ev.cost; break;
+            case RIPTRM_SM_RESIDUAL: v = ev.residual; break;
+            case RIPTRM_SM_GRADNORM: v = ev.gradnorm; break;
+            case RIPTRM_SM_COMPLVIOLATION: v = ev.compl_v; break;
+            case RIPTRM_SM_DUALVIOLATION: v = ev.dual_v; break;
+            case RIPTRM_SM_MANVIOLATION: v = ev.man_v; break;
+            case RIPTRM_SM_MAXVIOLATION: v = ev.max_v; break;
+            case RIPTRM_SM_MEANVIOLATION: v = ev.mean_v; break;
+            case RIPTRM_SM_MU: v = mu; break;
+            case RIPTRM_SM_RADIUS: v = Delta; break;
+            case RIPTRM_SM_OUTER_ITERS: v = (double)it; break;
+            case RIPTRM_SM_INNER_ITERS: v = cnt.inner; break;
+            case RIPTRM_SM_TCG_ITERS: v = cnt.tcg; break;
+            case RIPTRM_SM_AUX_HESSVECS: v = cnt.aux; break;
+            case RIPTRM_SM_STOP_REASON: v = (double)stop_reason; break;
+            case RIPTRM_SM_TRACE_ROWS: v = (double)rows; break;
+            default: break;
+        }
+        if (l < RIPTRM_SUMMARY_FIELDS) summary[l] = v;
+    }
+}
+
+}  // namespace riptrm

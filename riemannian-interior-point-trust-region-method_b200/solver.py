@@ -1,0 +1,267 @@
+"""Host-side mirror of the reference's solver interface for the trust-region path.
+
+    solver = RIPTRM(option)          # same option keys/defaults as src/solver/RIPTRM.py:305-361
+    output = solver.run(problem)     # -> Output(name, x, option, log, ineqLagmult, eqLagmult)
+
+exactly what `Simulator.set_solver` / `Simulator.run` do with the reference class
+(src/base/base_simulator.py:51-67, src/NonnegPCA/simulator.py:38).  `run_batch` solves many
+(problem_instance, initialpoint) pairs of one family in one kernel launch.  All arithmetic happens
+in csrc/ (CUDA, sm_100a) behind the C ABI of include/riptrm_b200.h; this module only marshals.
+"""
+import copy
+import ctypes as C
+import math
+import warnings
+from dataclasses import dataclass, field
+from typing import Any, Dict, Optional
+
+import numpy as np
+
+from . import _lib, options as _options
+from .structure import structure_from_problem
+
+
+@dataclass
+class Output:
+    """utils.Output (src/solver/utils.py:13-16 over base_solver.BaseOutput :6-11)."""
+    name: str
+    x: Any
+    option: Optional[Dict]
+    log: Optional[Dict]
+    ineqLagmult: Any
+    eqLagmult: Any = field(default_factory=list)
+
+
+class _Handle:
+    """RAII wrapper of a riptrm_handle."""
+
+    def __init__(self, family, n, p, m, batch, device):
+        self.lib = _lib.load_library()
+        self.h = C.c_void_p()
+        _lib.check(self.lib.riptrm_create(family, n, p, m, batch, device, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.lib.riptrm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BatchSolver:
+    """A device-resident batch of same-shaped problems of one family (the C-ABI handle plus the
+    marshalling of problem data).  This is the object bench.py and the parity tests drive."""
+
+    def __init__(self, structures, device=0):
+        st0 = structures[0]
+        self.structures = structures
+        self.family = st0.family
+        self.n, self.p, self.m = st0.shape
+        self.batch = len(structures)
+        self.device = device
+        for s in structures:
+            if s.family != self.family or s.shape != st0.shape:
+                raise ValueError("a batch must hold problems of one family and one shape")
+        self.handle = _Handle(self.family, self.n, self.p, self.m, self.batch, device)
+        self.lib = self.handle.lib
+        self._keep = []
+        self._set_problem()
+        self.x0 = np.ascontiguousarray(np.stack([s.pack_x(s.x0) for s in structures]), dtype=np.float64)
+        self.y0 = np.ascontiguousarray(np.stack([np.asarray(s.y0, dtype=np.float64) for s in structures]))
+        self.option = None
+        self.trace_mode = 0
+        self.trace_capacity = 0
+
+    def _set_problem(self):
+        h, st0 = self.handle.h, self.structures[0]
+        if self.family == _lib.FAMILY_NONNEGPCA_SPHERE:
+            Zs = [s.Z for s in self.structures]
+            shared = all(z is Zs[0] for z in Zs)
+            Z = np.ascontiguousarray(Zs[0][None] if shared else np.stack(Zs), dtype=np.float64)
+            if any(s.eps != st0.eps for s in self.structures):
+                raise ValueError("one eps per batch")
+            _lib.check(self.lib.riptrm_set_nonnegpca(h, _lib.ptr(Z), Z.shape[0], float(st0.eps), _lib.HOST))
+        elif self.family == _lib.FAMILY_ROSENBROCK_GRASSMANN:
+            _lib.check(self.lib.riptrm_set_rosenbrock(h, float(st0.alpha), float(st0.offset)))
+        elif self.family == _lib.FAMILY_STABLEID_PRODUCT:
+            X = np.ascontiguousarray(st0.X, dtype=np.float64)
+            XP = np.ascontiguousarray(st0.XP, dtype=np.float64)
+            cs = np.ascontiguousarray(st0.conspec, dtype=np.float64)
+            _lib.check(self.lib.riptrm_set_stableid(h, _lib.ptr(X), _lib.ptr(XP), X.shape[1], float(st0.h),
+                                                    _lib.ptr(cs), cs.shape[0], _lib.HOST))
+        else:
+            raise NotImplementedError(f"family {self.family}")
+
+    def set_options(self, option, trace_mode=0, trace_capacity=0):
+        o, keep = _options.to_c_options(option, trace_mode, trace_capacity)
+        _lib.check(self.lib.riptrm_set_options(self.handle.h, C.byref(o)))
+        self.option, self.trace_mode, self.trace_capacity = option, trace_mode, trace_capacity
+
+    def solve(self, stream=None):
+        """Host-buffer solve: returns (x [B, n*p], y [B, m], summary [B, 16], trace [B, cap, 25] | None)."""
+        B = self.batch
+        x = np.empty((B, self.x0.shape[1]))
+        y = np.empty((B, self.m))
+        summary = np.empty((B, _lib.SUMMARY_FIELDS))
+        trace = np.empty((B, self.trace_capacity, _lib.TRACE_FIELDS)) if self.trace_mode else None
+        _lib.check(self.lib.riptrm_solve(self.handle.h, _lib.ptr(self.x0), _lib.ptr(self.y0), _lib.ptr(x),
+                                         _lib.ptr(y), _lib.ptr(summary), _lib.ptr(trace), _lib.HOST, stream))
+        return x, y, summary, trace
+
+    def hessvec(self, x, y, mu, v):
+        out = np.empty_like(self.x0)
+        _lib.check(self.lib.riptrm_hessvec(self.handle.h, _lib.ptr(np.ascontiguousarray(x)),
+                                           _lib.ptr(np.ascontiguousarray(y)), float(mu),
+                                           _lib.ptr(np.ascontiguousarray(v)), _lib.ptr(out), _lib.HOST, None))
+        return out
+
+    def tcg(self, x, y, mu, Delta):
+        eta = np.empty_like(self.x0)
+        info = np.empty((self.batch, 4))
+        _lib.check(self.lib.riptrm_tcg(self.handle.h, _lib.ptr(np.ascontiguousarray(x)),
+                                       _lib.ptr(np.ascontiguousarray(y)), float(mu), float(Delta), _lib.ptr(eta),
+                                       _lib.ptr(info), _lib.HOST, None))
+        return eta, info
+
+    @property
+    def kernel_ms(self):
+        return float(self.lib.riptrm_last_kernel_ms(self.handle.h))
+
+    @property
+    def launches(self):
+        return int(self.lib.riptrm_launch_count(self.handle.h))
+
+    def close(self):
+        self.handle.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# log reconstruction: device trace rows -> the reference's dict of lists
+# ---------------------------------------------------------------------------------------------
+_EVAL_COLS = ("cost", "distance", "residual", "gradnorm", "complviolation", "dualviolation", "manviolation",
+              "maxviolation", "meanviolation")
+
+
+def _opt(v):
+    return None if math.isnan(v) else float(v)
+
+
+def _code(v, names):
+    return None if math.isnan(v) else names[int(v)]
+
+
+def trace_to_log(rows, save_inner_iteration=True):
+    """rows: [n_rows, TRACE_FIELDS] -> dict of equal-length lists in the reference's column order
+    (base_solver.py:58-76: iteration, time, evaluation columns utils.py:356-364, solver_status
+    columns RIPTRM.py:980-1024) plus the extra column `tcg_iters`."""
+    T = _lib.TR
+    log = {"iteration": [int(r[T["iteration"]]) for r in rows], "time": [float(r[T["time"]]) for r in rows]}
+    for c in _EVAL_COLS:
+        log[c] = [float(r[T[c]]) for r in rows]
+    log["mu"] = [float(r[T["mu"]]) for r in rows]
+    log["num_inner"] = [None if math.isnan(r[T["num_inner"]]) else int(r[T["num_inner"]]) for r in rows]
+    log["inner_status"] = [_code(r[T["inner_status"]], _lib.INNER_STATUS_NAMES) for r in rows]
+    log["TR_radius"] = [_opt(r[T["TR_radius"]]) for r in rows]
+    if save_inner_iteration:
+        log["dxtype"] = [None if math.isnan(r[T["dxtype"]]) else "tCG_" + _lib.TCG_STOP_NAMES[int(r[T["dxtype"]])]
+                         for r in rows]
+        for c in ("normdx", "minxfeasi", "minyfeasi", "compl"):
+            log[c] = [_opt(r[T[c]]) for r in rows]
+        log["mineigvalHw"] = [None for _ in rows]
+        log["ared/pred"] = [_opt(r[T["ared/pred"]]) for r in rows]
+        log["radius_update"] = [_code(r[T["radius_update"]], _lib.RADIUS_UPDATE_NAMES) for r in rows]
+        log["dual_clipping"] = [None if math.isnan(r[T["dual_clipping"]]) else bool(r[T["dual_clipping"]])
+                                for r in rows]
+    log["maxabsLagmult"] = [float(r[T["maxabsLagmult"]]) for r in rows]
+    log["tcg_iters"] = [None if math.isnan(r[T["tcg_iters"]]) else int(r[T["tcg_iters"]]) for r in rows]
+    return log
+
+
+def _stop_message(summary, option, run_time):
+    """The reason strings of base_solver.py:97-104 / RIPTRM.py:944."""
+    reason = _lib.STOP_REASONS[int(summary[_lib.SM["stop_reason"]])]
+    if reason == "maxtime":
+        return f"Max time exceeded; runtime={run_time:.2f} and maxtime={option['maxtime']}"
+    if reason == "maxiter":
+        return f"Max iteration count reached; maxiter={option['maxiter']} after {run_time:.2f} seconds"
+    if reason == "tolresid":
+        res = float(summary[_lib.SM["residual"]])
+        return ("KKT residual tolerance reached; current residual=" + str(res) + " and tolresid="
+                + str(option["tolresid"]) + f" after {run_time:.2f} seconds")
+    return f"stopped ({reason}) after {run_time:.2f} seconds"
+
+
+class RIPTRM:
+    """Drop-in for the reference's `RIPTRM` class on the tCG path (src/solver/RIPTRM.py:302-976)."""
+
+    def __init__(self, option):
+        default_option = _options.default_option()
+        default_option.update(option)  # the argument wins, as in RIPTRM.py:359-361
+        self.option = default_option
+        self.excluded_time = 0
+        self.log = {}
+        self.name = f"RIPTRM_{self.option['TRS_solver']}"  # :364
+        self.device = int(self.option.get("device", 0))
+        self.last_summary = None
+        self.initialize_wandb()
+
+    # base_solver.py:36-41
+    def initialize_wandb(self):
+        if self.option["wandb_logging"]:
+            import wandb
+            wandb.finish()
+            wandb.init(project=self.option["wandb_project"], name=self.name, config=self.option)
+
+    def run(self, problem):
+        if getattr(problem, "has_eqconstraints", False):  # RIPTRM.py:911-912
+            warnings.warn("Equality constraints detecred. Currently, RIPTRM does not support equality "
+                          "constraints and will completely ignore them.", Warning)
+        out = self.run_batch([problem])[0]
+        self.log = out.log
+        return out
+
+    def run_batch(self, problems, structures=None):
+        """Solves many (instance, initialpoint) pairs of one family in one launch; returns one
+        Output per problem.  `structures` bypasses closure recognition."""
+        option = self.option
+        _options.check_supported(option)
+        if structures is None:
+            structures = [structure_from_problem(p) for p in problems]
+        save_inner = bool(option["save_inner_iteration"])
+        trace_mode = 1 if save_inner else 2
+        maxiter = int(option["maxiter"])
+        cap = (maxiter + 1) if not save_inner else min(max(64, 12 * maxiter + 64), 1 << 16)
+        bs = BatchSolver(structures, device=self.device)
+        try:
+            while True:
+                bs.set_options(option, trace_mode, cap)
+                x, y, summary, trace = bs.solve()
+                need = int(summary[:, _lib.SM["trace_rows"]].max())
+                if need <= cap:
+                    break
+                cap = need  # the solve is deterministic: rerun with room for every row
+            run_time = bs.kernel_ms * 1e-3
+        finally:
+            bs.close()
+        self.last_summary = summary
+        outs = []
+        for i, st in enumerate(structures):
+            nrows = int(summary[i, _lib.SM["trace_rows"]])
+            log = trace_to_log(trace[i, :nrows], save_inner)
+            opt = copy.copy(option)
+            opt["stoppingcriterion"] = _stop_message(summary[i], option, run_time)
+            outs.append(Output(name=self.name, x=st.unpack_x(x[i]), option=opt, log=log,
+                               ineqLagmult=np.array(y[i]), eqLagmult=[]))
+        if option["wandb_logging"]:
+            import wandb
+            for row in zip(*outs[0].log.values()):
+                wandb.log(dict(zip(outs[0].log.keys(), row)))
+            wandb.finish()
+        if option["verbosity"]:
+            for o in outs:
+                print(o.option["stoppingcriterion"])
+        return outs
