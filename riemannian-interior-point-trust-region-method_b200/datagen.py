@@ -1,0 +1,48 @@
+"""Synthetic NonnegPCA instances by the reference's generator law (src/NonnegPCA/generator.py:9-65,
+config_dataset.yaml:6-8: dim=50, snr=0.5, delta=0.7).  The reference draws from the global, unseeded
+NumPy RNG; here every instance has its own `RandomState(seed)` (seed = instance id) so sweeps are
+reproducible and shardable: rank r of a sweep generates exactly its own instances.
+
+    Z  = sqrt(snr) v v' + N/sqrt(dim), diag(N) ~ 2/sqrt(dim) * randn      (:9-31, NOT symmetrised)
+    x0 = |u / ||u|||, u ~ U(0,1)^dim                                       (:46-51)
+    y0 = 1                                                                 (:63)
+"""
+import numpy as np
+
+
+def nonnegpca_instance(dim=50, snr=0.5, delta=0.7, seed=0):
+    rs = np.random.RandomState(seed)
+    samplesize = int(np.floor(delta * dim))
+    support = rs.choice(dim, samplesize, replace=False)
+    v = np.zeros(dim)
+    v[support] = 1 / np.sqrt(samplesize)
+    Z = np.sqrt(snr) * np.outer(v, v)
+    noise = rs.randn(dim, dim) / np.sqrt(dim)
+    for ii in range(dim):
+        noise[ii, ii] = rs.randn() * 2 / np.sqrt(dim)
+    Z = Z + noise
+    x0 = rs.rand(dim)
+    x0 = np.abs(x0 / np.linalg.norm(x0))
+    return Z, x0, np.ones(dim)
+
+
+def nonnegpca_batch(first_seed, count, dim=50, snr=0.5, delta=0.7, out=None):
+    """(Z [count, dim, dim], x0 [count, dim], y0 [count, dim]) for seeds first_seed .. first_seed+count-1.
+    `out` may hold preallocated (e.g. pinned) arrays to fill."""
+    if out is None:
+        Z = np.empty((count, dim, dim))
+        x0 = np.empty((count, dim))
+        y0 = np.empty((count, dim))
+    else:
+        Z, x0, y0 = out
+    for i in range(count):
+        Z[i], x0[i], y0[i] = nonnegpca_instance(dim, snr, delta, first_seed + i)
+    return Z, x0, y0
+
+
+def more_initial_points(x0, seed, count):
+    """`count` further strictly feasible starting points for one instance (the reference ships one,
+    `initx_a`; generator.py:46-51 is the law): |u/||u|||, u ~ U(0,1)^dim."""
+    rs = np.random.RandomState(seed)
+    pts = rs.rand(count, x0.shape[0])
+    return np.abs(pts / np.linalg.norm(pts, axis=1, keepdims=True))

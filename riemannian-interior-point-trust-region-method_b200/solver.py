@@ -96,6 +96,42 @@ class BatchSolver:
         else:
             raise NotImplementedError(f"family {self.family}")
 
+    @classmethod
+    def nonnegpca_from_arrays(cls, Z, x0, y0, eps=0.0, device=0):
+        """Batch of NonnegPCA/Sphere pairs straight from arrays: Z [B or 1, n, n], x0 [B, n], y0 [B, n]
+        (host ndarrays; the sweep path of bench.py, no per-instance Python objects)."""
+        self = cls.__new__(cls)
+        Z = np.ascontiguousarray(Z, dtype=np.float64)
+        self.x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        self.y0 = np.ascontiguousarray(y0, dtype=np.float64)
+        self.structures = None
+        self.family = _lib.FAMILY_NONNEGPCA_SPHERE
+        self.batch, self.n = self.x0.shape
+        self.p, self.m = 1, self.n
+        self.device = device
+        self.handle = _Handle(self.family, self.n, 1, self.n, self.batch, device)
+        self.lib = self.handle.lib
+        self._keep = []
+        self.eps = float(eps)
+        _lib.check(self.lib.riptrm_set_nonnegpca(self.handle.h, _lib.ptr(Z), Z.shape[0], self.eps, _lib.HOST))
+        self.option, self.trace_mode, self.trace_capacity = None, 0, 0
+        return self
+
+    def set_nonnegpca(self, Z, where=_lib.HOST):
+        """(Re)binds the data matrices: a host ndarray is staged to the device, a torch CUDA tensor /
+        device address is used in place (the caller keeps it alive)."""
+        batch_z = Z.shape[0]
+        _lib.check(self.lib.riptrm_set_nonnegpca(self.handle.h, _lib.ptr(Z), int(batch_z),
+                                                 float(getattr(self, "eps", 0.0)), where))
+        self._keep = [Z]
+
+    def solve_device(self, x0, y0, x, y, summary, trace=None, stream=None):
+        """Enqueues one solve on `stream` (a cudaStream_t address) with every buffer already on the
+        device (torch CUDA tensors); returns immediately."""
+        _lib.check(self.lib.riptrm_solve(self.handle.h, _lib.ptr(x0), _lib.ptr(y0), _lib.ptr(x), _lib.ptr(y),
+                                         _lib.ptr(summary), _lib.ptr(trace), _lib.DEVICE,
+                                         C.c_void_p(stream) if stream else None))
+
     def set_options(self, option, trace_mode=0, trace_capacity=0):
         o, keep = _options.to_c_options(option, trace_mode, trace_capacity)
         _lib.check(self.lib.riptrm_set_options(self.handle.h, C.byref(o)))

@@ -1,0 +1,128 @@
+"""Host-side logic that needs no GPU: option defaults / schedules, log reconstruction from trace rows,
+the synthetic-instance generator, structure recognition of reference-style closures."""
+import math
+
+import numpy as np
+import pytest
+
+import riptrm_b200 as rb
+from riptrm_b200 import _lib, options
+
+
+def test_defaults_match_oracle_defaults():
+    from oracle.riptrm_oracle import default_option as oracle_defaults
+    d, o = options.default_option(), oracle_defaults()
+    for k, v in o.items():
+        if callable(v):
+            for mu in (0.1, 1e-6, 1e-16):
+                if k.startswith("forcing"):
+                    assert d[k](mu) == v(mu)
+        elif k not in ("TRS_solver", "second_order_stationarity"):
+            assert d[k] == v, k
+    # the reference's class defaults (RIPTRM.py:320-321): Exact_RepMat + second order; configs override to tCG
+    assert d["TRS_solver"] == "Exact_RepMat" and d["second_order_stationarity"] is True
+
+
+def test_barrier_schedule():
+    opt = options.default_option()
+    opt["maxiter"] = 30
+    mu, tolL, tolC = options.barrier_schedule(opt)
+    assert len(mu) == 31 and mu[0] == 0.1
+    m = 0.1
+    for k in range(30):
+        m = max(1e-15, 0.5 * m ** 1.01)       # RIPTRM.py:890-891
+        assert mu[k + 1] == m
+    assert tolL[0] == 0.1 and tolC[0] == 1e-4
+    assert tolL[-1] == max(mu[-1], 1e-14)
+    opt["do_simple_barrier_parameter_update"] = False
+    mu2, _, _ = options.barrier_schedule(opt)
+    assert mu2[1] == min(0.8 * 0.1, 0.5 * 0.1 ** 1.01)
+
+
+def test_unsupported_options_raise():
+    for bad in ({"TRS_solver": "Exact_RepMat", "second_order_stationarity": False},
+                {"TRS_solver": "tCG", "second_order_stationarity": True}):
+        opt = options.default_option()
+        opt.update(bad)
+        with pytest.raises(NotImplementedError):
+            options.check_supported(opt)
+
+
+def test_trace_to_log_schema():
+    nan = float("nan")
+    T = _lib.TR
+    row0 = np.full(_lib.TRACE_FIELDS, nan)
+    row0[T["iteration"]] = 0
+    row0[T["mu"]] = 0.1
+    row0[T["cost"]] = -0.5
+    row0[T["maxabsLagmult"]] = 1.0
+    row1 = np.zeros(_lib.TRACE_FIELDS)
+    row1[T["iteration"]] = 1
+    row1[T["num_inner"]] = 1
+    row1[T["dxtype"]] = 2
+    row1[T["inner_status"]] = 3
+    row1[T["radius_update"]] = 2
+    row1[T["dual_clipping"]] = 1
+    row1[T["tcg_iters"]] = 7
+    log = rb.trace_to_log(np.stack([row0, row1]))
+    # reference column order: base_solver.py:58-76, utils.py:356-364, RIPTRM.py:980-1024
+    assert list(log)[:11] == ["iteration", "time", "cost", "distance", "residual", "gradnorm", "complviolation",
+                              "dualviolation", "manviolation", "maxviolation", "meanviolation"]
+    assert log["inner_status"] == [None, "successful"]
+    assert log["dxtype"] == [None, "tCG_EXCEEDED_TR"]
+    assert log["radius_update"] == [None, "expanded"]
+    assert log["dual_clipping"] == [None, True]
+    assert log["num_inner"] == [None, 1] and log["tcg_iters"] == [None, 7]
+    assert log["mineigvalHw"] == [None, None]
+    assert len({len(v) for v in log.values()}) == 1
+
+
+def test_datagen_follows_the_oracle_generator():
+    from oracle.problems import nonnegpca_generate_instance
+    for seed in (0, 5, 4095):
+        Z, x0, y0 = rb.datagen.nonnegpca_instance(50, seed=seed)
+        Zo, xo, yo = nonnegpca_generate_instance(50, seed=seed)
+        assert np.array_equal(Z, Zo) and np.array_equal(x0, xo) and np.array_equal(y0, yo)
+        assert np.all(x0 > 0) and abs(np.linalg.norm(x0) - 1) < 1e-15
+        assert np.max(np.abs(Z - Z.T)) > 0.1      # Z is not symmetric
+    Zb, xb, yb = rb.datagen.nonnegpca_batch(3, 2, 50)
+    assert np.array_equal(Zb[1], rb.datagen.nonnegpca_instance(50, seed=4)[0])
+
+
+def test_structure_recognition_from_closures(datasets):
+    """A reference-style problem (pymanopt-like manifold object + closures over Z / idx) is recognised
+    from its closures; unknown problems raise (no CPU fallback)."""
+    d = datasets["NonnegPCA/1"]
+    Z = d["Z"]
+
+    class Sphere:  # stands for pymanopt.manifolds.Sphere (recognised by class name)
+        pass
+
+    def cost(point):
+        return -point @ Z @ point
+
+    def make(idx):
+        def ineq(point):
+            return -point[idx]
+        return ineq
+
+    class P:
+        manifold = Sphere()
+        initialpoint = d["initx_a"]
+        initialineqLagmult = d["initineqLagmult"]
+        ineqconstraints_all = [make(i) for i in range(50)]
+    P.cost = staticmethod(cost)
+    st = rb.structure_from_problem(P)
+    assert isinstance(st, rb.NonnegPCAStructure) and st.shape == (50, 1, 50) and st.Z is not None
+    assert np.array_equal(st.Z, Z)
+
+    class Q(P):
+        manifold = type("Euclidean", (), {})()
+    with pytest.raises(NotImplementedError, match="no CPU fallback"):
+        rb.structure_from_problem(Q)
+
+
+def test_stableid_conspec_expansion(datasets):
+    cs = rb.StableIdStructure.conspec_from_constset(datasets["StableIdentification/1"]["constset"])
+    assert cs.shape == (16, 5)
+    assert sorted(set(cs[:, 0])) == [0.0, 1.0, 2.0]
