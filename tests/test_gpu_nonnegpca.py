@@ -44,9 +44,13 @@ def test_reference_dataset_trace_matches_golden(rb, datasets):
     # tCG iteration counts hinge on `norm_r <= target` (RIPTRM.py:183), an ulp-level test
     first_tcg = first_discrete_mismatch(L, G, columns=DISCRETE_COLUMNS + ("tcg_iters",))
     assert outer_of(first_tcg) > 8, f"tCG counts diverge at row {first_tcg} (outer {outer_of(first_tcg)})"
-    for col in ("cost", "TR_radius", "normdx", "mu"):
-        assert max_rel_diff(L, G, col, rows=first) < REL_TOL, col
-    assert max_rel_diff(L, G, "residual", rows=first, floor=1e-10) < 1e-6
+    # until the first differing tCG count the two runs follow the same path: every float column to 1e-8
+    for col in ("cost", "TR_radius", "normdx", "mu", "minxfeasi", "minyfeasi", "maxabsLagmult"):
+        assert max_rel_diff(L, G, col, rows=first_tcg) < REL_TOL, col
+    assert max_rel_diff(L, G, "residual", rows=first_tcg, floor=1e-10) < 1e-6
+    # afterwards inner iterates may differ transiently (a tCG call stopped one iteration apart), the
+    # trust-region radii and the objective still track each other
+    assert max_rel_diff(L, G, "cost", rows=first) < 1e-6
     # per-outer-iteration cost (rows where the inner loop converged) through the whole run
     conv = lambda log: [c for c, s in zip(log["cost"], log["inner_status"]) if s == "converged"]
     a, b = np.array(conv(L)), np.array(conv(G))
