@@ -205,6 +205,9 @@ int riptrm_tcg(riptrm_handle* h, const double* x, const double* y, double mu, do
 
 /* number of kernel launches the handle has issued (for bench.py's gpu_launches) */
 int64_t riptrm_launch_count(const riptrm_handle* h);
+/* COLUMNS family: number of full S.V streaming passes (one per Hessian-vector product, plus the S.X of the
+ * point cache) the handle has executed since riptrm_set_nonnegpca -- the unit of the HBM roofline */
+int64_t riptrm_matvec_passes(riptrm_handle* h);
 /* milliseconds the last riptrm_solve / hessvec / tcg kernel took on its stream (CUDA events
  * recorded around the launch); blocks until that kernel has finished */
 double riptrm_last_kernel_ms(riptrm_handle* h);

@@ -7,11 +7,13 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/riptrm_b200.h"
+#include "fam_columns.cuh"
 #include "fam_sphere.cuh"
 
 using namespace riptrm;
@@ -56,6 +58,12 @@ struct riptrm_handle {
     double* d_info = nullptr;   // hook info
     size_t trace_bytes = 0;
     int* d_counter = nullptr;
+    // COLUMNS family workspace
+    double* dS = nullptr;        // [n_pad][ld] = Z + Z'
+    double* d_colbuf = nullptr;  // 15 arrays of n_pad x P + partials
+    unsigned long long* d_passes = nullptr;
+    int colP = 0, n_pad = 0, ld = 0, col_slots = 0, col_R = 0, col_grid = 0;
+    unsigned long long last_passes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     double last_ms = 0.0;
@@ -195,6 +203,10 @@ extern "C" int riptrm_create(int family, int n, int p, int m, int batch, int dev
     if (family == RIPTRM_FAMILY_NONNEGPCA_SPHERE) {
         if (p != 1 || m != n) return fail(RIPTRM_E_INVALID, "NonnegPCA/Sphere needs p == 1 and m == n");
         if (n > 128) return fail(RIPTRM_E_UNSUPPORTED, "Sphere family: n <= 128 (use RIPTRM_FAMILY_NONNEGPCA_COLUMNS for large n)");
+    } else if (family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS) {
+        if (batch != 1) return fail(RIPTRM_E_INVALID, "COLUMNS family: batch must be 1 (the p columns are the batch)");
+        if (m != n * p) return fail(RIPTRM_E_INVALID, "COLUMNS family needs m == n * p");
+        if (p > col::MAXP) return fail(RIPTRM_E_UNSUPPORTED, "COLUMNS family: p <= 16");
     } else {
         return fail(RIPTRM_E_UNSUPPORTED, "family not built into this library");
     }
@@ -238,11 +250,175 @@ extern "C" int riptrm_destroy(riptrm_handle* h) {
     free_dev(h->d_trace);
     free_dev(h->d_v);
     free_dev(h->d_info);
+    free_dev(h->dS);
+    free_dev(h->d_colbuf);
+    if (h->d_passes) cudaFree(h->d_passes);
     if (h->d_counter) cudaFree(h->d_counter);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
     return RIPTRM_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// COLUMNS family (fam_columns.cuh): host side
+// ------------------------------------------------------------------------------------------
+static int finish_timing(riptrm_handle* h, bool sync);
+
+static int columns_template_p(int p) {
+    const int sizes[] = {1, 2, 4, 8, 10, 16};
+    for (int s : sizes)
+        if (p <= s) return s;
+    return -1;
+}
+
+static int columns_setup(riptrm_handle* h, const double* Z, double eps, int where) {
+    const int n = h->n;
+    h->colP = columns_template_p(h->p);
+    h->n_pad = (n + col::TJ - 1) / col::TJ * col::TJ;
+    h->ld = (n + col::TW - 1) / col::TW * col::TW;
+    h->col_grid = h->num_sms;
+    const long long NIB = h->ld / col::TW, NJT = h->n_pad / col::TJ, total = NIB * NJT;
+    const long long per_cta = (total + h->col_grid - 1) / h->col_grid;
+    h->col_slots = (int)((per_cta + NJT - 2) / NJT + 1);
+    h->col_R = (n + h->col_grid - 1) / h->col_grid;
+    const size_t sbytes = (size_t)h->n_pad * h->ld * sizeof(double);
+    free_dev(h->dS);
+    free_dev(h->d_colbuf);
+    CUDA_TRY(cudaMalloc(&h->dS, sbytes));
+    CUDA_TRY(cudaMemset(h->dS, 0, sbytes));
+    const double* dZ = Z;
+    double* tmpZ = nullptr;
+    if (where != RIPTRM_DEVICE) {
+        CUDA_TRY(cudaMalloc(&tmpZ, (size_t)n * n * sizeof(double)));
+        CUDA_TRY(cudaMemcpy(tmpZ, Z, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice));
+        dZ = tmpZ;
+    }
+    dim3 grid((n + 31) / 32, (n + 31) / 32), block(32, 8);
+    col::build_S_kernel<<<grid, block>>>(dZ, h->dS, n, h->n_pad / col::TJ);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    h->launches += 1;
+    if (tmpZ) cudaFree(tmpZ);
+    const size_t arr = (size_t)h->n_pad * h->colP;
+    const size_t mv = (size_t)h->col_grid * h->col_slots * col::TW * h->colP;
+    const size_t dots = (size_t)2 * h->col_grid * col::MAXQ * col::MAXP;
+    const size_t total_d = 17 * arr + mv + dots + 4 * col::MAXP + (size_t)2 * (h->col_grid + 2);
+    CUDA_TRY(cudaMalloc(&h->d_colbuf, total_d * sizeof(double)));
+    CUDA_TRY(cudaMemset(h->d_colbuf, 0, total_d * sizeof(double)));
+    {
+        // stream-K schedule: CTA g streams tiles [tbeg[g], tbeg[g+1]) of the linearised tile order
+        std::vector<long long> tb(h->col_grid + 1);
+        std::vector<int> ib0(h->col_grid + 2, 0);
+        for (int g = 0; g <= h->col_grid; ++g) tb[g] = total * g / h->col_grid;
+        for (int g = 0; g < h->col_grid; ++g) ib0[g] = (int)(tb[g] / NJT);
+        double* tail = h->d_colbuf + 17 * arr + mv + dots + 4 * col::MAXP;
+        CUDA_TRY(cudaMemcpy(tail, tb.data(), tb.size() * sizeof(long long), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(tail + (h->col_grid + 2), ib0.data(), ib0.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (h->d_passes == nullptr) CUDA_TRY(cudaMalloc(&h->d_passes, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(h->d_passes, 0, sizeof(unsigned long long)));
+    h->eps = eps;
+    h->have_problem = true;
+    return RIPTRM_OK;
+}
+
+template <int P, int MODE>
+static int columns_launch(riptrm_handle* h, col::Params& prm, cudaStream_t st) {
+    auto kern = col::columns_kernel<P, MODE>;
+    const size_t smem = sizeof(col::Smem<P>);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, col::NT, smem));
+    if (per_sm < 1) return fail(RIPTRM_E_UNSUPPORTED, "columns kernel does not fit on an SM");
+    void* args[] = {&prm};
+    CUDA_TRY(cudaEventRecord(h->ev0, st));
+    CUDA_TRY(cudaLaunchCooperativeKernel((void*)kern, dim3(h->col_grid), dim3(col::NT), args, smem, st));
+    CUDA_TRY(cudaEventRecord(h->ev1, st));
+    h->launches += 1;
+    return RIPTRM_OK;
+}
+
+template <int MODE>
+static int columns_dispatch(riptrm_handle* h, col::Params& prm, cudaStream_t st) {
+    switch (h->colP) {
+        case 1: return columns_launch<1, MODE>(h, prm, st);
+        case 2: return columns_launch<2, MODE>(h, prm, st);
+        case 4: return columns_launch<4, MODE>(h, prm, st);
+        case 8: return columns_launch<8, MODE>(h, prm, st);
+        case 10: return columns_launch<10, MODE>(h, prm, st);
+        case 16: return columns_launch<16, MODE>(h, prm, st);
+    }
+    return fail(RIPTRM_E_UNSUPPORTED, "unsupported column count");
+}
+
+// copies a caller array [n][p] (host or device) into the padded device layout [n_pad][P]
+static int columns_import(riptrm_handle* h, double* dst, const double* src, int where, cudaStream_t st) {
+    const cudaMemcpyKind kind = (where == RIPTRM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)h->colP * sizeof(double), src, (size_t)h->p * sizeof(double),
+                               (size_t)h->p * sizeof(double), h->n, kind, st));
+    return RIPTRM_OK;
+}
+static int columns_export(riptrm_handle* h, double* dst, const double* src, int where, cudaStream_t st) {
+    const cudaMemcpyKind kind = (where == RIPTRM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)h->p * sizeof(double), src, (size_t)h->colP * sizeof(double),
+                               (size_t)h->p * sizeof(double), h->n, kind, st));
+    return RIPTRM_OK;
+}
+
+static int columns_run(riptrm_handle* h, int mode, const double* x, const double* y, double mu, double Delta,
+                       const double* v, double* out, double* info, int where, cudaStream_t st) {
+    const size_t arr = (size_t)h->n_pad * h->colP;
+    double* b = h->d_colbuf;
+    col::Params prm{};
+    prm.n = h->n;
+    prm.n_pad = h->n_pad;
+    prm.ld = h->ld;
+    prm.p = h->p;
+    prm.NIB = h->ld / col::TW;
+    prm.NJT = h->n_pad / col::TJ;
+    prm.total_tiles = (long long)prm.NIB * prm.NJT;
+    prm.R = h->col_R;
+    prm.slots = h->col_slots;
+    prm.S = h->dS;
+    prm.eps = h->eps;
+    prm.embedded = h->have_opts ? h->opts.is_euclidean_embedded : 0;
+    double** fields[] = {&prm.X, &prm.Y, &prm.Sx, &prm.ys, &prm.c, &prm.V, &prm.Sv, &prm.t, &prm.Hd, &prm.eta,
+                         &prm.Heta, &prm.r, &prm.eta2, &prm.Heta2, &prm.r2};
+    for (int i = 0; i < 15; ++i) *fields[i] = b + i * arr;
+    double* d_vin = b + 15 * arr;
+    double* d_out = b + 16 * arr;
+    prm.mv_part = b + 17 * arr;
+    prm.dot_part = prm.mv_part + (size_t)h->col_grid * h->col_slots * col::TW * h->colP;
+    double* d_info = prm.dot_part + (size_t)2 * h->col_grid * col::MAXQ * col::MAXP;
+    prm.tbeg = reinterpret_cast<const long long*>(d_info + 4 * col::MAXP);
+    prm.tib0 = reinterpret_cast<const int*>(d_info + 4 * col::MAXP + (h->col_grid + 2));
+    prm.mu = mu;
+    prm.Delta = Delta;
+    prm.vin = d_vin;
+    prm.out = d_out;
+    prm.info = d_info;
+    prm.passes = h->d_passes;
+    prm.tcg_mininner = h->have_opts ? h->opts.tcg_mininner : 1;
+    prm.tcg_maxinner = h->have_opts ? h->opts.tcg_maxinner : -1;
+    prm.tcg_theta = h->have_opts ? h->opts.tcg_theta : 1.0;
+    prm.tcg_kappa = h->have_opts ? h->opts.tcg_kappa : 0.1;
+    int rc;
+    if ((rc = columns_import(h, prm.X, x, where, st)) || (rc = columns_import(h, prm.Y, y, where, st))) return rc;
+    if (mode == 1 && (rc = columns_import(h, d_vin, v, where, st))) return rc;
+    static const bool stream_only = getenv("RIPTRM_COLUMNS_STREAM_ONLY") != nullptr;  // diagnostic, see fam_columns.cuh
+    rc = (mode == 1) ? columns_dispatch<1>(h, prm, st)
+                     : (stream_only ? columns_dispatch<3>(h, prm, st) : columns_dispatch<2>(h, prm, st));
+    if (rc) return rc;
+    if ((rc = columns_export(h, out, d_out, where, st))) return rc;
+    if (info != nullptr && mode == 2) {
+        const cudaMemcpyKind kind = (where == RIPTRM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        CUDA_TRY(cudaMemcpyAsync(info, d_info, (size_t)h->p * 4 * sizeof(double), kind, st));
+    }
+    if (where == RIPTRM_DEVICE) return RIPTRM_OK;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return finish_timing(h, true);
 }
 
 extern "C" int riptrm_set_nonnegpca(riptrm_handle* h, const double* Z, int batch_z, double eps, int where) {
@@ -251,6 +427,7 @@ extern "C" int riptrm_set_nonnegpca(riptrm_handle* h, const double* Z, int batch
         return fail(RIPTRM_E_INVALID, "handle is not a NonnegPCA family");
     if (batch_z != 1 && batch_z != h->batch) return fail(RIPTRM_E_INVALID, "batch_z must be 1 or batch");
     CUDA_TRY(cudaSetDevice(h->device));
+    if (h->family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS) return columns_setup(h, Z, eps, where);
     const size_t bytes = (size_t)batch_z * h->n * h->n * sizeof(double);
     if (h->ownZ) free_dev(h->dZ);
     if (where == RIPTRM_DEVICE) {
@@ -378,6 +555,8 @@ extern "C" int riptrm_solve(riptrm_handle* h, const double* x0, const double* y0
     if (!h->have_opts) return fail(RIPTRM_E_STATE, "riptrm_set_options has not been called");
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (h->family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS)
+        return fail(RIPTRM_E_UNSUPPORTED, "COLUMNS family: use riptrm_hessvec / riptrm_tcg (whole solve not built yet)");
     const size_t B = h->batch;
     const size_t xb = B * h->vec_len * sizeof(double), yb = B * h->m * sizeof(double);
     const size_t sb = B * RIPTRM_SUMMARY_FIELDS * sizeof(double);
@@ -431,6 +610,7 @@ static int run_hook(riptrm_handle* h, int mode, const double* x, const double* y
     if (!h->have_problem) return fail(RIPTRM_E_STATE, "riptrm_set_<family> has not been called");
     if (mode == 2 && !h->have_opts) return fail(RIPTRM_E_STATE, "riptrm_set_options has not been called");
     CUDA_TRY(cudaSetDevice(h->device));
+    if (h->family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS) return columns_run(h, mode, x, y, mu, Delta, v, out, info, where, st);
     const size_t B = h->batch;
     const size_t xb = B * h->vec_len * sizeof(double), yb = B * h->m * sizeof(double), ib = B * 4 * sizeof(double);
     SphereParams P{};
@@ -476,6 +656,12 @@ extern "C" int riptrm_tcg(riptrm_handle* h, const double* x, const double* y, do
 }
 
 extern "C" int64_t riptrm_launch_count(const riptrm_handle* h) { return h ? h->launches : 0; }
+extern "C" int64_t riptrm_matvec_passes(riptrm_handle* h) {
+    if (h == nullptr || h->d_passes == nullptr) return 0;
+    unsigned long long v = 0;
+    if (cudaMemcpy(&v, h->d_passes, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int64_t)v;
+}
 extern "C" double riptrm_last_kernel_ms(riptrm_handle* h) {
     if (h == nullptr || h->launches == 0) return 0.0;
     if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0;

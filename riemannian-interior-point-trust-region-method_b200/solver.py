@@ -175,6 +175,139 @@ class BatchSolver:
         self.handle.close()
 
 
+class ColumnsSolver:
+    """NonnegPCA with one large data matrix shared by p unit-norm columns (family COLUMNS: BASELINE
+    config 4; each column is a reference-exact Sphere problem, src/NonnegPCA/coordinator.py:37-95).
+    X, Y, V are [n, p] arrays; host ndarrays are staged, torch CUDA tensors are used in place."""
+
+    def __init__(self, Z, p, eps=0.0, device=0, option=None):
+        n = Z.shape[0]
+        self.n, self.p, self.device = n, p, device
+        self.handle = _Handle(_lib.FAMILY_NONNEGPCA_COLUMNS, n, p, n * p, 1, device)
+        self.lib = self.handle.lib
+        where = _lib.HOST if isinstance(Z, np.ndarray) else _lib.DEVICE
+        if where == _lib.HOST:
+            Z = np.ascontiguousarray(Z, dtype=np.float64)
+        _lib.check(self.lib.riptrm_set_nonnegpca(self.handle.h, _lib.ptr(Z), 1, float(eps), where))
+        if option is not None:
+            self.set_options(option)
+
+    def set_options(self, option):
+        o, keep = _options.to_c_options(option, 0, 0)
+        _lib.check(self.lib.riptrm_set_options(self.handle.h, C.byref(o)))
+
+    @staticmethod
+    def _where(*arrays):
+        host = [isinstance(a, np.ndarray) for a in arrays]
+        if all(host):
+            return _lib.HOST
+        if not any(host):
+            return _lib.DEVICE
+        raise ValueError("mix of host and device arrays")
+
+    def hessvec(self, X, Y, mu, V, out=None, stream=None):
+        """out = Hw[V] column by column at (X, Y, mu) (RIPTRM.py:729)."""
+        where = self._where(X, Y, V)
+        if where == _lib.HOST:
+            X, Y, V = (np.ascontiguousarray(a, dtype=np.float64) for a in (X, Y, V))
+            out = np.empty((self.n, self.p)) if out is None else out
+        elif out is None:
+            out = X.new_empty((self.n, self.p))
+        _lib.check(self.lib.riptrm_hessvec(self.handle.h, _lib.ptr(X), _lib.ptr(Y), float(mu), _lib.ptr(V),
+                                           _lib.ptr(out), where, C.c_void_p(stream) if stream else None))
+        return out
+
+    def tcg(self, X, Y, mu, Delta, out=None, info=None, stream=None):
+        """One Steihaug-Toint tCG solve per column, in lock-step (RIPTRM.py:41-216): returns
+        (eta [n, p], info [p, 4] = {j+1, stop reason, ||eta||, model value})."""
+        where = self._where(X, Y)
+        if where == _lib.HOST:
+            X, Y = (np.ascontiguousarray(a, dtype=np.float64) for a in (X, Y))
+            out = np.empty((self.n, self.p)) if out is None else out
+            info = np.empty((self.p, 4)) if info is None else info
+        else:
+            out = X.new_empty((self.n, self.p)) if out is None else out
+            info = X.new_empty((self.p, 4)) if info is None else info
+        _lib.check(self.lib.riptrm_tcg(self.handle.h, _lib.ptr(X), _lib.ptr(Y), float(mu), float(Delta),
+                                       _lib.ptr(out), _lib.ptr(info), where, C.c_void_p(stream) if stream else None))
+        return out, info
+
+    @property
+    def kernel_ms(self):
+        return float(self.lib.riptrm_last_kernel_ms(self.handle.h))
+
+    @property
+    def matvec_passes(self):
+        return int(self.lib.riptrm_matvec_passes(self.handle.h))
+
+    @property
+    def launches(self):
+        return int(self.lib.riptrm_launch_count(self.handle.h))
+
+    def close(self):
+        self.handle.close()
+
+
+def columns_bench(n, p, dev, peak, launches_out, tcg_iters=40, reps=3):
+    """The roofline leg of bench.py: synthetic config-4 instance (generator law of
+    src/NonnegPCA/generator.py:9-31, drawn on the device), `reps` lock-step tCG solves capped at `tcg_iters`
+    iterations, timed with the handle's CUDA events on the launch stream.  Algorithmic bytes per Hessian-
+    vector product: 8 n^2 (S streamed once) + 40 n p (X, V, Y, s read; HwV written) -- SURVEY.md section 8d."""
+    import torch
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(20000 + n)
+    snr, delta = 0.5, 0.7
+    k = int(delta * n)
+    perm = torch.randperm(n, generator=gen, device=dev)[:k]
+    v = torch.zeros(n, dtype=torch.float64, device=dev)
+    v[perm] = 1.0 / math.sqrt(k)
+    Z = torch.randn((n, n), generator=gen, dtype=torch.float64, device=dev) / math.sqrt(n)
+    Z.diagonal().copy_(torch.randn(n, generator=gen, dtype=torch.float64, device=dev) * 2 / math.sqrt(n))
+    Z.add_(math.sqrt(snr) * torch.outer(v, v))
+    X = torch.rand((n, p), generator=gen, dtype=torch.float64, device=dev)
+    X = (X / X.norm(dim=0, keepdim=True)).abs().contiguous()
+    Y = torch.ones((n, p), dtype=torch.float64, device=dev)
+    option = _options.default_option()
+    option.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=1)
+    solver = ColumnsSolver(Z, p, device=dev.index or 0, option=option)
+    del Z
+    o, keep = _options.to_c_options(option, 0, 0)
+    o.tcg_maxinner = tcg_iters   # rate protocol (SURVEY.md section 8d): a fixed number of Hessian-vector
+    o.tcg_kappa = 0.0            # products per column -- residual target 0 is never reached, the cap ends the loop
+    _lib.check(solver.lib.riptrm_set_options(solver.handle.h, C.byref(o)))
+    stream = torch.cuda.current_stream().cuda_stream
+    eta, info = solver.tcg(X, Y, 0.1, 1e6, stream=stream)   # warm-up; radius large: runs to the cap
+    torch.cuda.synchronize()
+    l0 = solver.launches
+    times, passes, iters = [], [], []
+    for _ in range(reps):
+        p0 = solver.matvec_passes
+        solver.tcg(X, Y, 0.1, 1e6, out=eta, info=info, stream=stream)
+        torch.cuda.synchronize()
+        times.append(solver.kernel_ms)
+        passes.append(solver.matvec_passes - p0)
+        iters.append(float(info[:, 0].sum()))
+    launches_out.append(solver.launches - l0)
+    # hessvec alone (2 passes: S.X for the point cache, then S.V)
+    V = torch.randn((n, p), generator=gen, dtype=torch.float64, device=dev)
+    hv = solver.hessvec(X, Y, 0.1, V, stream=stream)
+    torch.cuda.synchronize()
+    hv_ms = solver.kernel_ms
+    solver.close()
+    alg = 8.0 * n * n + 40.0 * n * p
+    ms = float(np.mean(times))
+    ach = alg * float(np.mean(passes)) / (ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak[0], "unit": "GB/s", "frac": ach / peak[0],
+                "traffic": None, "peak_source": peak[1],
+                "kernel": f"columns_kernel<{p},2> (persistent lock-step tCG, n={n}, p={p}): "
+                          f"{np.mean(passes):.0f} S.V passes per launch, {alg:.4g} algorithmic bytes per pass"}
+    extra = {"n": n, "p": p, "tcg_launch_ms": ms, "matvec_passes_per_launch": float(np.mean(passes)),
+             "ms_per_hessvec": ms / float(np.mean(passes)), "hessvec_hbm_gbs": ach,
+             "column_tcg_iters_per_sec": float(np.mean(iters)) / (ms * 1e-3),
+             "hessvec_hook_ms": hv_ms, "finite": bool(torch.isfinite(hv).all())}
+    return roofline, extra
+
+
 # ---------------------------------------------------------------------------------------------
 # log reconstruction (SURVEY.md App. E): device trace rows -> the reference's dict of lists
 # ---------------------------------------------------------------------------------------------

@@ -1,0 +1,96 @@
+"""GPU parity of the large-n COLUMNS family (BASELINE config 4 at sizes the oracle finishes in seconds):
+the cooperative stream-K Hessian-vector kernel and the lock-step tCG against the per-column Sphere oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import riptrm_b200
+    return riptrm_b200
+
+
+def _instance(n, p, seed):
+    from oracle.problems import nonnegpca_generate_Z
+    Z, rs = nonnegpca_generate_Z(n, seed=seed)
+    X = rs.rand(n, p)
+    X = np.abs(X / np.linalg.norm(X, axis=0, keepdims=True))
+    Y = 0.5 + rs.rand(n, p)
+    return Z, X, Y, rs
+
+
+def _closed_form_hw(Z, x, y, mu, v):
+    """Hw[v] of SURVEY.md App. A.1 in NumPy (validated against the per-constraint oracle in test_oracle_*)."""
+    S = Z + Z.T
+    P = lambda u: u - (x @ u) * x
+    return P(-S @ v) + (x @ S @ x + y @ x) * v + P((y / x) * (v - x * (x @ v)))
+
+
+@pytest.mark.parametrize("n,p", [(96, 1), (500, 4), (1000, 10), (777, 3)])
+def test_hessvec_matches_closed_form_and_oracle(rb, n, p):
+    from oracle import riptrm_oracle as O
+    from oracle.problems import NonnegPCAProblem
+    Z, X, Y, rs = _instance(n, p, seed=n + p)
+    V = rs.randn(n, p)
+    V -= X * np.sum(X * V, axis=0, keepdims=True)
+    cs = rb.ColumnsSolver(Z, p)
+    out = cs.hessvec(X, Y, 0.05, V)
+    assert cs.matvec_passes == 2
+    for c in range(p):
+        ref = _closed_form_hw(Z, X[:, c], Y[:, c], 0.05, V[:, c])
+        assert np.max(np.abs(out[:, c] - ref)) < 1e-10 * max(1.0, np.max(np.abs(ref)))
+    if n <= 100:  # the per-constraint oracle costs O(n^2) Python calls per product
+        Pb = NonnegPCAProblem(Z, X[:, 0], Y[:, 0])
+        x, y = X[:, 0], Y[:, 0]
+        s = O.slack(Pb, x)
+        ref = O.hess_lagrangian(Pb, x, y, V[:, 0]) + O.G_apply(Pb, x, (y * O.Gadj_apply(Pb, x, V[:, 0])) / s)
+        assert np.max(np.abs(out[:, 0] - ref)) < 1e-10 * max(1.0, np.max(np.abs(ref)))
+    cs.close()
+
+
+@pytest.mark.parametrize("n,p,Delta", [(300, 4, 0.3), (300, 4, 5.0), (1000, 10, 0.05), (641, 2, 1.0)])
+def test_lockstep_tcg_matches_oracle_tcg(rb, n, p, Delta):
+    """Each column's tCG (iteration count, stop reason, eta) equals the oracle's Steihaug-Toint tCG
+    (RIPTRM.py:41-216) run on that column with the closed-form operator."""
+    from oracle import riptrm_oracle as O
+    from oracle.manifolds import Sphere
+    Z, X, Y, rs = _instance(n, p, seed=3 * n + p)
+    mu = 0.1
+    opt = rb.options.default_option()
+    opt.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=1)
+    cs = rb.ColumnsSolver(Z, p, option=opt)
+    eta, info = cs.tcg(X, Y, mu, Delta)
+    S = Z + Z.T
+    man = Sphere(n)
+    for c in range(p):
+        x, y = X[:, c], Y[:, c]
+        Pj = lambda u: u - (x @ u) * x
+        grad = Pj(-S @ x) - Pj(mu / x)
+        e_ref, _, j, stop = O.steihaug_tcg(man, lambda _x, v: _closed_form_hw(Z, x, y, mu, v), x, grad, Delta, 1, 0.1, 1,
+                                           man.dim, lambda _x, v: v)
+        assert int(info[c, 0]) == j + 1, (c, info[c], j + 1, stop)
+        assert O.TCG_STOPS[int(info[c, 1])] == stop
+        assert np.max(np.abs(eta[:, c] - e_ref)) < 1e-8 * max(1e-3, np.max(np.abs(e_ref)))
+        assert abs(info[c, 2] - np.linalg.norm(e_ref)) < 1e-8 * max(1e-3, np.linalg.norm(e_ref))
+        assert abs(x @ eta[:, c]) < 1e-10
+    cs.close()
+
+
+def test_streaming_pass_is_linear_and_symmetric(rb):
+    """Size-independent properties at a larger n: Hw is linear in V and self-adjoint on the tangent space."""
+    n, p = 4096, 10
+    Z, X, Y, rs = _instance(n, p, seed=11)
+    cs = rb.ColumnsSolver(Z, p)
+    proj = lambda V: V - X * np.sum(X * V, axis=0, keepdims=True)
+    U, V = proj(rs.randn(n, p)), proj(rs.randn(n, p))
+    HU, HV = cs.hessvec(X, Y, 0.01, U), cs.hessvec(X, Y, 0.01, V)
+    HUV = cs.hessvec(X, Y, 0.01, U + 2.0 * V)
+    scale = np.max(np.abs(HUV))
+    assert np.max(np.abs(HUV - (HU + 2.0 * HV))) < 1e-11 * scale
+    uhv, vhu = np.sum(U * HV, axis=0), np.sum(V * HU, axis=0)
+    assert np.max(np.abs(uhv - vhu)) < 1e-9 * np.max(np.abs(uhv))
+    # determinism: same bits run to run
+    assert np.array_equal(cs.hessvec(X, Y, 0.01, U), HU)
+    cs.close()
