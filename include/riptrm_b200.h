@@ -106,7 +106,10 @@ typedef struct {
     int32_t trace_mode;                 /* 0 none; 1 one row per inner iteration ('save_inner_iteration'=True);
                                            2 one row per outer iteration (False) */
     int32_t trace_capacity;             /* rows per instance, incl. row 0 */
-    int32_t reserved0;
+    int32_t schedule_split;             /* not a reference key.  Batches larger than the GPU's resident capacity are solved
+                                           in two launches: `schedule_split` outer iterations of every pair, then the
+                                           remainder with the pairs sorted by work so far (longest first).  Results are
+                                           bit-identical either way.  0 = automatic, < 0 = single launch */
     double tolresid;                    /* 'tolresid' */
     double maxtime;                     /* 'maxtime' seconds, measured on the device clock */
     double inner_maxtime;               /* 'inner_maxtime'; < 0 == None */

@@ -13,7 +13,8 @@
  *
  * What "deterministic" means here: every floating-point operation, its order and its fused-multiply-add
  * policy are specified (DESIGN.md "Arithmetic specification"): a vector of n <= 128 doubles is laid out on
- * 32 lanes, element e = k*32 + lane; a dot product is a per-lane fma chain over k followed by a halving tree
+ * 32 lanes in pairs, lane l owning the elements e(l,k) = 64*(k>>1) + 2*l + (k&1), k < K (K = 2 for n <= 64,
+ * else 4); a dot product is a per-lane fma chain over k followed by a halving tree
  * over lanes (what an xor-butterfly of warp shuffles computes); S.v accumulates even and odd rows in two
  * chains per element; elementwise expressions are evaluated without contraction (compile with
  * -ffp-contract=off).  The CUDA kernels implement the same specification, which is what allows bit-for-bit
@@ -30,6 +31,7 @@
 #define LANES 32
 #define MAXK 4
 #define MAXN (LANES * MAXK)
+#define ELEM(l, k) (64 * ((k) >> 1) + 2 * (l) + ((k) & 1))
 
 #define TRACE_FIELDS 25
 #define SUMMARY_FIELDS 16
@@ -77,8 +79,8 @@ static double lane_tree(double* p) {
 static double vdot(const Ctx* c, const double* a, const double* b) {
     double p[LANES];
     for (int l = 0; l < LANES; ++l) {
-        double q = a[l] * b[l];
-        for (int k = 1; k < c->K; ++k) q = fma(a[k * LANES + l], b[k * LANES + l], q);
+        double q = a[ELEM(l, 0)] * b[ELEM(l, 0)];
+        for (int k = 1; k < c->K; ++k) q = fma(a[ELEM(l, k)], b[ELEM(l, k)], q);
         p[l] = q;
     }
     return lane_tree(p);
@@ -322,7 +324,7 @@ static EvalRow evaluate(const Ctx* c, const Pt* pt, const double* y, const doubl
     for (int l = 0; l < LANES; ++l) {
         double a = 0.0, b = 0.0, d = 0.0, s = 0.0;
         for (int k = 0; k < c->K; ++k) {
-            const int e = k * LANES + l;
+            const int e = ELEM(l, k);
             if (e < c->n) {
                 const double g = -pt->s[e];
                 const double cv = y[e] * g;
@@ -408,7 +410,7 @@ typedef struct {
         for (int l = 0; l < LANES; ++l) {                         \
             double _a = 0.0;                                      \
             for (int k = 0; k < c->K; ++k) {                      \
-                const int e = k * LANES + l;                      \
+                const int e = ELEM(l, k);                      \
                 if (e < c->n) _a = _a + (EXPR_ACTIVE);            \
             }                                                     \
             _p[l] = _a;                                           \
@@ -522,7 +524,7 @@ int riptrm_det_solve_nonnegpca(int n, const double* Z, const double* x0, const d
     Ctx ctx;
     Ctx* c = &ctx;
     c->n = n;
-    c->K = (n + LANES - 1) / LANES;
+    c->K = (n <= 64) ? 2 : 4;
     c->eps = eps;
     c->embedded = o->is_euclidean_embedded != 0;
     for (int i = 0; i < n; ++i)
@@ -624,7 +626,7 @@ int riptrm_det_hessvec(int n, const double* Z, const double* x, const double* y,
     static Ctx ctx; /* not reentrant: hooks are single-threaded test helpers */
     Ctx* c = &ctx;
     c->n = n;
-    c->K = (n + LANES - 1) / LANES;
+    c->K = (n <= 64) ? 2 : 4;
     c->eps = eps;
     c->embedded = 0;
     for (int i = 0; i < n; ++i)

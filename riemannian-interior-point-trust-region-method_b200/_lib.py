@@ -38,7 +38,7 @@ class RiptrmOptions(C.Structure):
     _fields_ = [
         ("maxiter", C.c_int32), ("inner_maxiter", C.c_int32), ("tcg_mininner", C.c_int32),
         ("tcg_maxinner", C.c_int32), ("is_euclidean_embedded", C.c_int32), ("trace_mode", C.c_int32),
-        ("trace_capacity", C.c_int32), ("reserved0", C.c_int32),
+        ("trace_capacity", C.c_int32), ("schedule_split", C.c_int32),
         ("tolresid", C.c_double), ("maxtime", C.c_double), ("inner_maxtime", C.c_double),
         ("initial_tr_radius", C.c_double), ("minimal_initial_tr_radius", C.c_double),
         ("maximal_tr_radius", C.c_double), ("rho", C.c_double), ("reduction_regularization", C.c_double),

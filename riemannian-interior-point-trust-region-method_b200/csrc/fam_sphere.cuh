@@ -2,7 +2,7 @@
 // (src/NonnegPCA/coordinator.py:37-95; closed forms SURVEY.md App. A.1).
 //
 // One warp owns one instance.  S = Z + Z' (n x n, symmetric) sits in shared memory for the
-// whole solve; vectors are WVec<K> (element e = k*32 + lane), n <= 32*K.
+// whole solve; vectors are WVec<K> in the pair layout described below, n <= 32*K.
 //
 //   grad f      = P_x(-Sx),   P_x u = u - <x,u> x        (pymanopt Sphere.projection)
 //   Hess L[v]   = P_x(-Sv) + (x'Sx) v + (y'x) v           (RIPTRM.py:491-523 + Sphere.ehess2rhess)
@@ -14,17 +14,22 @@
 
 namespace riptrm {
 
+// Vector layout ("pair layout"): lane l owns the adjacent elements e = 64*(k>>1) + 2*l + (k&1), k = 0..K-1,
+// so one LDS.128 per lane fetches a lane's two entries of a row of S (shared-memory instruction issue, one
+// warp-wide load per 4 cycles per scheduler, is what bounds a single warp's S.v: 2x fewer instructions than
+// LDS.64 with the lane-strided layout; measured with scripts/microbench.cu).  K = 2 for n <= 64, 4 for n <= 128.
 template <int K_>
 struct SphereFam {
     static constexpr int K = K_;
     static constexpr int MK = K_;
+    static_assert(K_ == 2 || K_ == 4, "pair layout: K is 2 or 4");
     using Vec = WVec<K>;
     using CVec = WVec<K>;
 
     struct Ctx {
-        const double* S;  // shared memory, row-major n x n (+ tail padding), symmetric
+        const double* S;  // shared memory, row-major n x ns (ns = n rounded up to even, + tail padding), symmetric
         double* vbuf;     // shared memory, 32*K doubles, staging for the broadcast operand
-        int n;
+        int n, ns;
         double eps;
         bool embedded;    // 'is_euclidean_embedded'
     };
@@ -41,41 +46,51 @@ struct SphereFam {
         double kappa;  // x'Sx + y'x
     };
 
-    static __device__ __forceinline__ bool active(const Ctx& c, int k) { return k * 32 + lane_id() < c.n; }
+    static __device__ __forceinline__ int elem(int k) { return 64 * (k >> 1) + 2 * lane_id() + (k & 1); }
+    static __device__ __forceinline__ bool active(const Ctx& c, int k) { return elem(k) < c.n; }
     static __device__ __forceinline__ bool cactive(const Ctx& c, int k) { return active(c, k); }
     static __device__ __forceinline__ int dim(const Ctx& c) { return c.n - 1; }
     static __device__ __forceinline__ int num_constraints(const Ctx& c) { return c.n; }
     static __device__ __forceinline__ double typical_dist(const Ctx&) { return 3.141592653589793; }
     static __device__ __forceinline__ bool domain_ok(const Ctx&, const Pt&) { return true; }
 
-    // out = S v.  S symmetric, so (S v)_e = sum_j S[j][e] v_j: lane-contiguous (conflict-free)
-    // reads of row j, v_j broadcast from shared memory.  Two accumulators per element
-    // (even j / odd j) halve the dependent-FMA chain; their sum order is part of the spec.
+    // out = S v.  S symmetric, so (S v)_e = sum_j S[j][e] v_j: lane-contiguous (conflict-free) 16-byte reads of
+    // row j, v_j broadcast from shared memory.  Two accumulators per element (even j / odd j) halve the
+    // dependent-FMA chain; their sum order is part of the arithmetic specification.
     static __device__ __forceinline__ Vec matvec(const Ctx& c, const Vec& v) {
         const int lane = lane_id();
         const int n = c.n;
+        double2* vb2 = reinterpret_cast<double2*>(c.vbuf);
 #pragma unroll
-        for (int k = 0; k < K; ++k)
-            if (active(c, k)) c.vbuf[k * 32 + lane] = v.v[k];
+        for (int q = 0; q < K / 2; ++q) vb2[32 * q + lane] = make_double2(v.v[2 * q], v.v[2 * q + 1]);
         __syncwarp();
         double a0[K], a1[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) a0[k] = a1[k] = 0.0;
-        const double* row = c.S + lane;
+        const int ns2 = c.ns >> 1;
+        const double2* row = reinterpret_cast<const double2*>(c.S) + lane;
         int j = 0;
+#pragma unroll 5
         for (; j + 1 < n; j += 2) {
             const double2 vj = *reinterpret_cast<const double2*>(c.vbuf + j);
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                a0[k] = fma(row[k * 32], vj.x, a0[k]);
-                a1[k] = fma(row[n + k * 32], vj.y, a1[k]);
+            for (int q = 0; q < K / 2; ++q) {
+                const double2 s0 = row[32 * q], s1 = row[ns2 + 32 * q];
+                a0[2 * q] = fma(s0.x, vj.x, a0[2 * q]);
+                a0[2 * q + 1] = fma(s0.y, vj.x, a0[2 * q + 1]);
+                a1[2 * q] = fma(s1.x, vj.y, a1[2 * q]);
+                a1[2 * q + 1] = fma(s1.y, vj.y, a1[2 * q + 1]);
             }
-            row += 2 * n;
+            row += 2 * ns2;
         }
         if (j < n) {
             const double vj = c.vbuf[j];
 #pragma unroll
-            for (int k = 0; k < K; ++k) a0[k] = fma(row[k * 32], vj, a0[k]);
+            for (int q = 0; q < K / 2; ++q) {
+                const double2 s0 = row[32 * q];
+                a0[2 * q] = fma(s0.x, vj, a0[2 * q]);
+                a0[2 * q + 1] = fma(s0.y, vj, a0[2 * q + 1]);
+            }
         }
         __syncwarp();
         Vec out;
@@ -93,6 +108,10 @@ struct SphereFam {
         for (int k = 0; k < K; ++k) pt.s.v[k] = active(c, k) ? (x.v[k] + c.eps) : 0.0;
     }
 
+    // per-lane partial of <a, b>_x (the Sphere metric is the Euclidean one); wsum() of it is the inner product
+    static __device__ __forceinline__ double inner_partial(const Ctx&, const Pt&, const Vec& a, const Vec& b) {
+        return wdot_partial(a, b);
+    }
     static __device__ __forceinline__ double inner(const Ctx&, const Pt&, const Vec& a, const Vec& b) {
         return wdot(a, b);
     }
@@ -163,14 +182,19 @@ struct SphereFam {
         return a;
     }
 
-    // || grad f(x) + sum_i y_i grad g_i(x) ||, grad g_i = -P_x(e_i)
-    static __device__ __forceinline__ double gradL_norm(const Ctx&, const Pt& pt, const CVec& y) {
-        const double xy = wdot(pt.x, y);
+    // grad f(x) + sum_i y_i grad g_i(x), grad g_i = -P_x(e_i); `xy` = <x, y>
+    static __device__ __forceinline__ double gradL_xy_partial(const Ctx&, const Pt& pt, const CVec& y) {
+        return wdot_partial(pt.x, y);
+    }
+    static __device__ __forceinline__ double gradL_norm_given(const Ctx&, const Pt& pt, const CVec& y, double xy) {
         Vec g;
 #pragma unroll
         for (int k = 0; k < K; ++k)
             g.v[k] = (-pt.Sx.v[k] + pt.xSx * pt.x.v[k]) - (y.v[k] - xy * pt.x.v[k]);
         return sqrt(wdot(g, g));
+    }
+    static __device__ __forceinline__ double gradL_norm(const Ctx& c, const Pt& pt, const CVec& y) {
+        return gradL_norm_given(c, pt, y, wsum(gradL_xy_partial(c, pt, y)));
     }
 
     static __device__ __forceinline__ double manvio(const Ctx&, const Pt& pt) {

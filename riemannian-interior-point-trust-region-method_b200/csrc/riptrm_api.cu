@@ -6,10 +6,13 @@
 // There is no inter-warp synchronisation anywhere on the solve path.
 #include <cuda_runtime.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/riptrm_b200.h"
@@ -58,6 +61,12 @@ struct riptrm_handle {
     double* d_info = nullptr;   // hook info
     size_t trace_bytes = 0;
     int* d_counter = nullptr;
+    // two-launch schedule of the batched families (longest pairs first in the second launch)
+    double* d_pause = nullptr;   // [batch][kPauseFields]
+    float *d_keys = nullptr, *d_keys_sorted = nullptr;
+    int *d_idx = nullptr, *d_order = nullptr;
+    void* d_sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
     // COLUMNS family workspace
     double* dS = nullptr;        // [n_pad][ld] = Z + Z'
     double* d_colbuf = nullptr;  // 15 arrays of n_pad x P + partials
@@ -81,6 +90,11 @@ struct SphereParams {
     double* y;
     double* summary;
     double* trace;
+    // two-launch schedule
+    const int* order;  // slot -> pair (second launch) or nullptr
+    double* pause;     // [batch][kPauseFields] or nullptr
+    int resume;        // second launch: continue the paused pairs from (x, y, pause)
+    int pause_at;      // first launch: outer iteration to pause at (< 0: run to the end)
     // hooks
     const double* v;
     double mu;
@@ -91,56 +105,61 @@ struct SphereParams {
 
 // Loads Z of one instance into shared memory and symmetrises it in place: S = Z + Z'
 // (Z is not symmetric: src/NonnegPCA/generator.py:25-28; Hessian of -x'Zx is -(Z+Z')).
-__device__ __forceinline__ void load_S(const double* __restrict__ Zg, double* S, int n, int pad) {
+__device__ __forceinline__ void load_S(const double* __restrict__ Zg, double* S, int n, int ns, int pad) {
     const int lane = lane_id();
     const int nn = n * n;
-    if ((nn & 1) == 0) {
-        const double2* src = reinterpret_cast<const double2*>(Zg);
-        double2* dst = reinterpret_cast<double2*>(S);
-        for (int i = lane; i < nn / 2; i += 32) dst[i] = __ldg(src + i);
-    } else {
-        for (int i = lane; i < nn; i += 32) S[i] = __ldg(Zg + i);
+    for (int idx = lane; idx < nn; idx += 32) {
+        const int i = idx / n, j = idx - i * n;
+        S[i * ns + j] = __ldg(Zg + idx);
     }
-    for (int i = lane; i < pad; i += 32) S[nn + i] = 0.0;
+    if (ns != n)
+        for (int i = lane; i < n; i += 32) S[i * ns + n] = 0.0;
+    for (int i = lane; i < pad; i += 32) S[n * ns + i] = 0.0;
     __syncwarp();
     for (int idx = lane; idx < nn; idx += 32) {
         const int i = idx / n, j = idx - i * n;
         if (i <= j) {
-            const double s = S[i * n + j] + S[j * n + i];
-            S[i * n + j] = s;
-            S[j * n + i] = s;
+            const double s = S[i * ns + j] + S[j * ns + i];
+            S[i * ns + j] = s;
+            S[j * ns + i] = s;
         }
     }
     __syncwarp();
 }
 
+// global [len] <-> pair layout (element 64*(k>>1) + 2*lane + (k&1))
 template <int K>
 __device__ __forceinline__ WVec<K> load_vec(const double* __restrict__ g, int len) {
     WVec<K> r;
-    const int lane = lane_id();
 #pragma unroll
-    for (int k = 0; k < K; ++k) r.v[k] = (k * 32 + lane < len) ? g[k * 32 + lane] : 0.0;
+    for (int k = 0; k < K; ++k) {
+        const int e = SphereFam<K>::elem(k);
+        r.v[k] = (e < len) ? g[e] : 0.0;
+    }
     return r;
 }
 template <int K>
 __device__ __forceinline__ void store_vec(double* g, const WVec<K>& r, int len) {
-    const int lane = lane_id();
 #pragma unroll
-    for (int k = 0; k < K; ++k)
-        if (k * 32 + lane < len) g[k * 32 + lane] = r.v[k];
+    for (int k = 0; k < K; ++k) {
+        const int e = SphereFam<K>::elem(k);
+        if (e < len) g[e] = r.v[k];
+    }
 }
 
 // mode 0: whole solve; 1: one Hessian-vector product; 2: one tCG solve
 template <int K, int MODE>
-__global__ void __launch_bounds__(32) sphere_kernel(SphereParams P, DevOpts o, int* counter) {
+__global__ void __launch_bounds__(32, (K == 2) ? 8 : 4) sphere_kernel(SphereParams P, DevOpts o, int* counter) {
     using F = SphereFam<K>;
     extern __shared__ __align__(16) double smem[];
     const int n = P.n;
+    const int ns = (n + 1) & ~1;
     const int pad = 32 * K;
     typename F::Ctx ctx;
     ctx.S = smem;
-    ctx.vbuf = smem + ((n * n + pad + 1) & ~1);
+    ctx.vbuf = smem + n * ns + pad;
     ctx.n = n;
+    ctx.ns = ns;
     ctx.eps = P.eps;
     ctx.embedded = o.is_euclidean_embedded != 0;
     const int lane = lane_id();
@@ -150,13 +169,17 @@ __global__ void __launch_bounds__(32) sphere_kernel(SphereParams P, DevOpts o, i
         if (lane == 0) inst = atomicAdd(counter, 1);
         inst = __shfl_sync(kFull, inst, 0);
         if (inst >= P.batch) break;
+        if (P.order != nullptr) inst = P.order[inst];
+        double* pause = (P.pause != nullptr) ? P.pause + (size_t)inst * kPauseFields : nullptr;
+        if (MODE == 0 && P.resume && pause[7] == 0.0) continue;  // finished in the first launch
         const int zi = (P.batch_z == 1) ? 0 : inst;
         if (zi != loaded_z) {
-            load_S(P.Z + (size_t)zi * n * n, smem, n, pad);
+            load_S(P.Z + (size_t)zi * n * n, smem, n, ns, pad);
             loaded_z = zi;
         }
-        const typename F::Vec x0 = load_vec<K>(P.x0 + (size_t)inst * n, n);
-        const typename F::CVec y0 = load_vec<K>(P.y0 + (size_t)inst * n, n);
+        const bool resume = (MODE == 0) && P.resume;
+        const typename F::Vec x0 = load_vec<K>((resume ? P.x : P.x0) + (size_t)inst * n, n);
+        const typename F::CVec y0 = load_vec<K>((resume ? P.y : P.y0) + (size_t)inst * n, n);
         if (MODE == 0) {
             typename F::Pt pt;
             typename F::CVec y;
@@ -164,7 +187,7 @@ __global__ void __launch_bounds__(32) sphere_kernel(SphereParams P, DevOpts o, i
                              ? P.trace + (size_t)inst * o.trace_capacity * RIPTRM_TRACE_FIELDS
                              : nullptr;
             solve_instance<F>(ctx, o, x0, y0, pt, y, P.summary ? P.summary + (size_t)inst * RIPTRM_SUMMARY_FIELDS : nullptr,
-                              tr);
+                              tr, pause, resume, P.pause_at);
             if (P.x) store_vec<K>(P.x + (size_t)inst * n, pt.x, n);
             if (P.y) store_vec<K>(P.y + (size_t)inst * n, y, n);
         } else {
@@ -252,6 +275,12 @@ extern "C" int riptrm_destroy(riptrm_handle* h) {
     free_dev(h->d_info);
     free_dev(h->dS);
     free_dev(h->d_colbuf);
+    free_dev(h->d_pause);
+    if (h->d_keys) cudaFree(h->d_keys);
+    if (h->d_keys_sorted) cudaFree(h->d_keys_sorted);
+    if (h->d_idx) cudaFree(h->d_idx);
+    if (h->d_order) cudaFree(h->d_order);
+    if (h->d_sort_tmp) cudaFree(h->d_sort_tmp);
     if (h->d_passes) cudaFree(h->d_passes);
     if (h->d_counter) cudaFree(h->d_counter);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -286,6 +315,12 @@ static int columns_setup(riptrm_handle* h, const double* Z, double eps, int wher
     const size_t sbytes = (size_t)h->n_pad * h->ld * sizeof(double);
     free_dev(h->dS);
     free_dev(h->d_colbuf);
+    free_dev(h->d_pause);
+    if (h->d_keys) cudaFree(h->d_keys);
+    if (h->d_keys_sorted) cudaFree(h->d_keys_sorted);
+    if (h->d_idx) cudaFree(h->d_idx);
+    if (h->d_order) cudaFree(h->d_order);
+    if (h->d_sort_tmp) cudaFree(h->d_sort_tmp);
     CUDA_TRY(cudaMalloc(&h->dS, sbytes));
     CUDA_TRY(cudaMemset(h->dS, 0, sbytes));
     const double* dZ = Z;
@@ -511,7 +546,8 @@ static int ensure(double*& p, size_t bytes) {
 template <int K, int MODE>
 static int launch_sphere(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
     const int n = h->n;
-    const size_t smem = (size_t)(((n * n + 32 * K + 1) & ~1) + 32 * K) * sizeof(double);
+    const int ns = (n + 1) & ~1;
+    const size_t smem = (size_t)(n * ns + 32 * K + 32 * K) * sizeof(double);
     auto kern = sphere_kernel<K, MODE>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -529,12 +565,20 @@ static int launch_sphere(riptrm_handle* h, const SphereParams& P, const DevOpts&
     return RIPTRM_OK;
 }
 
+// sort key of the second launch: work spent in the first one (tCG iterations + 2 per trust-region iteration);
+// pairs that already finished sort last
+__global__ void schedule_keys_kernel(const double* __restrict__ pause, float* keys, int* idx, int batch) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    const double* p = pause + (size_t)i * kPauseFields;
+    keys[i] = (p[7] != 0.0) ? (float)(p[3] + 2.0 * p[2]) : -1.0f;
+    idx[i] = i;
+}
+
 template <int MODE>
 static int dispatch_sphere(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
     const int n = h->n;
-    if (n <= 32) return launch_sphere<1, MODE>(h, P, o, st);
     if (n <= 64) return launch_sphere<2, MODE>(h, P, o, st);
-    if (n <= 96) return launch_sphere<3, MODE>(h, P, o, st);
     return launch_sphere<4, MODE>(h, P, o, st);
 }
 
@@ -546,6 +590,62 @@ static int finish_timing(riptrm_handle* h, bool sync) {
         h->last_ms = ms;
     }
     return RIPTRM_OK;
+}
+
+// One launch, or two with the pairs re-ordered in between (see solve_instance): `schedule_split` outer
+// iterations for every pair first, then the rest, longest first.  Bit-identical results either way.
+static int solve_scheduled(riptrm_handle* h, SphereParams P, const DevOpts& o, cudaStream_t st) {
+    int split = h->opts.schedule_split;  //: 0 auto, < 0 off, > 0 outer iteration
+    const int resident = h->num_sms * 8;
+    if (split == 0) split = (h->batch > resident && h->opts.maxiter > 12) ? 6 : -1;
+    if (split <= 0 || split >= h->opts.maxiter) {
+        P.order = nullptr;
+        P.pause = nullptr;
+        P.resume = 0;
+        P.pause_at = -1;
+        return dispatch_sphere<0>(h, P, o, st);
+    }
+    const size_t B = h->batch;
+    int rc;
+    if ((rc = ensure(h->d_pause, B * kPauseFields * sizeof(double)))) return rc;
+    if (h->d_keys == nullptr) {
+        CUDA_TRY(cudaMalloc(&h->d_keys, B * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&h->d_keys_sorted, B * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&h->d_idx, B * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&h->d_order, B * sizeof(int)));
+        CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, h->sort_tmp_bytes, h->d_keys, h->d_keys_sorted, h->d_idx,
+                                                           h->d_order, (int)B, 0, 32, st));
+        CUDA_TRY(cudaMalloc(&h->d_sort_tmp, h->sort_tmp_bytes));
+    }
+    // the paused iterates travel in the x / y output buffers
+    if (P.x == nullptr) {
+        if ((rc = ensure(h->d_x, B * h->vec_len * sizeof(double)))) return rc;
+        P.x = h->d_x;
+    }
+    if (P.y == nullptr) {
+        if ((rc = ensure(h->d_y, B * h->m * sizeof(double)))) return rc;
+        P.y = h->d_y;
+    }
+    cudaEvent_t first_start = nullptr;
+    CUDA_TRY(cudaEventCreateWithFlags(&first_start, cudaEventDefault));
+    P.order = nullptr;
+    P.pause = h->d_pause;
+    P.resume = 0;
+    P.pause_at = split;
+    if ((rc = dispatch_sphere<0>(h, P, o, st))) return rc;
+    std::swap(first_start, h->ev0);  // keep the start of the first launch: the reported time spans both
+    schedule_keys_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(h->d_pause, h->d_keys, h->d_idx, (int)B);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(h->d_sort_tmp, h->sort_tmp_bytes, h->d_keys, h->d_keys_sorted,
+                                                       h->d_idx, h->d_order, (int)B, 0, 32, st));
+    h->launches += 2;
+    P.order = h->d_order;
+    P.resume = 1;
+    P.pause_at = -1;
+    rc = dispatch_sphere<0>(h, P, o, st);
+    std::swap(first_start, h->ev0);
+    cudaEventDestroy(first_start);
+    return rc;
 }
 
 extern "C" int riptrm_solve(riptrm_handle* h, const double* x0, const double* y0, double* x, double* y,
@@ -575,8 +675,7 @@ extern "C" int riptrm_solve(riptrm_handle* h, const double* x0, const double* y0
         P.y = y;
         P.summary = summary;
         P.trace = trace;
-        int rc = dispatch_sphere<0>(h, P, o, st);
-        return rc;
+        return solve_scheduled(h, P, o, st);
     }
     int rc;
     if ((rc = ensure(h->d_x0, xb)) || (rc = ensure(h->d_y0, yb)) || (rc = ensure(h->d_x, xb)) ||
@@ -595,7 +694,7 @@ extern "C" int riptrm_solve(riptrm_handle* h, const double* x0, const double* y0
     P.y = h->d_y;
     P.summary = h->d_summary;
     P.trace = (tb != 0 && trace != nullptr) ? h->d_trace : nullptr;
-    if ((rc = dispatch_sphere<0>(h, P, o, st))) return rc;
+    if ((rc = solve_scheduled(h, P, o, st))) return rc;
     if (x) CUDA_TRY(cudaMemcpyAsync(x, h->d_x, xb, cudaMemcpyDeviceToHost, st));
     if (y) CUDA_TRY(cudaMemcpyAsync(y, h->d_y, yb, cudaMemcpyDeviceToHost, st));
     if (summary) CUDA_TRY(cudaMemcpyAsync(summary, h->d_summary, sb, cudaMemcpyDeviceToHost, st));

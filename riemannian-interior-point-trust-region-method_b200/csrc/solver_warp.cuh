@@ -88,8 +88,16 @@ __device__ __forceinline__ TcgResult tcg(const typename F::Ctx& ctx, const DevOp
             new_eta.v[k] = eta.v[k] + alpha * delta.v[k];  // :150
             new_Heta.v[k] = Heta.v[k] + alpha * Hd.v[k];   // :154
         }
-        const double new_model =
-            F::inner(ctx, pt, new_eta, st.c) + 0.5 * F::inner(ctx, pt, new_eta, new_Heta);  // :86-87,:162
+        // r_new is formed before the model test so that its norm rides in the same butterfly as the two
+        // model-value dot products (three sums, one reduction latency); the values are those of :162 / :175
+        Vec r_new;
+#pragma unroll
+        for (int k = 0; k < K; ++k) r_new.v[k] = r.v[k] + alpha * Hd.v[k];  // :172
+        double ip_ec = F::inner_partial(ctx, pt, new_eta, st.c);
+        double ip_eh = F::inner_partial(ctx, pt, new_eta, new_Heta);
+        double ip_rr = F::inner_partial(ctx, pt, r_new, r_new);
+        wsum3(ip_ec, ip_eh, ip_rr);
+        const double new_model = ip_ec + 0.5 * ip_eh;  // :86-87,:162
         if (new_model >= model_value) {                    // :163
             res.stop = RIPTRM_TCG_MODEL_INCREASED;
             ++j;
@@ -98,9 +106,8 @@ __device__ __forceinline__ TcgResult tcg(const typename F::Ctx& ctx, const DevOp
         eta = new_eta;                                     // :167-169
         Heta = new_Heta;
         model_value = new_model;
-#pragma unroll
-        for (int k = 0; k < K; ++k) r.v[k] = r.v[k] + alpha * Hd.v[k];  // :172
-        r_r = F::inner(ctx, pt, r, r);                     // :175
+        r = r_new;
+        r_r = ip_rr;                                       // :175
         const double norm_r = sqrt(r_r);
         if (j >= o.tcg_mininner && norm_r <= target) {     // :183-191
             res.stop = (o.tcg_kappa < nr_theta) ? RIPTRM_TCG_REACHED_TARGET_LINEAR
@@ -284,8 +291,10 @@ __device__ __forceinline__ bool inner_step(const typename F::Ctx& ctx, const Dev
     }
     xfe = wall(xfe) && F::domain_ok(ctx, ptN);
     yfe = wall(yfe);
-    const double compl_v = sqrt(wsum(p_c));
-    const double ngl = F::gradL_norm(ctx, ptN, yNew);               // :593
+    double p_xy = F::gradL_xy_partial(ctx, ptN, yNew);
+    wsum2(p_c, p_xy);
+    const double compl_v = sqrt(p_c);
+    const double ngl = F::gradL_norm_given(ctx, ptN, yNew, p_xy);   // :593
     info.minxfeasi = wmin(mins);
     info.minyfeasi = wmin(miny);
     info.compl_v = compl_v;
@@ -317,7 +326,9 @@ __device__ __forceinline__ bool inner_step(const typename F::Ctx& ctx, const Dev
     double ared = phi_cur - phi_new;                                // :658
     const Vec Hdx = F::Hw(ctx, pt, y, st, dx);                      // the extra Hessian-vector of :659
     cnt.aux += 1.0;
-    double pred = (0.0 - 0.5 * F::inner(ctx, pt, Hdx, dx)) - F::inner(ctx, pt, st.c, dx);
+    double ip_hd = F::inner_partial(ctx, pt, Hdx, dx), ip_cd = F::inner_partial(ctx, pt, st.c, dx);
+    wsum2(ip_hd, ip_cd);
+    double pred = (0.0 - 0.5 * ip_hd) - ip_cd;
     const double reg = (fmax(1.0, fabs(phi_cur)) * 2.220446049250313e-16) * o.reduction_regularization;  // :660
     ared = ared + reg;
     pred = pred + reg;
@@ -359,12 +370,25 @@ __device__ __forceinline__ bool inner_step(const typename F::Ctx& ctx, const Dev
 
 // ------------------------------------------------------------------------------------------
 // Whole solve: RIPTRM.run (:909-976) with outer_step (:866-896) and inner_run (:785-847)
+//
+// Pause / resume: a batch is solved in two launches (riptrm_api.cu: the first few outer iterations of every
+// pair, then the remainder in order of decreasing work so far, the longest pairs first).  A pair pauses right
+// after the loop-top bookkeeping of outer iteration `pause_at` (evaluation done, stop tests passed); its
+// state is (x, y) plus the 8 doubles of `PauseState`.  Everything else is a deterministic function of those,
+// so a resumed solve is bit-identical to an uninterrupted one.
 // ------------------------------------------------------------------------------------------
+constexpr int kPauseFields = 8;
+struct PauseState {
+    double Delta, it, inner, tcg, aux, rows, elapsed_s, paused;
+};
+
 template <class F>
 __device__ __forceinline__ void solve_instance(const typename F::Ctx& ctx, const DevOpts& o,
                                                const typename F::Vec& x0, const typename F::CVec& y0,
                                                typename F::Pt& pt, typename F::CVec& y, double* summary,
-                                               double* trace /* this instance's rows or nullptr */) {
+                                               double* trace /* this instance's rows or nullptr */,
+                                               double* pause /* kPauseFields doubles or nullptr */, bool resume,
+                                               int pause_at /* outer iteration to pause at; < 0: never */) {
     using Vec = typename F::Vec;
     using CVec = typename F::CVec;
     F::eval_point(ctx, x0, pt);                                     // outer_preprocess (:849-864)
@@ -375,23 +399,45 @@ __device__ __forceinline__ void solve_instance(const typename F::Ctx& ctx, const
     Counters cnt = {0.0, 0.0, 0.0};
     int it = 0, rows = 0, stop_reason = RIPTRM_STOP_RUNNING;
     double mu = o.mu[0];
+    double elapsed0 = 0.0;
+    if (resume) {
+        Delta = pause[0];
+        it = (int)pause[1];
+        cnt.inner = pause[2];
+        cnt.tcg = pause[3];
+        cnt.aux = pause[4];
+        rows = (int)pause[5];
+        elapsed0 = pause[6];
+        mu = o.mu[it];
+    }
     const uint64_t t_start = global_timer_ns();
     EvalRow ev;
+    bool skip_top = resume;
     while (true) {                                                  // :931
-        ev = evaluate<F>(ctx, pt, y, xPrev);                        // :933
-        if (o.trace_mode != 0 && (it == 0 || o.trace_mode == 2)) {  // :936-941
-            if (trace != nullptr && rows < o.trace_capacity)
-                write_trace_row(trace + (size_t)rows * RIPTRM_TRACE_FIELDS, it, mu, info, max_abs_mult<F>(ctx, y), ev,
-                                (double)(global_timer_ns() - t_start) * 1e-9);
-            ++rows;
+        if (!skip_top) {
+            ev = evaluate<F>(ctx, pt, y, xPrev);                    // :933
+            if (o.trace_mode != 0 && (it == 0 || o.trace_mode == 2)) {  // :936-941
+                if (trace != nullptr && rows < o.trace_capacity)
+                    write_trace_row(trace + (size_t)rows * RIPTRM_TRACE_FIELDS, it, mu, info, max_abs_mult<F>(ctx, y),
+                                    ev, elapsed0 + (double)(global_timer_ns() - t_start) * 1e-9);
+                ++rows;
+            }
+            xPrev = pt.x;                                           // :946
+            // base_solver.check_stoppingcriterion (:85-106) + residual criterion (:942-945)
+            const double run_time = elapsed0 + (double)(global_timer_ns() - t_start) * 1e-9;
+            if (run_time >= o.maxtime) stop_reason = RIPTRM_STOP_MAXTIME;
+            else if (it >= o.maxiter) stop_reason = RIPTRM_STOP_MAXITER;
+            if (ev.residual <= o.tolresid) stop_reason = RIPTRM_STOP_TOLRESID;
+            if (stop_reason != RIPTRM_STOP_RUNNING) break;
+            if (it == pause_at) {                                   // hand over to the second launch
+                const int l = lane_id();
+                const double v = (l == 0) ? Delta : (l == 1) ? (double)it : (l == 2) ? cnt.inner : (l == 3) ? cnt.tcg
+                               : (l == 4) ? cnt.aux : (l == 5) ? (double)rows : (l == 6) ? run_time : 1.0;
+                if (l < kPauseFields) pause[l] = v;
+                return;
+            }
         }
-        xPrev = pt.x;                                               // :946
-        // base_solver.check_stoppingcriterion (:85-106) + residual criterion (:942-945)
-        const double run_time = (double)(global_timer_ns() - t_start) * 1e-9;
-        if (run_time >= o.maxtime) stop_reason = RIPTRM_STOP_MAXTIME;
-        else if (it >= o.maxiter) stop_reason = RIPTRM_STOP_MAXITER;
-        if (ev.residual <= o.tolresid) stop_reason = RIPTRM_STOP_TOLRESID;
-        if (stop_reason != RIPTRM_STOP_RUNNING) break;
+        skip_top = false;
         it += 1;                                                    // :959
         // ---- outer_step (:866-896)
         mu = o.mu[it - 1];
@@ -411,14 +457,16 @@ __device__ __forceinline__ void solve_instance(const typename F::Ctx& ctx, const
                 if (trace != nullptr && rows < o.trace_capacity) {
                     const EvalRow evi = evaluate<F>(ctx, pt, y, xPrevInner);
                     write_trace_row(trace + (size_t)rows * RIPTRM_TRACE_FIELDS, it, mu, info,
-                                    max_abs_mult<F>(ctx, y), evi, (double)(global_timer_ns() - t_start) * 1e-9);
+                                    max_abs_mult<F>(ctx, y), evi,
+                                    elapsed0 + (double)(global_timer_ns() - t_start) * 1e-9);
                 }
                 ++rows;
             }
             xPrevInner = pt.x;                                      // :819
             bool rollback = false;
             const uint64_t now = global_timer_ns();                 // :822-834
-            const double rt = (o.inner_maxtime < 0.0) ? (double)(now - t_start) * 1e-9 : (double)(now - t_inner) * 1e-9;
+            const double rt = (o.inner_maxtime < 0.0) ? elapsed0 + (double)(now - t_start) * 1e-9
+                                                      : (double)(now - t_inner) * 1e-9;
             const double lim = (o.inner_maxtime < 0.0) ? o.maxtime : o.inner_maxtime;
             if (rt >= lim) {
                 info.inner_status = (double)RIPTRM_INNER_MAX_TIME;
@@ -439,6 +487,7 @@ __device__ __forceinline__ void solve_instance(const typename F::Ctx& ctx, const
         mu = o.mu[it];                                              // :890-893 (host-evaluated schedule)
         Delta = fmax(Delta, o.minimal_initial_tr_radius);           // :894
     }
+    if (pause != nullptr && lane_id() == 7) pause[7] = 0.0;        // finished, nothing left for a second launch
     if (summary != nullptr) {
         const int l = lane_id();
         double v = 0.0;

@@ -106,6 +106,7 @@ def to_c_options(option, trace_mode, trace_capacity):
     o.is_euclidean_embedded = int(bool(option["is_euclidean_embedded"]))
     o.trace_mode = int(trace_mode)
     o.trace_capacity = int(trace_capacity)
+    o.schedule_split = int(option.get("schedule_split", 0))  # riptrm_b200 extension, see include/riptrm_b200.h
     o.tolresid = float(option["tolresid"])
     o.maxtime = float(option["maxtime"]) if math.isfinite(float(option["maxtime"])) else 1e300
     o.inner_maxtime = -1.0 if option["inner_maxtime"] is None else float(option["inner_maxtime"])
