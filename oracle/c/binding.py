@@ -40,15 +40,21 @@ def _try_build():
         return False
 
 
-def load():
-    global _lib
+_lib_faithful = None
+
+
+def load(faithful=False):
+    """faithful=False: the merged-reduction tCG (bit-identical to the CUDA kernel); True: reference operation order."""
+    global _lib, _lib_faithful
     if _lib is None:
         _build.build()
         _lib = C.CDLL(_build.LIB)
-        _lib.riptrm_det_solve_nonnegpca.restype = C.c_int
-        _lib.riptrm_det_solve_many.restype = C.c_int
-        _lib.riptrm_det_hessvec.restype = C.c_int
-    return _lib
+        _lib_faithful = C.CDLL(_build.LIB_FAITHFUL)
+        for l in (_lib, _lib_faithful):
+            l.riptrm_det_solve_nonnegpca.restype = C.c_int
+            l.riptrm_det_solve_many.restype = C.c_int
+            l.riptrm_det_hessvec.restype = C.c_int
+    return _lib_faithful if faithful else _lib
 
 
 def make_options(option=None, trace_mode=0, trace_capacity=0):
@@ -94,9 +100,9 @@ def _p(a):
     return a.ctypes.data_as(_DP) if a is not None else None
 
 
-def solve(Z, x0, y0, option=None, eps=0.0, trace_capacity=0):
+def solve(Z, x0, y0, option=None, eps=0.0, trace_capacity=0, faithful=False):
     """One NonnegPCA/Sphere solve.  Returns (x, y, summary[16], trace[rows, 25] | None)."""
-    lib = load()
+    lib = load(faithful)
     Z, x0, y0 = (np.ascontiguousarray(a, dtype=np.float64) for a in (Z, x0, y0))
     n = x0.shape[0]
     d, keep = make_options(option, 1 if trace_capacity else 0, trace_capacity)
@@ -109,7 +115,7 @@ def solve(Z, x0, y0, option=None, eps=0.0, trace_capacity=0):
     if tr is not None:
         rows = int(sm[15])
         if rows > trace_capacity:
-            return solve(Z, x0, y0, option, eps, rows)
+            return solve(Z, x0, y0, option, eps, rows, faithful)
         tr = tr[:rows]
     return x, y, sm, tr
 

@@ -9,13 +9,18 @@ LIB = os.path.join(OUT_DIR, "libriptrm_det.so")
 SRC = os.path.join(HERE, "riptrm_det.c")
 
 
+LIB_FAITHFUL = os.path.join(OUT_DIR, "libriptrm_det_faithful.so")
+
+
 def build(force=False):
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
+    """libriptrm_det.so (merged-reduction tCG, the arithmetic the CUDA kernel implements) and
+    libriptrm_det_faithful.so (-DFAITHFUL_TCG: the tCG loop in the reference's operation order)."""
+    if not force and all(os.path.exists(l) and os.path.getmtime(l) >= os.path.getmtime(SRC) for l in (LIB, LIB_FAITHFUL)):
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = ["gcc", "-O2", "-std=c99", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-mfma",
-           "-o", LIB, SRC, "-lm"]
-    subprocess.run(cmd, check=True)
+    base = ["gcc", "-O2", "-std=c99", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-mfma"]
+    subprocess.run(base + ["-o", LIB, SRC, "-lm"], check=True)
+    subprocess.run(base + ["-DFAITHFUL_TCG", "-o", LIB_FAITHFUL, SRC, "-lm"], check=True)
     return LIB
 
 

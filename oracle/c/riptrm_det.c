@@ -250,6 +250,81 @@ static TcgResult tcg(const Ctx* c, const det_options* o, const Pt* pt, const Ste
     const double nr_theta = (o->tcg_theta == 1.0) ? norm_r0 : pow(norm_r0, o->tcg_theta);
     const double target = norm_r0 * fmin(nr_theta, o->tcg_kappa);
     int j = 0;
+#ifndef FAITHFUL_TCG
+    /* Merged-reduction form (what the CUDA Sphere kernel runs): algebraically the loop of RIPTRM.py:98-214, with
+     * <x,t>, <delta,H delta> and the projection coefficient assembled from 6 + 4 inner products taken in two
+     * reduction rounds per iteration instead of five dependent ones.  -DFAITHFUL_TCG compiles the loop in the
+     * reference's operation order instead (same results to rounding; tests/test_oracle_c.py compares both). */
+    double wv[MAXN], Sv[MAXN], tmp[MAXN], r_new[MAXN];
+    for (int e = 0; e < N; ++e) wv[e] = pt->x[e] * st->ys[e];
+    const double q = vdot(c, wv, pt->x);
+    for (; j < maxinner; ++j) {
+        matvec(c, delta, Sv);
+        const double a = vdot(c, pt->x, Sv), b = vdot(c, pt->x, delta), g1 = vdot(c, wv, delta);
+        const double h1 = vdot(c, delta, Sv), h2 = vdot(c, delta, delta);
+        for (int e = 0; e < N; ++e) tmp[e] = st->ys[e] * delta[e];
+        const double h3 = vdot(c, delta, tmp);
+        const double d = c->embedded ? g1 : (g1 - b * q);
+        for (int e = 0; e < N; ++e) {
+            const double ga = c->embedded ? delta[e] : (delta[e] - pt->x[e] * b);
+            const double t = st->ys[e] * ga;
+            const double hl = (-Sv[e] + a * pt->x[e]) + st->kappa * delta[e];
+            const double g = t - d * pt->x[e];
+            Hd[e] = hl + g;
+        }
+        const double dt = c->embedded ? h3 : (h3 - b * g1);
+        const double d_Hd = (((-h1 + a * b) + st->kappa * h2) + dt) - d * b;
+        double alpha = 0.0, e_Pe_new = e_Pe;
+        if (d_Hd != 0.0) {
+            alpha = z_r / d_Hd;
+            e_Pe_new = (e_Pe + (2.0 * alpha) * e_Pd) + (alpha * alpha) * d_Pd;
+        }
+        if (d_Hd <= 0.0 || e_Pe_new >= Delta2) {
+            const double tau = (-e_Pd + sqrt(e_Pd * e_Pd + d_Pd * (Delta2 - e_Pe))) / d_Pd;
+            for (int e = 0; e < N; ++e) {
+                eta[e] = eta[e] + tau * delta[e];
+                Heta[e] = Heta[e] + tau * Hd[e];
+            }
+            res.stop = (d_Hd <= 0.0) ? TCG_NEGATIVE_CURVATURE : TCG_EXCEEDED_TR;
+            ++j;
+            break;
+        }
+        e_Pe = e_Pe_new;
+        for (int e = 0; e < N; ++e) {
+            new_eta[e] = eta[e] + alpha * delta[e];
+            new_Heta[e] = Heta[e] + alpha * Hd[e];
+            r_new[e] = r[e] + alpha * Hd[e];
+        }
+        const double new_model = vdot(c, new_eta, st->c) + 0.5 * vdot(c, new_eta, new_Heta);
+        const double rr_new = vdot(c, r_new, r_new), xr = vdot(c, pt->x, r_new);
+        if (new_model >= model_value) {
+            res.stop = TCG_MODEL_INCREASED;
+            ++j;
+            break;
+        }
+        memcpy(eta, new_eta, sizeof(double) * N);
+        memcpy(Heta, new_Heta, sizeof(double) * N);
+        memcpy(r, r_new, sizeof(double) * N);
+        model_value = new_model;
+        r_r = rr_new;
+        const double norm_r = sqrt(r_r);
+        if (j >= o->tcg_mininner && norm_r <= target) {
+            res.stop = (o->tcg_kappa < nr_theta) ? TCG_REACHED_TARGET_LINEAR : TCG_REACHED_TARGET_SUPERLINEAR;
+            ++j;
+            break;
+        }
+        const double zold_rold = z_r;
+        z_r = r_r;
+        const double beta = z_r / zold_rold;
+        const double xd = -xr + beta * b; /* <x, -r + beta delta> */
+        for (int e = 0; e < N; ++e) {
+            const double dn = -r[e] + beta * delta[e];
+            delta[e] = dn - xd * pt->x[e];
+        }
+        e_Pd = beta * (e_Pd + alpha * d_Pd);
+        d_Pd = z_r + (beta * beta) * d_Pd;
+    }
+#else
     for (; j < maxinner; ++j) {
         Hw(c, pt, st, delta, Hd);
         const double d_Hd = vdot(c, delta, Hd);
@@ -298,6 +373,7 @@ static TcgResult tcg(const Ctx* c, const det_options* o, const Pt* pt, const Ste
         e_Pd = beta * (e_Pd + alpha * d_Pd);
         d_Pd = z_r + (beta * beta) * d_Pd;
     }
+#endif
     res.iters = j;
     res.model_value = model_value;
     return res;

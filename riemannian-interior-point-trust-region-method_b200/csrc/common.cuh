@@ -44,6 +44,17 @@ __device__ __forceinline__ void wsum3(double& a, double& b, double& c) {
         c = c + tc;
     }
 }
+template <int N>
+__device__ __forceinline__ void wsumN(double (&v)[N]) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double t[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) t[i] = __shfl_xor_sync(kFull, v[i], off);
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = v[i] + t[i];
+    }
+}
 __device__ __forceinline__ double wmin(double p) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) p = fmin(p, __shfl_xor_sync(kFull, p, off));

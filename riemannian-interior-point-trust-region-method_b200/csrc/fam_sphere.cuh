@@ -172,6 +172,123 @@ struct SphereFam {
         return out;
     }
 
+    // Steihaug-Toint tCG (RIPTRM.py:41-216) with merged reductions.  A warp-wide fp64 sum costs ~185 cycles
+    // of pure latency on B200 whether it carries one value or six (scripts/microbench.cu), and the loop in the
+    // reference's operation order needs five dependent ones per iteration.  Here <x,t>, <delta, Hw delta> and the
+    // coefficient of the re-projection of delta (:210) are assembled from inner products that do not depend on
+    // each other: with w = x*(y/s), q = <w,x>,
+    //     d      = <x, (y/s)*(delta - b x)>            = <w,delta> - b q
+    //     d_Hd   = <delta, P(-S delta) + kappa delta + P((y/s)*G*[delta])>
+    //            = -<delta,S delta> + a b + kappa <delta,delta> + (<delta,(y/s)*delta> - b <w,delta>) - d b
+    //     <x, -r' + beta delta> = -<x,r'> + beta b
+    // so an iteration is S.delta, one 6-value reduction, the step, one 4-value reduction.  Same algorithm, same
+    // exits; rounding differs from the reference order by the usual few ulp (oracle/c/riptrm_det.c implements
+    // exactly this arithmetic and tests/test_oracle_c.py compares both orders and the reference's golden run).
+    static __device__ __forceinline__ TcgResult tcg(const Ctx& ctx, const DevOpts& o, const Pt& pt, const CVec& y,
+                                                    const Step& st, double Delta, Vec& eta, Vec& Heta) {
+        (void)y;
+        eta = wzero<K>();
+        Heta = wzero<K>();                                     // :47
+        Vec r = st.c, delta, wv;                               // :48
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            delta.v[k] = -r.v[k];                              // :71
+            wv.v[k] = pt.x.v[k] * st.ys.v[k];
+        }
+        double r_r = wdot_partial(r, r), q = wdot_partial(wv, pt.x);
+        wsum2(r_r, q);                                         // :56
+        const double norm_r0 = sqrt(r_r);
+        double z_r = r_r, d_Pd = r_r, e_Pe = 0.0, e_Pd = 0.0, model_value = 0.0;
+        TcgResult res;
+        res.stop = RIPTRM_TCG_MAX_INNER_ITER;                  // :95
+        const int maxinner = o.tcg_maxinner < 0 ? dim(ctx) : o.tcg_maxinner;
+        const double Delta2 = Delta * Delta;
+        const double nr_theta = (o.tcg_theta == 1.0) ? norm_r0 : pow(norm_r0, o.tcg_theta);
+        const double target = norm_r0 * fmin(nr_theta, o.tcg_kappa);
+        int j = 0;
+        for (; j < maxinner; ++j) {                            // :98
+            const Vec Sv = matvec(ctx, delta);                 // :100
+            Vec tmp;
+#pragma unroll
+            for (int k = 0; k < K; ++k) tmp.v[k] = st.ys.v[k] * delta.v[k];
+            double s6[6] = {wdot_partial(pt.x, Sv), wdot_partial(pt.x, delta), wdot_partial(wv, delta),
+                            wdot_partial(delta, Sv), wdot_partial(delta, delta), wdot_partial(delta, tmp)};
+            wsumN<6>(s6);
+            const double a = s6[0], b = s6[1], g1 = s6[2], h1 = s6[3], h2 = s6[4], h3 = s6[5];
+            const double d = ctx.embedded ? g1 : (g1 - b * q);
+            Vec Hd;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double ga = ctx.embedded ? delta.v[k] : (delta.v[k] - pt.x.v[k] * b);
+                const double t = st.ys.v[k] * ga;
+                const double hl = (-Sv.v[k] + a * pt.x.v[k]) + st.kappa * delta.v[k];
+                const double g = t - d * pt.x.v[k];
+                Hd.v[k] = hl + g;
+            }
+            const double dt = ctx.embedded ? h3 : (h3 - b * g1);
+            const double d_Hd = (((-h1 + a * b) + st.kappa * h2) + dt) - d * b;   // :103
+            double alpha = 0.0, e_Pe_new = e_Pe;
+            if (d_Hd != 0.0) {                                 // :106-114
+                alpha = z_r / d_Hd;
+                e_Pe_new = (e_Pe + (2.0 * alpha) * e_Pd) + (alpha * alpha) * d_Pd;
+            }
+            if (d_Hd <= 0.0 || e_Pe_new >= Delta2) {           // :118
+                const double tau = (-e_Pd + sqrt(e_Pd * e_Pd + d_Pd * (Delta2 - e_Pe))) / d_Pd;  // :123-125
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    eta.v[k] = eta.v[k] + tau * delta.v[k];    // :127
+                    Heta.v[k] = Heta.v[k] + tau * Hd.v[k];     // :132
+                }
+                res.stop = (d_Hd <= 0.0) ? RIPTRM_TCG_NEGATIVE_CURVATURE : RIPTRM_TCG_EXCEEDED_TR;
+                ++j;
+                break;
+            }
+            e_Pe = e_Pe_new;                                   // :149
+            Vec new_eta, new_Heta, r_new;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                new_eta.v[k] = eta.v[k] + alpha * delta.v[k];  // :150
+                new_Heta.v[k] = Heta.v[k] + alpha * Hd.v[k];   // :154
+                r_new.v[k] = r.v[k] + alpha * Hd.v[k];         // :172
+            }
+            double s4[4] = {wdot_partial(new_eta, st.c), wdot_partial(new_eta, new_Heta), wdot_partial(r_new, r_new),
+                            wdot_partial(pt.x, r_new)};
+            wsumN<4>(s4);
+            const double new_model = s4[0] + 0.5 * s4[1];      // :86-87, :162
+            if (new_model >= model_value) {                    // :163
+                res.stop = RIPTRM_TCG_MODEL_INCREASED;
+                ++j;
+                break;
+            }
+            eta = new_eta;                                     // :167-169
+            Heta = new_Heta;
+            r = r_new;
+            model_value = new_model;
+            r_r = s4[2];                                       // :175
+            const double norm_r = sqrt(r_r);
+            if (j >= o.tcg_mininner && norm_r <= target) {     // :183-191
+                res.stop = (o.tcg_kappa < nr_theta) ? RIPTRM_TCG_REACHED_TARGET_LINEAR
+                                                    : RIPTRM_TCG_REACHED_TARGET_SUPERLINEAR;
+                ++j;
+                break;
+            }
+            const double zold_rold = z_r;                      // :200
+            z_r = r_r;                                         // :202
+            const double beta = z_r / zold_rold;               // :205
+            const double xd = -s4[3] + beta * b;               // <x, -r + beta delta>
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double dn = -r.v[k] + beta * delta.v[k]; // :206
+                delta.v[k] = dn - xd * pt.x.v[k];              // :210
+            }
+            e_Pd = beta * (e_Pd + alpha * d_Pd);               // :213
+            d_Pd = z_r + (beta * beta) * d_Pd;                 // :214
+        }
+        res.iters = j;
+        res.model_value = model_value;
+        return res;
+    }
+
     static __device__ __forceinline__ Vec retract(const Ctx&, const Pt& pt, const Vec& dx) {
         Vec a;
 #pragma unroll

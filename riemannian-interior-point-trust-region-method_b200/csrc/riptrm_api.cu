@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(32, (K == 2) ? 8 : 4) sphere_kernel(SpherePara
                 store_vec<K>(P.out + (size_t)inst * n, hv, n);
             } else {
                 typename F::Vec eta, Heta;
-                const TcgResult r = tcg<F>(ctx, o, pt, y0, st, P.Delta, eta, Heta);
+                const TcgResult r = F::tcg(ctx, o, pt, y0, st, P.Delta, eta, Heta);
                 store_vec<K>(P.out + (size_t)inst * n, eta, n);
                 const double nrm = sqrt(F::inner(ctx, pt, eta, eta));  // warp-collective: all lanes
                 if (P.info != nullptr && lane < 4) {

@@ -33,10 +33,12 @@ struct TcgResult {
 };
 
 // ------------------------------------------------------------------------------------------
-// Steihaug-Toint truncated CG, eta0 = 0, identity preconditioner  (RIPTRM.py:41-216)
+// Steihaug-Toint truncated CG, eta0 = 0, identity preconditioner  (RIPTRM.py:41-216), in the reference's
+// operation order, for any family.  A family's F::tcg either forwards here or provides a form with merged
+// reductions (fam_sphere.cuh).
 // ------------------------------------------------------------------------------------------
 template <class F>
-__device__ __forceinline__ TcgResult tcg(const typename F::Ctx& ctx, const DevOpts& o, const typename F::Pt& pt,
+__device__ __forceinline__ TcgResult tcg_generic(const typename F::Ctx& ctx, const DevOpts& o, const typename F::Pt& pt,
                                          const typename F::CVec& y, const typename F::Step& st, double Delta,
                                          typename F::Vec& eta, typename F::Vec& Heta) {
     using Vec = typename F::Vec;
@@ -253,7 +255,7 @@ __device__ __forceinline__ bool inner_step(const typename F::Ctx& ctx, const Dev
     F::begin_step(ctx, pt, y, mu, st);                              // s, grad f, c  (:724-730)
 
     Vec dx, Hdx_unused;
-    const TcgResult tr = tcg<F>(ctx, o, pt, y, st, Delta, dx, Hdx_unused);  // :733 -> :445-452
+    const TcgResult tr = F::tcg(ctx, o, pt, y, st, Delta, dx, Hdx_unused);  // :733 -> :445-452
     cnt.tcg += (double)tr.iters;
     info.dxtype = (double)tr.stop;
     info.tcg_iters = (double)tr.iters;

@@ -84,3 +84,18 @@ def test_c_oracle_is_deterministic_and_threads_agree():
     x1, y1, s1 = detc.solve_many(Z, X, Y, opt, threads=1)
     x2, y2, s2 = detc.solve_many(Z, X, Y, opt, threads=3)
     assert np.array_equal(x1, x2) and np.array_equal(y1, y2) and np.array_equal(s1, s2)
+
+
+def test_merged_reduction_tcg_matches_reference_operation_order(datasets):
+    """The kernel's merged-reduction tCG vs the same C oracle compiled with the tCG loop in the reference's
+    operation order (-DFAITHFUL_TCG): same discrete trace in the well-conditioned window, same final iterate."""
+    d = datasets["NonnegPCA/1"]
+    opt = {"maxiter": 40, "tolresid": 0}
+    xa, ya, sa, ta = detc.solve(d["Z"], d["initx_a"], d["initineqLagmult"], opt, trace_capacity=512)
+    xb, yb, sb, tb = detc.solve(d["Z"], d["initx_a"], d["initineqLagmult"], opt, trace_capacity=512, faithful=True)
+    La, Lb = rb.trace_to_log(ta), rb.trace_to_log(tb)
+    first = first_discrete_mismatch(La, Lb, columns=DISCRETE_COLUMNS + ("tcg_iters",))
+    assert Lb["iteration"][min(first, len(Lb["iteration"]) - 1)] > 8
+    assert np.max(np.abs(xa - xb)) < 1e-12 and abs(sa[0] - sb[0]) < 1e-12 * abs(sb[0])
+    g = load_golden("nonnegpca_1_a_K40")
+    assert np.max(np.abs(xb - np.array(g["x"]))) < REL_TOL
