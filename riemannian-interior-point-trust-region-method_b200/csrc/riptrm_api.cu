@@ -47,6 +47,7 @@ struct riptrm_handle {
     // problem data
     double* dZ = nullptr;  // [batch_z][n][n]
     bool ownZ = false;
+    size_t z_bytes = 0;
     int batch_z = 0;
     double eps = 0.0;
     bool have_problem = false;
@@ -464,14 +465,22 @@ extern "C" int riptrm_set_nonnegpca(riptrm_handle* h, const double* Z, int batch
     CUDA_TRY(cudaSetDevice(h->device));
     if (h->family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS) return columns_setup(h, Z, eps, where);
     const size_t bytes = (size_t)batch_z * h->n * h->n * sizeof(double);
-    if (h->ownZ) free_dev(h->dZ);
     if (where == RIPTRM_DEVICE) {
+        if (h->ownZ) free_dev(h->dZ);
         h->dZ = const_cast<double*>(Z);
         h->ownZ = false;
+        h->z_bytes = 0;
     } else {
-        CUDA_TRY(cudaMalloc(&h->dZ, bytes));
-        h->ownZ = true;
-        CUDA_TRY(cudaMemcpy(h->dZ, Z, bytes, cudaMemcpyHostToDevice));
+        // staging buffer is kept across calls (re-binding new data every step must not pay cudaMalloc / cudaFree)
+        if (!h->ownZ || h->z_bytes != bytes) {
+            if (h->ownZ) free_dev(h->dZ);
+            h->dZ = nullptr;
+            CUDA_TRY(cudaMalloc(&h->dZ, bytes));
+            h->ownZ = true;
+            h->z_bytes = bytes;
+        }
+        CUDA_TRY(cudaMemcpyAsync(h->dZ, Z, bytes, cudaMemcpyHostToDevice, 0));
+        CUDA_TRY(cudaStreamSynchronize(0));  // the caller may reuse its buffer on return
     }
     h->batch_z = batch_z;
     h->eps = eps;
