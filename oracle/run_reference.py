@@ -85,27 +85,31 @@ def load_cfg(problem_name, overrides=None):
     return cfg
 
 
-def run_reference(problem_name, overrides=None, solver_name="RIPTRM"):
-    """Returns (output, tcg_iters:list[int], scratch_dir)."""
+def run_reference(problem_name, overrides=None, solver_name="RIPTRM", solver_path=None):
+    """Returns (output, tcg_iters:list[int], scratch_dir).  `solver_path`: a directory put ahead of the
+    reference's ./src/solver on sys.path (tests/test_dropin_recognition.py uses it to let the reference's
+    Simulator pick up integration/RIPTRM.py instead of its own solver module)."""
     scratch = tempfile.mkdtemp(prefix="riptrm_ref_")
     os.symlink(f"{REFERENCE}/src", f"{scratch}/src")
     os.symlink(f"{REFERENCE}/dataset", f"{scratch}/dataset")
     old_cwd = os.getcwd()
     os.chdir(scratch)
-    sys.path[:0] = [f"{REPO}/oracle/shims", REPO, f"./src/{problem_name}", "./src/solver", "./src/base"]
+    sys.path[:0] = ([solver_path] if solver_path else []) + [
+        f"{REPO}/oracle/shims", REPO, f"./src/{problem_name}", "./src/solver", "./src/base"]
     try:
         import simulator  # the reference's src/<problem>/simulator.py
-        import RIPTRM as ref_riptrm  # the reference's src/solver/RIPTRM.py
+        import RIPTRM as ref_riptrm  # the reference's src/solver/RIPTRM.py (or the drop-in under solver_path)
 
         tcg_iters = []
-        orig_tcg = ref_riptrm.truncated_conjugate_gradient
+        if hasattr(ref_riptrm, "truncated_conjugate_gradient"):
+            orig_tcg = ref_riptrm.truncated_conjugate_gradient
 
-        def counting_tcg(*a, **k):
-            eta, Heta, j, stop = orig_tcg(*a, **k)
-            tcg_iters.append(int(j) + 1)
-            return eta, Heta, j, stop
+            def counting_tcg(*a, **k):
+                eta, Heta, j, stop = orig_tcg(*a, **k)
+                tcg_iters.append(int(j) + 1)
+                return eta, Heta, j, stop
 
-        ref_riptrm.truncated_conjugate_gradient = counting_tcg
+            ref_riptrm.truncated_conjugate_gradient = counting_tcg
 
         ov = {"solver_name": [solver_name]}
         ov.update(overrides or {})

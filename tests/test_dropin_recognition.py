@@ -58,3 +58,28 @@ def test_stableid_problem_is_recognised():
     out = _run("StableIdentification")
     assert out["type"] == "StableIdStructure" and out["shape"] == [5, 3, 16]
     assert out["conspec_rows"] == 16 and out["kinds"] == [0.0, 1.0, 2.0] and out["N"] == 95
+
+
+def test_reference_simulator_reaches_the_c_abi_through_the_dropin_module():
+    """The reference's own Simulator (unmodified, on the stand-ins) resolves solver_name=[RIPTRM] to
+    integration/RIPTRM.py, builds the option dict, hands over its NonlinearProblem, and the call reaches the CUDA
+    library -- which, in this GPU-less container, must fail loudly (RiptrmError from the C ABI), not fall back."""
+    script = r'''
+import sys
+sys.path.insert(0, {repo!r})
+from oracle.run_reference import run_reference
+try:
+    run_reference("NonnegPCA", {{"solver_option.common.maxiter": 3, "solver_option.common.tolresid": 0}},
+                  solver_path={repo!r} + "/integration")
+    print("RESULT solved")
+except Exception as e:
+    print("RESULT", type(e).__name__, str(e)[:200])
+'''.format(repo=REPO)
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, cwd=REPO, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")][-1]
+    import torch
+    if torch.cuda.is_available():
+        assert line == "RESULT solved"
+    else:
+        assert line.startswith("RESULT RiptrmError") and "riptrm error -2" in line, line
