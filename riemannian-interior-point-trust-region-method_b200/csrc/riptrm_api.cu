@@ -17,6 +17,7 @@
 
 #include "../../include/riptrm_b200.h"
 #include "fam_columns.cuh"
+#include "fam_grassmann.cuh"
 #include "fam_sphere.cuh"
 
 using namespace riptrm;
@@ -50,6 +51,7 @@ struct riptrm_handle {
     size_t z_bytes = 0;
     int batch_z = 0;
     double eps = 0.0;
+    double ros_alpha = 0.0, ros_offset = 0.0;
     bool have_problem = false;
     // options
     riptrm_options opts{};
@@ -227,6 +229,9 @@ extern "C" int riptrm_create(int family, int n, int p, int m, int batch, int dev
     if (family == RIPTRM_FAMILY_NONNEGPCA_SPHERE) {
         if (p != 1 || m != n) return fail(RIPTRM_E_INVALID, "NonnegPCA/Sphere needs p == 1 and m == n");
         if (n > 128) return fail(RIPTRM_E_UNSUPPORTED, "Sphere family: n <= 128 (use RIPTRM_FAMILY_NONNEGPCA_COLUMNS for large n)");
+    } else if (family == RIPTRM_FAMILY_ROSENBROCK_GRASSMANN) {
+        if (n * p > 32 || p > GrassmannFam::PMAX || p > n) return fail(RIPTRM_E_UNSUPPORTED, "Grassmann family: n*p <= 32, p <= 5");
+        if (m != n * p) return fail(RIPTRM_E_INVALID, "Rosenbrock/Grassmann needs m == n * p");
     } else if (family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS) {
         if (batch != 1) return fail(RIPTRM_E_INVALID, "COLUMNS family: batch must be 1 (the p columns are the batch)");
         if (m != n * p) return fail(RIPTRM_E_INVALID, "COLUMNS family needs m == n * p");
@@ -488,8 +493,13 @@ extern "C" int riptrm_set_nonnegpca(riptrm_handle* h, const double* Z, int batch
     return RIPTRM_OK;
 }
 
-extern "C" int riptrm_set_rosenbrock(riptrm_handle*, double, double) {
-    return fail(RIPTRM_E_UNSUPPORTED, "Rosenbrock family not built into this library");
+extern "C" int riptrm_set_rosenbrock(riptrm_handle* h, double alpha, double offset) {
+    if (h == nullptr) return fail(RIPTRM_E_INVALID, "NULL argument");
+    if (h->family != RIPTRM_FAMILY_ROSENBROCK_GRASSMANN) return fail(RIPTRM_E_INVALID, "handle is not the Rosenbrock family");
+    h->ros_alpha = alpha;
+    h->ros_offset = offset;
+    h->have_problem = true;
+    return RIPTRM_OK;
 }
 extern "C" int riptrm_set_stableid(riptrm_handle*, const double*, const double*, int, double, const double*, int, int) {
     return fail(RIPTRM_E_UNSUPPORTED, "StableIdentification family not built into this library");
@@ -601,6 +611,107 @@ static int finish_timing(riptrm_handle* h, bool sync) {
     return RIPTRM_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// small-manifold families (Grassmann, Product[Skew, SPD, SPD]): one warp per pair, vectors on lanes, matrix
+// products through a per-warp shared-memory scratch; same generic solve (solver_warp.cuh)
+// ------------------------------------------------------------------------------------------
+struct SmallParams {
+    int n, p, m, batch;
+    double alpha, offset;  // Rosenbrock
+    const double* x0;
+    const double* y0;
+    double* x;
+    double* y;
+    double* summary;
+    double* trace;
+    const double* v;
+    double mu, Delta;
+    double* out;
+    double* info;
+};
+
+template <class F, int MODE>
+__global__ void __launch_bounds__(32) small_kernel(SmallParams P, DevOpts o, int* counter) {
+    extern __shared__ __align__(16) double smem[];
+    typename F::Ctx ctx = F::make_ctx(P, o, smem);
+    const int lane = lane_id();
+    const int xl = P.n * P.p * F::kComponents;
+    while (true) {
+        int inst = 0;
+        if (lane == 0) inst = atomicAdd(counter, 1);
+        inst = __shfl_sync(kFull, inst, 0);
+        if (inst >= P.batch) break;
+        const typename F::Vec x0 = F::load_x(ctx, P.x0 + (size_t)inst * xl);
+        const typename F::CVec y0 = F::load_y(ctx, P.y0 + (size_t)inst * P.m);
+        if (MODE == 0) {
+            typename F::Pt pt;
+            typename F::CVec y;
+            double* tr = (P.trace != nullptr && o.trace_mode != 0)
+                             ? P.trace + (size_t)inst * o.trace_capacity * RIPTRM_TRACE_FIELDS
+                             : nullptr;
+            solve_instance<F>(ctx, o, x0, y0, pt, y, P.summary ? P.summary + (size_t)inst * RIPTRM_SUMMARY_FIELDS : nullptr,
+                              tr, nullptr, false, -1);
+            if (P.x) F::store_x(ctx, P.x + (size_t)inst * xl, pt.x);
+            if (P.y) F::store_y(ctx, P.y + (size_t)inst * P.m, y);
+        } else {
+            typename F::Pt pt;
+            F::eval_point(ctx, x0, pt);
+            typename F::Step st;
+            F::begin_step(ctx, pt, y0, P.mu, st);
+            if (MODE == 1) {
+                const typename F::Vec v = F::load_x(ctx, P.v + (size_t)inst * xl);
+                const typename F::Vec hv = F::Hw(ctx, pt, y0, st, v);
+                F::store_x(ctx, P.out + (size_t)inst * xl, hv);
+            } else {
+                typename F::Vec eta, Heta;
+                const TcgResult r = F::tcg(ctx, o, pt, y0, st, P.Delta, eta, Heta);
+                F::store_x(ctx, P.out + (size_t)inst * xl, eta);
+                const double nrm = sqrt(F::inner(ctx, pt, eta, eta));
+                if (P.info != nullptr && lane < 4) {
+                    const double val = (lane == 0) ? (double)r.iters : (lane == 1) ? (double)r.stop : (lane == 2) ? nrm : r.model_value;
+                    P.info[(size_t)inst * 4 + lane] = val;
+                }
+            }
+        }
+    }
+}
+
+template <class F, int MODE>
+static int launch_small(riptrm_handle* h, const SmallParams& P, const DevOpts& o, cudaStream_t st) {
+    auto kern = small_kernel<F, MODE>;
+    const size_t smem = (size_t)F::kScratchDoubles * sizeof(double);
+    int grid = h->num_sms * 8;
+    if (grid > h->batch) grid = h->batch;
+    CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
+    CUDA_TRY(cudaEventRecord(h->ev0, st));
+    kern<<<grid, 32, smem, st>>>(P, o, h->d_counter);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->ev1, st));
+    h->launches += 1;
+    return RIPTRM_OK;
+}
+
+static int dispatch_small(riptrm_handle* h, int mode, const SmallParams& P, const DevOpts& o, cudaStream_t st) {
+    if (h->family == RIPTRM_FAMILY_ROSENBROCK_GRASSMANN) {
+        if (mode == 0) return launch_small<GrassmannFam, 0>(h, P, o, st);
+        if (mode == 1) return launch_small<GrassmannFam, 1>(h, P, o, st);
+        return launch_small<GrassmannFam, 2>(h, P, o, st);
+    }
+    return fail(RIPTRM_E_UNSUPPORTED, "family not built into this library");
+}
+
+static SmallParams small_params(const riptrm_handle* h) {
+    SmallParams P{};
+    P.n = h->n;
+    P.p = h->p;
+    P.m = h->m;
+    P.batch = h->batch;
+    P.alpha = h->ros_alpha;
+    P.offset = h->ros_offset;
+    return P;
+}
+
 // One launch, or two with the pairs re-ordered in between (see solve_instance): `schedule_split` outer
 // iterations for every pair first, then the rest, longest first.  Bit-identical results either way.
 static int solve_scheduled(riptrm_handle* h, SphereParams P, const DevOpts& o, cudaStream_t st) {
@@ -670,6 +781,7 @@ extern "C" int riptrm_solve(riptrm_handle* h, const double* x0, const double* y0
     const size_t xb = B * h->vec_len * sizeof(double), yb = B * h->m * sizeof(double);
     const size_t sb = B * RIPTRM_SUMMARY_FIELDS * sizeof(double);
     const size_t tb = (h->opts.trace_mode != 0) ? B * (size_t)h->opts.trace_capacity * RIPTRM_TRACE_FIELDS * sizeof(double) : 0;
+    const bool small = (h->family == RIPTRM_FAMILY_ROSENBROCK_GRASSMANN || h->family == RIPTRM_FAMILY_STABLEID_PRODUCT);
     SphereParams P{};
     P.Z = h->dZ;
     P.batch_z = h->batch_z;
@@ -677,6 +789,11 @@ extern "C" int riptrm_solve(riptrm_handle* h, const double* x0, const double* y0
     P.batch = h->batch;
     P.eps = h->eps;
     const DevOpts o = make_devopts(h);
+    if (small && where == RIPTRM_DEVICE) {
+        SmallParams Q = small_params(h);
+        Q.x0 = x0; Q.y0 = y0; Q.x = x; Q.y = y; Q.summary = summary; Q.trace = trace;
+        return dispatch_small(h, 0, Q, o, st);
+    }
     if (where == RIPTRM_DEVICE) {
         P.x0 = x0;
         P.y0 = y0;
@@ -703,7 +820,13 @@ extern "C" int riptrm_solve(riptrm_handle* h, const double* x0, const double* y0
     P.y = h->d_y;
     P.summary = h->d_summary;
     P.trace = (tb != 0 && trace != nullptr) ? h->d_trace : nullptr;
-    if ((rc = solve_scheduled(h, P, o, st))) return rc;
+    if (small) {
+        SmallParams Q = small_params(h);
+        Q.x0 = P.x0; Q.y0 = P.y0; Q.x = P.x; Q.y = P.y; Q.summary = P.summary; Q.trace = P.trace;
+        if ((rc = dispatch_small(h, 0, Q, o, st))) return rc;
+    } else if ((rc = solve_scheduled(h, P, o, st))) {
+        return rc;
+    }
     if (x) CUDA_TRY(cudaMemcpyAsync(x, h->d_x, xb, cudaMemcpyDeviceToHost, st));
     if (y) CUDA_TRY(cudaMemcpyAsync(y, h->d_y, yb, cudaMemcpyDeviceToHost, st));
     if (summary) CUDA_TRY(cudaMemcpyAsync(summary, h->d_summary, sb, cudaMemcpyDeviceToHost, st));
@@ -733,7 +856,13 @@ static int run_hook(riptrm_handle* h, int mode, const double* x, const double* y
     if (h->have_opts) o = make_devopts(h);
     else { o.tcg_maxinner = -1; o.tcg_theta = 1.0; o.tcg_kappa = 0.1; o.tcg_mininner = 1; }
     int rc;
+    const bool small = (h->family == RIPTRM_FAMILY_ROSENBROCK_GRASSMANN || h->family == RIPTRM_FAMILY_STABLEID_PRODUCT);
     if (where == RIPTRM_DEVICE) {
+        if (small) {
+            SmallParams Q = small_params(h);
+            Q.x0 = x; Q.y0 = y; Q.v = v; Q.out = out; Q.info = info; Q.mu = mu; Q.Delta = Delta;
+            return dispatch_small(h, mode, Q, o, st);
+        }
         P.x0 = x; P.y0 = y; P.v = v; P.out = out; P.info = info;
         return mode == 1 ? dispatch_sphere<1>(h, P, o, st) : dispatch_sphere<2>(h, P, o, st);
     }
@@ -744,7 +873,12 @@ static int run_hook(riptrm_handle* h, int mode, const double* x, const double* y
     CUDA_TRY(cudaMemcpyAsync(h->d_y0, y, yb, cudaMemcpyHostToDevice, st));
     if (v) CUDA_TRY(cudaMemcpyAsync(h->d_v, v, xb, cudaMemcpyHostToDevice, st));
     P.x0 = h->d_x0; P.y0 = h->d_y0; P.v = h->d_v; P.out = h->d_x; P.info = info ? h->d_info : nullptr;
-    rc = mode == 1 ? dispatch_sphere<1>(h, P, o, st) : dispatch_sphere<2>(h, P, o, st);
+    if (small) {
+        SmallParams Q = small_params(h);
+        Q.x0 = P.x0; Q.y0 = P.y0; Q.v = P.v; Q.out = P.out; Q.info = P.info; Q.mu = mu; Q.Delta = Delta;
+        rc = dispatch_small(h, mode, Q, o, st);
+    } else
+        rc = mode == 1 ? dispatch_sphere<1>(h, P, o, st) : dispatch_sphere<2>(h, P, o, st);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(out, h->d_x, xb, cudaMemcpyDeviceToHost, st));
     if (info) CUDA_TRY(cudaMemcpyAsync(info, h->d_info, ib, cudaMemcpyDeviceToHost, st));
