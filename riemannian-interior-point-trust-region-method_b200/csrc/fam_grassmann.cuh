@@ -44,6 +44,7 @@ struct GrassmannFam {
     };
 
     static constexpr int kScratchDoubles = 6 * 32;
+    static constexpr int smem_doubles(int, int) { return kScratchDoubles; }
     static constexpr int kComponents = 1;
     template <class Params>
     static __device__ __forceinline__ Ctx make_ctx(const Params& P, const DevOpts& o, double* smem) {

@@ -1,0 +1,420 @@
+// fam_stableid.cuh -- the reference's StableIdentification workload: fit A = (J - R) Q to trajectory data on
+// Product[SkewSymmetric(d), SPD(d), SPD(d)] with box / "two-box" constraints on entries of A
+// (src/StableIdentification/coordinator.py:34-179; closed forms SURVEY.md App. A.3, manifold formulas App. B).
+//
+//   f(J,R,Q) = tr(E E') / N,  E = X' - (I + h A) X                                          (:92-98)
+//   G_A = df/dA = -2h E X'/N ;  along (dJ,dR,dQ): dA = (dJ-dR) Q + (J-R) dQ,  dG_A = 2h^2 dA (X X')/N
+//   chain rule for any phi(A) with Phi = dphi/dA:  d/dJ = Phi Q', d/dR = -Phi Q', d/dQ = (J-R)' Phi
+//   constraints (:108-152), Phi_i = coef_i E_{rc}:  g = -A_rc + a (coef -1) | A_rc - a (coef +1) |
+//                                                   -(A_rc - a)^2 + b (coef -2 (A_rc - a), d coef = -2 dA_rc)
+//   Riemannian conversions: Skew: skew(.) ; SPD (affine-invariant metric): rgrad = P sym(eg) P,
+//   rhess = P sym(eh) P + sym(V sym(eg) P), <A,B>_P = tr(P^-1 A P^-1 B), retraction sym(P + V + V P^-1 V / 2).
+//
+// The conversions are linear in (egrad, ehess), so Hess L[v] is formed from the Euclidean gradient / Hessian of
+// the Lagrangian (Phi_L = G_A + sum_i y_i Phi_i), which is the reference's `do_euclidean_lincomb` form
+// (RIPTRM.py:497-517) and equals its default per-constraint sum up to rounding.  With tangent v,
+//   G*_x[v]_i = <grad s_i, v>_x = -coef_i dA_rc      (the SPD metric cancels against P sym(eg) P)
+//   G_x(w)    = -rgrad( pull( sum_i w_i Phi_i ) ).
+//
+// One warp per instance.  A point / tangent vector is WVec<3>: slot k = component (J, R, Q), entry (i,j) of the
+// d x d matrix on lane i*d + j (d*d <= 32); constraint i lives on lane i (m <= 32).  Products go through the warp's
+// shared-memory scratch (smallmat.cuh); X, X' and X X' are staged once per CTA.
+#pragma once
+#include "smallmat.cuh"
+#include "solver_warp.cuh"
+
+namespace riptrm {
+
+struct StableIdFam {
+    static constexpr int K = 3;
+    static constexpr int MK = 1;
+    static constexpr int DMAX = 5;
+    static constexpr int kComponents = 3;
+    static constexpr int kSlots = 8;
+    using Vec = WVec<3>;
+    using CVec = WVec<1>;
+    using LM = double;  // "lane matrix": a d x d matrix with one entry per lane
+
+    struct Ctx {
+        int d, dd, m, N;
+        double h;
+        bool embedded;
+        const double* X;    // shared memory [d][N]
+        const double* XP;   // shared memory [d][N]
+        const double* XXt;  // shared memory [d][d]
+        double* sc;         // scratch: kSlots slots of 32 doubles + E [d][N]
+        double* E;
+        // this lane's constraint (lane < m)
+        int kind, rc;
+        double ca, cb;
+    };
+    struct Pt {
+        Vec x;
+        CVec s;
+        double cost;
+        LM A, GA, JmR;       // (J-R) Q, df/dA, J - R
+        LM Rinv, Qinv;
+        CVec coef;           // Phi_i = coef_i E_rc
+        bool spd_ok;
+    };
+    struct Step {
+        Vec c;
+        CVec ys;
+        LM PhiL;             // G_A + sum_i y_i Phi_i
+    };
+
+    static constexpr int smem_doubles(int d, int N) { return kSlots * 32 + 3 * d * N + d * d; }
+
+    template <class Params>
+    static __device__ __forceinline__ Ctx make_ctx(const Params& P, const DevOpts& o, double* smem) {
+        Ctx c;
+        c.d = P.n;
+        c.dd = P.n * P.n;
+        c.m = P.m;
+        c.N = P.N;
+        c.h = P.hstep;
+        c.embedded = o.is_euclidean_embedded != 0;
+        c.sc = smem;
+        double* X = smem + kSlots * 32;
+        double* XP = X + c.d * c.N;
+        c.E = XP + c.d * c.N;
+        double* XXt = c.E + c.d * c.N;
+        for (int e = lane_id(); e < c.d * c.N; e += 32) {
+            X[e] = P.Xd[e];
+            XP[e] = P.XPd[e];
+        }
+        __syncwarp();
+        sm::mm(XXt, X, X, c.d, c.N, c.d, false, true);
+        c.X = X;
+        c.XP = XP;
+        c.XXt = XXt;
+        c.kind = 0;
+        c.rc = 0;
+        c.ca = c.cb = 0.0;
+        if (lane_id() < c.m) {
+            const double* row = P.conspec + lane_id() * 5;
+            c.kind = (int)row[0];
+            c.rc = (int)row[1] * c.d + (int)row[2];
+            c.ca = row[3];
+            c.cb = row[4];
+        }
+        return c;
+    }
+
+    static __device__ __forceinline__ double* slot(const Ctx& c, int i) { return c.sc + 32 * i; }
+    static __device__ __forceinline__ bool on(const Ctx& c) { return lane_id() < c.dd; }
+    static __device__ __forceinline__ bool active(const Ctx& c, int) { return on(c); }
+    static __device__ __forceinline__ bool cactive(const Ctx& c, int) { return lane_id() < c.m; }
+    static __device__ __forceinline__ int dim(const Ctx& c) { return c.d * (c.d - 1) / 2 + c.d * (c.d + 1); }
+    static __device__ __forceinline__ int num_constraints(const Ctx& c) { return c.m; }
+    static __device__ __forceinline__ double typical_dist(const Ctx& c) { return sqrt((double)dim(c)); }
+    static __device__ __forceinline__ bool domain_ok(const Ctx&, const Pt&) { return true; }
+
+    static __device__ __forceinline__ Vec load_x(const Ctx& c, const double* g) {
+        Vec r;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) r.v[k] = on(c) ? g[k * c.dd + lane_id()] : 0.0;
+        return r;
+    }
+    static __device__ __forceinline__ void store_x(const Ctx& c, double* g, const Vec& v) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (on(c)) g[k * c.dd + lane_id()] = v.v[k];
+    }
+    static __device__ __forceinline__ CVec load_y(const Ctx& c, const double* g) {
+        CVec r;
+        r.v[0] = (lane_id() < c.m) ? g[lane_id()] : 0.0;
+        return r;
+    }
+    static __device__ __forceinline__ void store_y(const Ctx& c, double* g, const CVec& v) {
+        if (lane_id() < c.m) g[lane_id()] = v.v[0];
+    }
+
+    // ---- lane-matrix helpers ---------------------------------------------------------------------------
+    static __device__ __forceinline__ void put(const Ctx& c, int s, LM a) {
+        slot(c, s)[lane_id()] = a;
+        __syncwarp();
+    }
+    // op(A) op(B) for d x d lane matrices
+    static __device__ __forceinline__ LM mul(const Ctx& c, LM a, LM b, bool tA = false, bool tB = false) {
+        put(c, 0, a);
+        put(c, 1, b);
+        const int l = lane_id(), d = c.d;
+        double s = 0.0;
+        if (l < c.dd) {
+            const int i = l / d, j = l - i * d;
+            const double* A = slot(c, 0);
+            const double* B = slot(c, 1);
+            for (int k = 0; k < d; ++k) s = fma(tA ? A[k * d + i] : A[i * d + k], tB ? B[j * d + k] : B[k * d + j], s);
+        }
+        __syncwarp();
+        return s;
+    }
+    static __device__ __forceinline__ LM transpose(const Ctx& c, LM a) {
+        put(c, 0, a);
+        const int l = lane_id(), d = c.d;
+        double r = 0.0;
+        if (l < c.dd) {
+            const int i = l / d, j = l - i * d;
+            r = slot(c, 0)[j * d + i];
+        }
+        __syncwarp();
+        return r;
+    }
+    static __device__ __forceinline__ LM symm(const Ctx& c, LM a) { return 0.5 * (a + transpose(c, a)); }
+    static __device__ __forceinline__ LM skew(const Ctx& c, LM a) { return 0.5 * (a - transpose(c, a)); }
+    static __device__ __forceinline__ LM inverse(const Ctx& c, LM a, bool& ok) {
+        put(c, 2, a);
+        ok = sm::inverse<DMAX>(slot(c, 3), slot(c, 2), c.d);
+        const double r = (on(c) && ok) ? slot(c, 3)[lane_id()] : 0.0;
+        __syncwarp();
+        return r;
+    }
+    // sum_i w_i coef_i E_{r_i c_i} (+ base) as a lane matrix; contributions added in constraint order
+    static __device__ __forceinline__ LM scatter(const Ctx& c, const CVec& w, const CVec& coef, LM base) {
+        double* P = slot(c, 4);
+        double* wc = slot(c, 5);
+        int* rc = reinterpret_cast<int*>(slot(c, 6));
+        P[lane_id()] = base;
+        wc[lane_id()] = (lane_id() < c.m) ? w.v[0] * coef.v[0] : 0.0;
+        rc[lane_id()] = c.rc;
+        __syncwarp();
+        if (lane_id() == 0)
+            for (int i = 0; i < c.m; ++i) P[rc[i]] = P[rc[i]] + wc[i];
+        __syncwarp();
+        const double r = on(c) ? P[lane_id()] : 0.0;
+        __syncwarp();
+        return r;
+    }
+    // value of a lane matrix at this lane's constraint entry (r_i, c_i)
+    static __device__ __forceinline__ double at_constraint(const Ctx& c, LM a) {
+        put(c, 0, a);
+        const double r = (lane_id() < c.m) ? slot(c, 0)[c.rc] : 0.0;
+        __syncwarp();
+        return r;
+    }
+
+    // Euclidean -> Riemannian gradient, componentwise
+    static __device__ __forceinline__ Vec egrad2rgrad(const Ctx& c, const Pt& pt, LM egJ, LM egR, LM egQ) {
+        Vec r;
+        r.v[0] = skew(c, egJ);
+        r.v[1] = mul(c, mul(c, pt.x.v[1], symm(c, egR)), pt.x.v[1]);
+        r.v[2] = mul(c, mul(c, pt.x.v[2], symm(c, egQ)), pt.x.v[2]);
+        return r;
+    }
+    // pull(Phi) = [Phi Q', -Phi Q', (J-R)' Phi], then egrad2rgrad
+    static __device__ __forceinline__ Vec rgrad_of_phi(const Ctx& c, const Pt& pt, LM Phi) {
+        const LM gJ = mul(c, Phi, pt.x.v[2], false, true);
+        const LM gQ = mul(c, pt.JmR, Phi, true, false);
+        return egrad2rgrad(c, pt, gJ, -gJ, gQ);
+    }
+
+    static __device__ __forceinline__ void eval_point(const Ctx& c, const Vec& x, Pt& pt) {
+        pt.x = x;
+        pt.JmR = x.v[0] - x.v[1];
+        pt.A = mul(c, pt.JmR, x.v[2]);
+        // E = X' - (I + h A) X  (d x N), cost = tr(E E')/N, G_A = -2h E X'/N
+        put(c, 2, pt.A);
+        const double* A = slot(c, 2);
+        const int d = c.d, N = c.N;
+        double part = 0.0;
+        for (int e = lane_id(); e < d * N; e += 32) {
+            const int i = e / N, t = e - i * N;
+            double ax = 0.0;
+            for (int k = 0; k < d; ++k) ax = fma(((i == k) ? 1.0 : 0.0) + c.h * A[i * d + k], c.X[k * N + t], ax);
+            const double ev = c.XP[e] - ax;
+            c.E[e] = ev;
+            part = fma(ev, ev, part);
+        }
+        __syncwarp();
+        pt.cost = wsum(part) / (double)N;
+        double ga = 0.0;
+        if (on(c)) {
+            const int i = lane_id() / d, j = lane_id() - i * d;
+            double s = 0.0;
+            for (int t = 0; t < N; ++t) s = fma(c.E[i * N + t], c.X[j * N + t], s);
+            ga = (-2.0 * c.h) * s / (double)N;
+        }
+        __syncwarp();
+        pt.GA = ga;
+        // constraints
+        const double Arc = at_constraint(c, pt.A);
+        double g = 0.0, coef = 0.0;
+        if (lane_id() < c.m) {
+            if (c.kind == 0) {
+                g = -Arc + c.ca;
+                coef = -1.0;
+            } else if (c.kind == 1) {
+                g = Arc - c.ca;
+                coef = 1.0;
+            } else {
+                g = -((Arc - c.ca) * (Arc - c.ca)) + c.cb;
+                coef = -2.0 * (Arc - c.ca);
+            }
+        }
+        pt.s.v[0] = -g;
+        pt.coef.v[0] = coef;
+        bool okR, okQ;
+        pt.Rinv = inverse(c, x.v[1], okR);
+        pt.Qinv = inverse(c, x.v[2], okQ);
+        put(c, 2, x.v[1]);
+        const bool pdR = sm::is_spd<DMAX>(slot(c, 2), c.d);
+        __syncwarp();
+        put(c, 2, x.v[2]);
+        const bool pdQ = sm::is_spd<DMAX>(slot(c, 2), c.d);
+        __syncwarp();
+        pt.spd_ok = okR && okQ && pdR && pdQ;
+    }
+
+    // <a, b>_x = <aJ, bJ> + tr(R^-1 aR R^-1 bR) + tr(Q^-1 aQ Q^-1 bQ): per-lane partial
+    static __device__ __forceinline__ double inner_partial(const Ctx& c, const Pt& pt, const Vec& a, const Vec& b) {
+        const LM tR = mul(c, mul(c, pt.Rinv, a.v[1]), pt.Rinv);
+        const LM tQ = mul(c, mul(c, pt.Qinv, a.v[2]), pt.Qinv);
+        const LM bRt = transpose(c, b.v[1]), bQt = transpose(c, b.v[2]);
+        return (a.v[0] * b.v[0] + tR * bRt) + tQ * bQt;
+    }
+    static __device__ __forceinline__ double inner(const Ctx& c, const Pt& pt, const Vec& a, const Vec& b) {
+        return wsum(inner_partial(c, pt, a, b));
+    }
+
+    static __device__ __forceinline__ Vec project(const Ctx& c, const Pt&, const Vec& v) {
+        Vec r;
+        r.v[0] = skew(c, v.v[0]);
+        r.v[1] = symm(c, v.v[1]);
+        r.v[2] = symm(c, v.v[2]);
+        return r;
+    }
+
+    static __device__ __forceinline__ void begin_step(const Ctx& c, const Pt& pt, const CVec& y, double mu, Step& st) {
+        CVec w;
+        const bool onc = cactive(c, 0);
+        w.v[0] = onc ? mu * (1.0 / pt.s.v[0]) : 0.0;
+        st.ys.v[0] = onc ? y.v[0] / pt.s.v[0] : 0.0;
+        st.PhiL = scatter(c, y, pt.coef, pt.GA);
+        const Vec gradf = rgrad_of_phi(c, pt, pt.GA);
+        const Vec gw = rgrad_of_phi(c, pt, scatter(c, w, pt.coef, 0.0));  // = -G_x(mu/s)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) st.c.v[k] = gradf.v[k] + gw.v[k];      // grad f - G_x(mu/s)
+    }
+
+    // dA along v
+    static __device__ __forceinline__ LM dA_of(const Ctx& c, const Pt& pt, const Vec& v) {
+        return mul(c, v.v[0] - v.v[1], pt.x.v[2]) + mul(c, pt.JmR, v.v[2]);
+    }
+
+    static __device__ __forceinline__ CVec gadj(const Ctx& c, const Pt& pt, const Vec& v) {
+        CVec g;
+        g.v[0] = -pt.coef.v[0] * at_constraint(c, dA_of(c, pt, v));
+        return g;
+    }
+
+    static __device__ __forceinline__ Vec Hw(const Ctx& c, const Pt& pt, const CVec& y, const Step& st, const Vec& v) {
+        const LM dA = dA_of(c, pt, v);
+        // Euclidean Hessian of the Lagrangian along v: dPhi_L = dG_A + sum_i y_i dcoef_i E_rc
+        put(c, 7, dA);
+        double dga = 0.0;
+        if (on(c)) {
+            const int d = c.d, i = lane_id() / d, j = lane_id() - i * d;
+            double s = 0.0;
+            for (int k = 0; k < d; ++k) s = fma(slot(c, 7)[i * d + k], c.XXt[k * d + j], s);
+            dga = (2.0 * c.h * c.h) * s / (double)c.N;
+        }
+        __syncwarp();
+        const double dArc = at_constraint(c, dA);
+        CVec dcoef, ones;
+        dcoef.v[0] = (lane_id() < c.m && c.kind == 2) ? -2.0 * dArc : 0.0;
+        ones.v[0] = 1.0;
+        CVec ydc;
+        ydc.v[0] = y.v[0] * dcoef.v[0];
+        const LM dPhiL = scatter(c, ydc, ones, dga);
+        const LM Qt_dummy = 0.0;
+        (void)Qt_dummy;
+        // pull_d: hJ = dPhi Q' + Phi dQ' ; hR = -hJ ; hQ = (dJ - dR)' Phi + (J - R)' dPhi
+        const LM hJ = mul(c, dPhiL, pt.x.v[2], false, true) + mul(c, st.PhiL, v.v[2], false, true);
+        const LM hQ = mul(c, v.v[0] - v.v[1], st.PhiL, true, false) + mul(c, pt.JmR, dPhiL, true, false);
+        // Euclidean gradient of the Lagrangian
+        const LM gJ = mul(c, st.PhiL, pt.x.v[2], false, true);
+        const LM gQ = mul(c, pt.JmR, st.PhiL, true, false);
+        Vec hl;
+        hl.v[0] = skew(c, hJ);
+        {
+            const LM R = pt.x.v[1];
+            hl.v[1] = mul(c, mul(c, R, symm(c, -hJ)), R) + symm(c, mul(c, mul(c, v.v[1], symm(c, -gJ)), R));
+            const LM Q = pt.x.v[2];
+            hl.v[2] = mul(c, mul(c, Q, symm(c, hQ)), Q) + symm(c, mul(c, mul(c, v.v[2], symm(c, gQ)), Q));
+        }
+        // condensed barrier term G_x((y/s) * G*[v]) = -rgrad(pull(sum_i w_i Phi_i))
+        CVec w;
+        w.v[0] = st.ys.v[0] * (-pt.coef.v[0] * dArc);
+        const Vec gw = rgrad_of_phi(c, pt, scatter(c, w, pt.coef, 0.0));
+        Vec out;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) out.v[k] = hl.v[k] - gw.v[k];
+        return out;
+    }
+
+    static __device__ __forceinline__ TcgResult tcg(const Ctx& ctx, const DevOpts& o, const Pt& pt, const CVec& y,
+                                                    const Step& st, double Delta, Vec& eta, Vec& Heta) {
+        return tcg_generic<StableIdFam>(ctx, o, pt, y, st, Delta, eta, Heta);
+    }
+
+    static __device__ __forceinline__ Vec retract(const Ctx& c, const Pt& pt, const Vec& dx) {
+        Vec r;
+        r.v[0] = pt.x.v[0] + dx.v[0];
+        r.v[1] = symm(c, (pt.x.v[1] + dx.v[1]) + mul(c, dx.v[1], mul(c, pt.Rinv, dx.v[1])) / 2.0);
+        r.v[2] = symm(c, (pt.x.v[2] + dx.v[2]) + mul(c, dx.v[2], mul(c, pt.Qinv, dx.v[2])) / 2.0);
+        return r;
+    }
+
+    static __device__ __forceinline__ double gradL_xy_partial(const Ctx&, const Pt&, const CVec&) { return 0.0; }
+    static __device__ __forceinline__ double gradL_norm_given(const Ctx& c, const Pt& pt, const CVec& y, double) {
+        const Vec g = rgrad_of_phi(c, pt, scatter(c, y, pt.coef, pt.GA));
+        return sqrt(inner(c, pt, g, g));
+    }
+    static __device__ __forceinline__ double gradL_norm(const Ctx& c, const Pt& pt, const CVec& y) {
+        return gradL_norm_given(c, pt, y, 0.0);
+    }
+
+    // src/StableIdentification/simulator.py:11-33
+    static __device__ __forceinline__ double manvio(const Ctx& c, const Pt& pt) {
+        const LM a = pt.x.v[0] + transpose(c, pt.x.v[0]);
+        const LM b = pt.x.v[1] - transpose(c, pt.x.v[1]);
+        const LM q = pt.x.v[2] - transpose(c, pt.x.v[2]);
+        double pa = a * a, pb = b * b, pq = q * q;
+        wsum3(pa, pb, pq);
+        const double v = (sqrt(pa) + sqrt(pb)) + sqrt(pq);
+        return pt.spd_ok ? v : CUDART_INF;
+    }
+
+    // eigenvalues of P^{-1/2} B P^{-1/2} (= those of chol(P)^-1 B chol(P)^-T): || log w ||
+    static __device__ __forceinline__ double spd_dist(const Ctx& c, LM P, LM B) {
+        put(c, 2, P);
+        double w[DMAX], V[DMAX][DMAX];
+        sm::jacobi_eig<DMAX>(slot(c, 2), c.d, w, V);
+        __syncwarp();
+        double ih = 0.0;
+        if (on(c)) {
+            const int d = c.d, i = lane_id() / d, j = lane_id() - i * d;
+            for (int k = 0; k < d; ++k) ih = fma(V[i][k] * (1.0 / sqrt(w[k])), V[j][k], ih);
+        }
+        const LM M = symm(c, mul(c, mul(c, ih, B), ih));
+        put(c, 2, M);
+        sm::jacobi_eig<DMAX>(slot(c, 2), c.d, w, V);
+        __syncwarp();
+        double acc = 0.0;
+        for (int k = 0; k < c.d; ++k) {
+            const double lg = log(w[k]);
+            acc += lg * lg;
+        }
+        return sqrt(acc);
+    }
+    static __device__ __forceinline__ double dist(const Ctx& c, const Vec& xPrev, const Pt& pt) {
+        const double dj = xPrev.v[0] - pt.x.v[0];
+        const double nJ = sqrt(wsum(dj * dj));
+        const double nR = spd_dist(c, xPrev.v[1], pt.x.v[1]);
+        const double nQ = spd_dist(c, xPrev.v[2], pt.x.v[2]);
+        return sqrt((nJ * nJ + nR * nR) + nQ * nQ);
+    }
+};
+
+}  // namespace riptrm

@@ -19,6 +19,7 @@
 #include "fam_columns.cuh"
 #include "fam_grassmann.cuh"
 #include "fam_sphere.cuh"
+#include "fam_stableid.cuh"
 
 using namespace riptrm;
 
@@ -52,6 +53,9 @@ struct riptrm_handle {
     int batch_z = 0;
     double eps = 0.0;
     double ros_alpha = 0.0, ros_offset = 0.0;
+    double* d_sid = nullptr;  // StableIdentification: X [d][N], XP [d][N], conspec [m][5]
+    int sid_N = 0;
+    double sid_h = 0.0;
     bool have_problem = false;
     // options
     riptrm_options opts{};
@@ -232,6 +236,8 @@ extern "C" int riptrm_create(int family, int n, int p, int m, int batch, int dev
     } else if (family == RIPTRM_FAMILY_ROSENBROCK_GRASSMANN) {
         if (n * p > 32 || p > GrassmannFam::PMAX || p > n) return fail(RIPTRM_E_UNSUPPORTED, "Grassmann family: n*p <= 32, p <= 5");
         if (m != n * p) return fail(RIPTRM_E_INVALID, "Rosenbrock/Grassmann needs m == n * p");
+    } else if (family == RIPTRM_FAMILY_STABLEID_PRODUCT) {
+        if (p != 3 || n > StableIdFam::DMAX || m > 32) return fail(RIPTRM_E_UNSUPPORTED, "StableIdentification family: p == 3 blocks, d <= 5, m <= 32");
     } else if (family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS) {
         if (batch != 1) return fail(RIPTRM_E_INVALID, "COLUMNS family: batch must be 1 (the p columns are the batch)");
         if (m != n * p) return fail(RIPTRM_E_INVALID, "COLUMNS family needs m == n * p");
@@ -250,7 +256,7 @@ extern "C" int riptrm_create(int family, int n, int p, int m, int batch, int dev
     h->m = m;
     h->batch = batch;
     h->device = device;
-    h->vec_len = n * p;
+    h->vec_len = (family == RIPTRM_FAMILY_STABLEID_PRODUCT) ? 3 * n * n : n * p;
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
@@ -282,6 +288,7 @@ extern "C" int riptrm_destroy(riptrm_handle* h) {
     free_dev(h->dS);
     free_dev(h->d_colbuf);
     free_dev(h->d_pause);
+    free_dev(h->d_sid);
     if (h->d_keys) cudaFree(h->d_keys);
     if (h->d_keys_sorted) cudaFree(h->d_keys_sorted);
     if (h->d_idx) cudaFree(h->d_idx);
@@ -501,8 +508,28 @@ extern "C" int riptrm_set_rosenbrock(riptrm_handle* h, double alpha, double offs
     h->have_problem = true;
     return RIPTRM_OK;
 }
-extern "C" int riptrm_set_stableid(riptrm_handle*, const double*, const double*, int, double, const double*, int, int) {
-    return fail(RIPTRM_E_UNSUPPORTED, "StableIdentification family not built into this library");
+extern "C" int riptrm_set_stableid(riptrm_handle* h, const double* X, const double* XP, int N, double hstep,
+                                   const double* conspec, int m, int where) {
+    if (h == nullptr || X == nullptr || XP == nullptr || conspec == nullptr) return fail(RIPTRM_E_INVALID, "NULL argument");
+    if (h->family != RIPTRM_FAMILY_STABLEID_PRODUCT) return fail(RIPTRM_E_INVALID, "handle is not the StableIdentification family");
+    if (m != h->m || N <= 0) return fail(RIPTRM_E_INVALID, "m must match riptrm_create, N > 0");
+    for (int i = 0; where != RIPTRM_DEVICE && i < m; ++i) {
+        const double* r = conspec + 5 * i;
+        if (!(r[0] == 0 || r[0] == 1 || r[0] == 2) || r[1] < 0 || r[1] >= h->n || r[2] < 0 || r[2] >= h->n)
+            return fail(RIPTRM_E_INVALID, "conspec row: kind in {0,1,2}, 0 <= row, col < d");
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t dn = (size_t)h->n * N;
+    free_dev(h->d_sid);
+    CUDA_TRY(cudaMalloc(&h->d_sid, (2 * dn + 5 * (size_t)m) * sizeof(double)));
+    const cudaMemcpyKind kind = (where == RIPTRM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CUDA_TRY(cudaMemcpy(h->d_sid, X, dn * sizeof(double), kind));
+    CUDA_TRY(cudaMemcpy(h->d_sid + dn, XP, dn * sizeof(double), kind));
+    CUDA_TRY(cudaMemcpy(h->d_sid + 2 * dn, conspec, 5 * (size_t)m * sizeof(double), kind));
+    h->sid_N = N;
+    h->sid_h = hstep;
+    h->have_problem = true;
+    return RIPTRM_OK;
 }
 
 extern "C" int riptrm_set_options(riptrm_handle* h, const riptrm_options* o) {
@@ -619,6 +646,9 @@ static int finish_timing(riptrm_handle* h, bool sync) {
 struct SmallParams {
     int n, p, m, batch;
     double alpha, offset;  // Rosenbrock
+    const double *Xd, *XPd, *conspec;  // StableIdentification
+    int N;
+    double hstep;
     const double* x0;
     const double* y0;
     double* x;
@@ -636,7 +666,7 @@ __global__ void __launch_bounds__(32) small_kernel(SmallParams P, DevOpts o, int
     extern __shared__ __align__(16) double smem[];
     typename F::Ctx ctx = F::make_ctx(P, o, smem);
     const int lane = lane_id();
-    const int xl = P.n * P.p * F::kComponents;
+    const int xl = (F::kComponents == 1) ? P.n * P.p : P.n * P.n * F::kComponents;
     while (true) {
         int inst = 0;
         if (lane == 0) inst = atomicAdd(counter, 1);
@@ -680,7 +710,8 @@ __global__ void __launch_bounds__(32) small_kernel(SmallParams P, DevOpts o, int
 template <class F, int MODE>
 static int launch_small(riptrm_handle* h, const SmallParams& P, const DevOpts& o, cudaStream_t st) {
     auto kern = small_kernel<F, MODE>;
-    const size_t smem = (size_t)F::kScratchDoubles * sizeof(double);
+    const size_t smem = (size_t)F::smem_doubles(P.n, P.N) * sizeof(double);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = h->num_sms * 8;
     if (grid > h->batch) grid = h->batch;
     CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
@@ -698,6 +729,12 @@ static int dispatch_small(riptrm_handle* h, int mode, const SmallParams& P, cons
         if (mode == 1) return launch_small<GrassmannFam, 1>(h, P, o, st);
         return launch_small<GrassmannFam, 2>(h, P, o, st);
     }
+    if (h->family == RIPTRM_FAMILY_STABLEID_PRODUCT) {
+        if (o.is_euclidean_embedded) return fail(RIPTRM_E_UNSUPPORTED, "StableIdentification family: is_euclidean_embedded=True is not built");
+        if (mode == 0) return launch_small<StableIdFam, 0>(h, P, o, st);
+        if (mode == 1) return launch_small<StableIdFam, 1>(h, P, o, st);
+        return launch_small<StableIdFam, 2>(h, P, o, st);
+    }
     return fail(RIPTRM_E_UNSUPPORTED, "family not built into this library");
 }
 
@@ -709,6 +746,14 @@ static SmallParams small_params(const riptrm_handle* h) {
     P.batch = h->batch;
     P.alpha = h->ros_alpha;
     P.offset = h->ros_offset;
+    if (h->d_sid != nullptr) {
+        const size_t dn = (size_t)h->n * h->sid_N;
+        P.Xd = h->d_sid;
+        P.XPd = h->d_sid + dn;
+        P.conspec = h->d_sid + 2 * dn;
+        P.N = h->sid_N;
+        P.hstep = h->sid_h;
+    }
     return P;
 }
 
