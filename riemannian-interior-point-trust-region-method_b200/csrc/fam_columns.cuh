@@ -39,7 +39,7 @@ constexpr int STAGES = 5;   // shared-memory ring depth (5 x 32 KB in flight per
 constexpr int NCW = 8;      // consumer warps
 constexpr int NT = (NCW + 1) * 32;
 constexpr int MAXP = 16;
-constexpr int MAXQ = 4;     // dot products per phase and column
+constexpr int MAXQ = 10;    // reductions per phase and column (sums first, then mins)
 
 struct Params {
     int n, n_pad, ld, p;           // ld: leading dimension of S (multiple of TW); n_pad: multiple of TJ
@@ -65,6 +65,23 @@ struct Params {
     // tCG options
     int tcg_mininner, tcg_maxinner;
     double tcg_theta, tcg_kappa;
+    // whole-solve mode (riptrm_solve on this family): per-column state and the solver options
+    int solve;                     // 1: mu / Delta / activity per column come from colstate, the point cache is valid
+    double* colstate;              // [MAXP][CS_FIELDS]
+    double *XN, *YN, *SxN, *Xinit, *Yinit, *Sxinit, *Xprev;
+    const double *mu_sched, *tolL_sched, *tolC_sched;
+    int maxiter, inner_maxiter, trace_mode, trace_capacity;
+    double tolresid, initial_tr_radius, minimal_initial_tr_radius, maximal_tr_radius, rho, reduction_regularization,
+        gamma, const_left, const_right;
+    double* trace;                 // [p][trace_capacity][RIPTRM_TRACE_FIELDS] or nullptr
+    double* summary;               // [p][RIPTRM_SUMMARY_FIELDS]
+    int* all_done;                 // device flag read by the host loop
+};
+
+// per-column solver state kept in global memory between launches
+enum {
+    CS_IT = 0, CS_K, CS_DELTA, CS_XSX, CS_COST, CS_CNT_INNER, CS_CNT_TCG, CS_CNT_AUX, CS_ROWS, CS_FINISHED, CS_STOP,
+    CS_DELTA_INIT, CS_XSX_INIT, CS_COST_INIT, CS_TCG_ITERS, CS_TCG_STOP, CS_KAPPA, CS_FIELDS = 24
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -273,7 +290,7 @@ __device__ __forceinline__ void gather_scalars(const Params& prm, Smem<P>& sm, i
 
 // per-column tCG state, identical in every CTA
 struct ColState {
-    double e_Pe, e_Pd, d_Pd, z_r, r_r, norm_r0, nr_theta, target, model_value, alpha, beta, kappa, xSx, a, b, d;
+    double e_Pe, e_Pd, d_Pd, z_r, r_r, norm_r0, nr_theta, target, model_value, alpha, beta, kappa, xSx, a, b, d, mu, Delta2;
     int done, iters, stop;
 };
 
@@ -316,19 +333,36 @@ __global__ void __launch_bounds__(NT, 1) columns_kernel(Params prm) {
         return;
     }
 
+    // per-column barrier parameter / radius / activity: hook arguments, or the solver state in whole-solve mode
+    if (tid < P) {
+        cs[tid].mu = prm.mu;
+        cs[tid].Delta2 = prm.Delta * prm.Delta;
+        cs[tid].done = (tid >= prm.p) ? 1 : 0;  // padding columns (P > p) never run
+        if (prm.solve) {
+            const double* st = prm.colstate + tid * CS_FIELDS;
+            const int it = (int)st[CS_IT];
+            cs[tid].mu = prm.mu_sched[it > 0 ? it - 1 : 0];
+            cs[tid].Delta2 = st[CS_DELTA] * st[CS_DELTA];
+            if (st[CS_FINISHED] != 0.0) cs[tid].done = 1;
+        }
+    }
+    __syncthreads();
     // ---- point cache (eval_point + begin_step of fam_sphere.cuh), operand V := X -----------------------
-    FOR_ELEMS(e) prm.V[e] = prm.X[e];
-    fence_proxy_async();
-    grid.sync();
-    stream_pass<P>(prm, sm, pipe);
-    grid.sync();
+    if (!prm.solve) {
+        FOR_ELEMS(e) prm.V[e] = prm.X[e];
+        fence_proxy_async();
+        grid.sync();
+        stream_pass<P>(prm, sm, pipe);
+        grid.sync();
+    }
     {
         double part[3] = {0.0, 0.0, 0.0};
+        const double mu_c = cs[myc].mu;
         FOR_ELEMS(e) {
-            const double sx = gather_elem(prm, (int)(e / P), myc, P);
+            const double sx = prm.solve ? prm.Sx[e] : gather_elem(prm, (int)(e / P), myc, P);
             const double x = prm.X[e], y = prm.Y[e];
             const double s = x + prm.eps;
-            const double w = prm.mu * (1.0 / s);
+            const double w = mu_c * (1.0 / s);
             prm.Sx[e] = sx;
             prm.ys[e] = y / s;
             part[0] = fma(x, sx, part[0]);  // x'Sx
@@ -344,7 +378,6 @@ __global__ void __launch_bounds__(NT, 1) columns_kernel(Params prm) {
         cs[tid].xSx = sm.scal[0 * P + tid];
         cs[tid].kappa = sm.scal[0 * P + tid] + sm.scal[2 * P + tid];
         cs[tid].a = sm.scal[1 * P + tid];  // xw, used just below
-        cs[tid].done = (tid >= prm.p) ? 1 : 0;  // padding columns (P > p) never run
         cs[tid].iters = 0;
         cs[tid].stop = RIPTRM_TCG_MAX_INNER_ITER;
     }
@@ -352,11 +385,11 @@ __global__ void __launch_bounds__(NT, 1) columns_kernel(Params prm) {
     {
         // c = grad f - G_x(mu/s);  r = c, delta = -c, eta = Heta = 0;  r_r = <c, c>
         double part[1] = {0.0};
-        const double xSx = cs[myc].xSx, xw = cs[myc].a;
+        const double xSx = cs[myc].xSx, xw = cs[myc].a, mu_c = cs[myc].mu;
         FOR_ELEMS(e) {
             const double x = prm.X[e];
             const double s = x + prm.eps;
-            const double w = prm.mu * (1.0 / s);
+            const double w = mu_c * (1.0 / s);
             const double gradf = -prm.Sx[e] + xSx * x;
             const double Gw = w - xw * x;
             const double cc = gradf - Gw;
@@ -375,7 +408,6 @@ __global__ void __launch_bounds__(NT, 1) columns_kernel(Params prm) {
     }
     fence_proxy_async();
     grid.sync();
-    const double Delta2 = prm.Delta * prm.Delta;
     int maxinner = prm.tcg_maxinner < 0 ? (n - 1) : prm.tcg_maxinner;
     if (MODE == 2) {
         gather_scalars<P, 1>(prm, sm, buf);
@@ -472,9 +504,9 @@ __global__ void __launch_bounds__(NT, 1) columns_kernel(Params prm) {
                 e_Pe_new = (s.e_Pe + (2.0 * s.alpha) * s.e_Pd) + (s.alpha * s.alpha) * s.d_Pd;
             }
             s.iters = j + 1;
-            if (d_Hd <= 0.0 || e_Pe_new >= Delta2) {
+            if (d_Hd <= 0.0 || e_Pe_new >= s.Delta2) {
                 // tau solve (RIPTRM.py:123-125); alpha carries tau into the update below
-                s.alpha = (-s.e_Pd + sqrt(s.e_Pd * s.e_Pd + s.d_Pd * (Delta2 - s.e_Pe))) / s.d_Pd;
+                s.alpha = (-s.e_Pd + sqrt(s.e_Pd * s.e_Pd + s.d_Pd * (s.Delta2 - s.e_Pe))) / s.d_Pd;
                 s.stop = (d_Hd <= 0.0) ? RIPTRM_TCG_NEGATIVE_CURVATURE : RIPTRM_TCG_EXCEEDED_TR;
                 s.done = 2;  // boundary exit: commit eta + tau delta in this phase
             } else {
@@ -596,12 +628,580 @@ __global__ void __launch_bounds__(NT, 1) columns_kernel(Params prm) {
         block_reduce_store<P, 1>(prm, sm, part, buf);
         grid.sync();
         gather_scalars<P, 1>(prm, sm, buf);
+        if (prm.solve && g == 0 && tid < prm.p && prm.colstate[tid * CS_FIELDS + CS_FINISHED] == 0.0) {
+            double* st = prm.colstate + tid * CS_FIELDS;
+            st[CS_TCG_ITERS] = (double)cs[tid].iters;
+            st[CS_TCG_STOP] = (double)cs[tid].stop;
+            st[CS_KAPPA] = cs[tid].kappa;
+            st[CS_CNT_TCG] += (double)cs[tid].iters;
+        }
         if (g == 0 && tid < P && tid < prm.p && prm.info != nullptr) {
             prm.info[tid * 4 + 0] = (double)cs[tid].iters;
             prm.info[tid * 4 + 1] = (double)cs[tid].stop;
             prm.info[tid * 4 + 2] = sqrt(sm.scal[tid]);
             prm.info[tid * 4 + 3] = cs[tid].model_value;
         }
+    }
+#undef FOR_ELEMS
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Whole solve on this family: the host (riptrm_api.cu) alternates the lock-step tCG launch above with this
+// kernel, which performs everything else of one trust-region iteration for every column (RIPTRM.py:735-783,
+// :574-705) and the outer-iteration bookkeeping of columns whose inner loop ended (:785-896, utils.py:237-368),
+// with the same vector-phase machinery (fixed-order reductions, grid barriers, redundant bit-identical scalars).
+// Two S.V passes per call: S x_new for the new point's cache and S dx for the reference's extra Hw(dx) (:659).
+// INIT = true: the start of the solve instead (point cache of x0, log row 0, outer iteration 1 begins).
+// ------------------------------------------------------------------------------------------------------
+template <int P, int QS, int QM>
+__device__ __forceinline__ void reduce_store_mixed(const Params& prm, Smem<P>& sm, const double (&part)[QS + QM], int buf) {
+    constexpr int NTV = (NT / P) * P;
+#pragma unroll
+    for (int q = 0; q < QS + QM; ++q) sm.redv[q][threadIdx.x] = part[q];
+    __syncthreads();
+    if (threadIdx.x < (QS + QM) * P) {
+        const int q = threadIdx.x / P, c = threadIdx.x - q * P;
+        double s = sm.redv[q][c];
+        if (q < QS)
+            for (int i = c + P; i < NTV; i += P) s = s + sm.redv[q][i];
+        else
+            for (int i = c + P; i < NTV; i += P) s = fmin(s, sm.redv[q][i]);
+        prm.dot_part[((size_t)buf * gridDim.x + blockIdx.x) * (MAXQ * MAXP) + threadIdx.x] = s;
+    }
+}
+template <int P, int QS, int QM>
+__device__ __forceinline__ void gather_mixed(const Params& prm, Smem<P>& sm, int buf) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = gridDim.x;
+    for (int k = warp; k < (QS + QM) * P; k += NCW + 1) {
+        const bool is_sum = k < QS * P;
+        double s = is_sum ? 0.0 : CUDART_INF;
+        for (int g = lane; g < G; g += 32) {
+            const double v = prm.dot_part[((size_t)buf * G + g) * (MAXQ * MAXP) + k];
+            s = is_sum ? (s + v) : fmin(s, v);
+        }
+        s = is_sum ? wsum(s) : wmin(s);
+        if (lane == 0) sm.scal[k] = s;
+    }
+    __syncthreads();
+}
+
+struct PostState {  // per column, identical in every CTA
+    double it, k, Delta, xSx, cost, cnt_inner, cnt_tcg, cnt_aux, rows, finished, stop, Delta_init, xSx_init, cost_init;
+    double mu, tolL, tolC, kappa, normdx, nrm, bdot, xSxN, costN, minx, miny, compl_v, xy, ngl, pl_cur, pl_new, a, b, d;
+    double ared_pred, radius_update, inner_status, dual_clipping, tcg_iters, tcg_stop, DeltaNext;
+    int path;      // 0 idle (finished), 1 converged, 2 primal infeasible, 3 normal (rho test)
+    int accept, boundary, rollback;
+};
+
+template <int P, bool INIT>
+__global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem<P>& sm = *reinterpret_cast<Smem<P>*>(smem_raw);
+    __shared__ PostState ps[P];
+    cg::grid_group grid = cg::this_grid();
+    constexpr int NTV = (NT / P) * P;
+    const int g = blockIdx.x, tid = threadIdx.x, n = prm.n;
+    const int row_lo = min(n, g * prm.R), row_hi = min(n, row_lo + prm.R);
+    const size_t ebeg = (size_t)row_lo * P + tid, eend = (size_t)row_hi * P;
+    const bool vthread = tid < NTV;
+    const int myc = tid % P;
+#define FOR_ELEMS(e) for (size_t e = ebeg; vthread && e < eend; e += NTV)
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < P) {
+        PostState& s = ps[tid];
+        const double* st = prm.colstate + tid * CS_FIELDS;
+        s.it = st[CS_IT]; s.k = st[CS_K]; s.Delta = st[CS_DELTA]; s.xSx = st[CS_XSX]; s.cost = st[CS_COST];
+        s.cnt_inner = st[CS_CNT_INNER]; s.cnt_tcg = st[CS_CNT_TCG]; s.cnt_aux = st[CS_CNT_AUX]; s.rows = st[CS_ROWS];
+        s.finished = (tid >= prm.p) ? 1.0 : st[CS_FINISHED]; s.stop = st[CS_STOP];
+        s.Delta_init = st[CS_DELTA_INIT]; s.xSx_init = st[CS_XSX_INIT]; s.cost_init = st[CS_COST_INIT];
+        s.tcg_iters = st[CS_TCG_ITERS]; s.tcg_stop = st[CS_TCG_STOP]; s.kappa = st[CS_KAPPA];
+        const int it = (int)s.it;
+        s.mu = prm.mu_sched[it > 0 ? it - 1 : 0];
+        s.tolL = prm.tolL_sched[it > 0 ? it - 1 : 0];
+        s.tolC = prm.tolC_sched[it > 0 ? it - 1 : 0];
+        s.path = (s.finished != 0.0) ? 0 : 3;
+        s.accept = s.boundary = s.rollback = 0;
+        s.ared_pred = s.radius_update = s.dual_clipping = CUDART_NAN;
+        s.inner_status = CUDART_NAN;
+        s.normdx = s.minx = s.miny = s.compl_v = CUDART_NAN;
+    }
+    __syncthreads();
+    Pipe pipe{0, 0u};
+    int buf = 0;
+    const double nan = CUDART_NAN;
+    (void)nan;
+
+    if (INIT) {
+        // x0 -> X, V; S x0; cost, x'Sx; the first outer iteration starts after the evaluation below
+        FOR_ELEMS(e) prm.V[e] = prm.X[e];
+        fence_proxy_async();
+        grid.sync();
+        stream_pass<P>(prm, sm, pipe);
+        grid.sync();
+        {
+            double part[1] = {0.0};
+            FOR_ELEMS(e) {
+                const double sx = gather_elem(prm, (int)(e / P), myc, P);
+                prm.Sx[e] = sx;
+                prm.Xprev[e] = prm.X[e];
+                part[0] = fma(prm.X[e], sx, part[0]);
+            }
+            block_reduce_store<P, 1>(prm, sm, part, buf);
+        }
+        grid.sync();
+        gather_scalars<P, 1>(prm, sm, buf);
+        buf ^= 1;
+        if (tid < P) {
+            PostState& s = ps[tid];
+            s.xSx = sm.scal[tid];
+            s.cost = -0.5 * s.xSx;
+            s.it = 0.0;
+            s.k = 0.0;
+            s.Delta = prm.initial_tr_radius > 0.0 ? prm.initial_tr_radius : 3.141592653589793 / 8.0;
+            s.cnt_inner = s.cnt_tcg = s.cnt_aux = s.rows = 0.0;
+            s.finished = (tid >= prm.p) ? 1.0 : 0.0;
+            s.stop = (double)RIPTRM_STOP_RUNNING;
+            s.mu = prm.mu_sched[0];
+            s.boundary = (s.finished == 0.0);
+            s.path = 0;
+        }
+        __syncthreads();
+    } else {
+        // ---- P1: ||dx||^2, <x,dx>, ||x+dx||^2  (RIPTRM.py:735, :743, :744) ---------------------------------
+        {
+            double part[3] = {0.0, 0.0, 0.0};
+            if (ps[myc].path) {
+                FOR_ELEMS(e) {
+                    const double x = prm.X[e], dx = prm.eta[e], a = x + dx;
+                    part[0] = fma(dx, dx, part[0]);
+                    part[1] = fma(x, dx, part[1]);
+                    part[2] = fma(a, a, part[2]);
+                }
+            }
+            block_reduce_store<P, 3>(prm, sm, part, buf);
+        }
+        grid.sync();
+        gather_scalars<P, 3>(prm, sm, buf);
+        buf ^= 1;
+        if (tid < P && ps[tid].path) {
+            ps[tid].normdx = sqrt(sm.scal[tid]);
+            ps[tid].bdot = sm.scal[P + tid];
+            ps[tid].nrm = sqrt(sm.scal[2 * P + tid]);
+        }
+        __syncthreads();
+        // ---- P2: yNew, xNew; operand V := xNew ------------------------------------------------------------
+        if (ps[myc].path) {
+            const double b = ps[myc].bdot, nrm = ps[myc].nrm, mu = ps[myc].mu;
+            FOR_ELEMS(e) {
+                const double x = prm.X[e], y = prm.Y[e], dx = prm.eta[e];
+                const double s = x + prm.eps;
+                const double ga = prm.embedded ? dx : (dx - x * b);
+                const double dy = (-y + mu * (1.0 / s)) - (y * ga) / s;
+                const double xn = (x + dx) / nrm;
+                prm.YN[e] = y + dy;
+                prm.XN[e] = xn;
+                prm.V[e] = xn;
+            }
+        }
+        fence_proxy_async();
+        grid.sync();
+        stream_pass<P>(prm, sm, pipe);  // S x_new
+        grid.sync();
+        // ---- P3: Sx_new, x_new' S x_new ---------------------------------------------------------------------
+        {
+            double part[1] = {0.0};
+            if (ps[myc].path) {
+                FOR_ELEMS(e) {
+                    const double sx = gather_elem(prm, (int)(e / P), myc, P);
+                    prm.SxN[e] = sx;
+                    part[0] = fma(prm.XN[e], sx, part[0]);
+                }
+            }
+            block_reduce_store<P, 1>(prm, sm, part, buf);
+        }
+        grid.sync();
+        gather_scalars<P, 1>(prm, sm, buf);
+        buf ^= 1;
+        if (tid < P && ps[tid].path) {
+            ps[tid].xSxN = sm.scal[tid];
+            ps[tid].costN = -0.5 * sm.scal[tid];
+        }
+        __syncthreads();
+        // ---- P4: feasibility, complementarity, <x_new, y_new>  (:591-596) ----------------------------------------
+        {
+            double part[4] = {0.0, 0.0, CUDART_INF, CUDART_INF};
+            if (ps[myc].path) {
+                const double mu = ps[myc].mu;
+                FOR_ELEMS(e) {
+                    const double xn = prm.XN[e], yn = prm.YN[e];
+                    const double sn = xn + prm.eps;
+                    const double cv = yn * sn - mu;
+                    part[0] = part[0] + cv * cv;
+                    part[1] = fma(xn, yn, part[1]);
+                    part[2] = fmin(part[2], sn);
+                    part[3] = fmin(part[3], yn);
+                }
+            }
+            reduce_store_mixed<P, 2, 2>(prm, sm, part, buf);
+        }
+        grid.sync();
+        gather_mixed<P, 2, 2>(prm, sm, buf);
+        buf ^= 1;
+        if (tid < P && ps[tid].path) {
+            ps[tid].compl_v = sqrt(sm.scal[tid]);
+            ps[tid].xy = sm.scal[P + tid];
+            ps[tid].minx = sm.scal[2 * P + tid];
+            ps[tid].miny = sm.scal[3 * P + tid];
+        }
+        __syncthreads();
+        // ---- P5: || grad L(x_new, y_new) ||  (:593) ----------------------------------------------------------------
+        {
+            double part[1] = {0.0};
+            if (ps[myc].path) {
+                const double xSxN = ps[myc].xSxN, xy = ps[myc].xy;
+                FOR_ELEMS(e) {
+                    const double xn = prm.XN[e];
+                    const double gl = (-prm.SxN[e] + xSxN * xn) - (prm.YN[e] - xy * xn);
+                    part[0] = fma(gl, gl, part[0]);
+                }
+            }
+            block_reduce_store<P, 1>(prm, sm, part, buf);
+        }
+        grid.sync();
+        gather_scalars<P, 1>(prm, sm, buf);
+        buf ^= 1;
+        if (tid < P && ps[tid].path) {
+            PostState& s = ps[tid];
+            s.ngl = sqrt(sm.scal[tid]);
+            const bool xfe = s.minx > 0.0, yfe = s.miny > 0.0;
+            if (xfe && yfe && s.ngl <= s.tolL && s.compl_v <= s.tolC) s.path = 1;        // :762-766
+            else if (!xfe) s.path = 2;                                                     // :769-775
+            else s.path = 3;
+        }
+        __syncthreads();
+        // ---- P6: log-barrier sums; operand V := dx for the extra Hessian-vector product (:644-659) -----------------------
+        bool any_normal = false;
+#pragma unroll
+        for (int c = 0; c < P; ++c) any_normal = any_normal || (ps[c].path == 3);
+        if (any_normal) {
+            {
+                double part[2] = {0.0, 0.0};
+                if (ps[myc].path == 3) {
+                    FOR_ELEMS(e) {
+                        part[0] = part[0] + det_log(prm.X[e] + prm.eps);
+                        part[1] = part[1] + det_log(prm.XN[e] + prm.eps);
+                        prm.V[e] = prm.eta[e];
+                    }
+                }
+                block_reduce_store<P, 2>(prm, sm, part, buf);
+            }
+            fence_proxy_async();
+            grid.sync();
+            gather_scalars<P, 2>(prm, sm, buf);
+            buf ^= 1;
+            if (tid < P && ps[tid].path == 3) {
+                ps[tid].pl_cur = sm.scal[tid];
+                ps[tid].pl_new = sm.scal[P + tid];
+            }
+            __syncthreads();
+            stream_pass<P>(prm, sm, pipe);  // S dx
+            grid.sync();
+            // ---- P7-P9: Hw[dx] as in the tCG kernel, then <Hw dx, dx>, <c, dx> ------------------------------------------
+            {
+                double part[2] = {0.0, 0.0};
+                if (ps[myc].path == 3) {
+                    FOR_ELEMS(e) {
+                        const double sv = gather_elem(prm, (int)(e / P), myc, P);
+                        const double x = prm.X[e];
+                        prm.Sv[e] = sv;
+                        part[0] = fma(x, sv, part[0]);
+                        part[1] = fma(x, prm.eta[e], part[1]);
+                    }
+                }
+                block_reduce_store<P, 2>(prm, sm, part, buf);
+            }
+            grid.sync();
+            gather_scalars<P, 2>(prm, sm, buf);
+            buf ^= 1;
+            if (tid < P && ps[tid].path == 3) {
+                ps[tid].a = sm.scal[tid];
+                ps[tid].b = sm.scal[P + tid];
+            }
+            __syncthreads();
+            {
+                double part[1] = {0.0};
+                if (ps[myc].path == 3) {
+                    const double b = ps[myc].b;
+                    FOR_ELEMS(e) {
+                        const double x = prm.X[e], v = prm.eta[e];
+                        const double ga = prm.embedded ? v : (v - x * b);
+                        const double tt = prm.ys[e] * ga;
+                        prm.t[e] = tt;
+                        part[0] = fma(x, tt, part[0]);
+                    }
+                }
+                block_reduce_store<P, 1>(prm, sm, part, buf);
+            }
+            grid.sync();
+            gather_scalars<P, 1>(prm, sm, buf);
+            buf ^= 1;
+            if (tid < P && ps[tid].path == 3) ps[tid].d = sm.scal[tid];
+            __syncthreads();
+            {
+                double part[2] = {0.0, 0.0};
+                if (ps[myc].path == 3) {
+                    const double a = ps[myc].a, d = ps[myc].d, kappa = ps[myc].kappa;
+                    FOR_ELEMS(e) {
+                        const double x = prm.X[e], v = prm.eta[e];
+                        const double hl = (-prm.Sv[e] + a * x) + kappa * v;
+                        const double gg = prm.t[e] - d * x;
+                        const double hd = hl + gg;
+                        part[0] = fma(hd, v, part[0]);
+                        part[1] = fma(prm.c[e], v, part[1]);
+                    }
+                }
+                block_reduce_store<P, 2>(prm, sm, part, buf);
+            }
+            grid.sync();
+            gather_scalars<P, 2>(prm, sm, buf);
+            buf ^= 1;
+        }
+        // ---- P10: rho test, radius update (:660-677), acceptance, inner-loop bookkeeping (:808-842) --------------------
+        if (tid < P && ps[tid].path) {
+            PostState& s = ps[tid];
+            s.k += 1.0;
+            s.cnt_inner += 1.0;
+            s.DeltaNext = s.Delta;
+            if (s.path == 1) {
+                s.inner_status = (double)RIPTRM_INNER_CONVERGED;
+                s.accept = 1;
+                s.boundary = 1;
+            } else if (s.path == 2) {
+                s.inner_status = (double)RIPTRM_INNER_PRIMAL_INFEASIBLE;
+                s.DeltaNext = prm.gamma * s.normdx;
+            } else {
+                s.cnt_aux += 1.0;
+                const double phi_cur = s.cost - s.mu * s.pl_cur, phi_new = s.costN - s.mu * s.pl_new;
+                double ared = phi_cur - phi_new;
+                double pred = (0.0 - 0.5 * sm.scal[tid]) - sm.scal[P + tid];
+                const double reg = (fmax(1.0, fabs(phi_cur)) * 2.220446049250313e-16) * prm.reduction_regularization;
+                ared = ared + reg;
+                pred = pred + reg;
+                s.ared_pred = ared / pred;
+                if (ared < 0.25 * pred) {
+                    s.radius_update = (double)RIPTRM_RADIUS_REDUCED;
+                    s.DeltaNext = 0.25 * s.Delta;
+                } else if (ared >= 0.75 * pred && fabs(s.normdx - s.Delta) <= 1e-15) {
+                    s.radius_update = (double)RIPTRM_RADIUS_EXPANDED;
+                    s.DeltaNext = fmin(2.0 * s.Delta, prm.maximal_tr_radius);
+                } else {
+                    s.radius_update = (double)RIPTRM_RADIUS_UNCHANGED;
+                }
+                if (ared > prm.rho * pred) {
+                    s.inner_status = (double)RIPTRM_INNER_SUCCESSFUL;
+                    s.accept = 2;  // accept with dual clipping
+                } else {
+                    s.inner_status = (double)RIPTRM_INNER_UNSUCCESSFUL;
+                }
+            }
+            if (prm.inner_maxiter >= 0 && (int)s.k >= prm.inner_maxiter) {  // :835-842 (after the step, as the reference)
+                s.inner_status = (double)RIPTRM_INNER_MAX_ITER;
+                s.rollback = 1;
+                s.boundary = 1;
+            }
+        }
+        __syncthreads();
+        // ---- P10b: commit (x, y) / clip the duals (:681-696) / roll back -------------------------------------------------
+        {
+            double part[1] = {0.0};
+            const PostState& s = ps[myc];
+            if (s.path) {
+                const double I_right = fmax(prm.const_right, prm.const_right / s.mu);
+                FOR_ELEMS(e) {
+                    if (s.rollback) {
+                        prm.X[e] = prm.Xinit[e];
+                        prm.Y[e] = prm.Yinit[e];
+                        prm.Sx[e] = prm.Sxinit[e];
+                    } else if (s.accept == 1) {
+                        prm.X[e] = prm.XN[e];
+                        prm.Y[e] = prm.YN[e];
+                        prm.Sx[e] = prm.SxN[e];
+                    } else if (s.accept == 2) {
+                        const double yn = prm.YN[e], xn = prm.XN[e];
+                        const double I_left = prm.const_left * fmin(fmin(prm.Y[e], s.mu / (xn + prm.eps)), 1.0);
+                        const double cl = fmin(fmax(yn, I_left), I_right);
+                        if (!(cl == yn)) part[0] = part[0] + 1.0;
+                        prm.X[e] = xn;
+                        prm.Y[e] = cl;
+                        prm.Sx[e] = prm.SxN[e];
+                    }
+                }
+            }
+            block_reduce_store<P, 1>(prm, sm, part, buf);
+        }
+        grid.sync();
+        gather_scalars<P, 1>(prm, sm, buf);
+        buf ^= 1;
+        if (tid < P && ps[tid].path) {
+            PostState& s = ps[tid];
+            if (s.rollback) {
+                s.xSx = s.xSx_init;
+                s.cost = s.cost_init;
+                s.Delta = s.Delta_init;
+            } else {
+                if (s.accept) {
+                    s.xSx = s.xSxN;
+                    s.cost = s.costN;
+                }
+                if (s.accept == 2) s.dual_clipping = (sm.scal[tid] > 0.0) ? 1.0 : 0.0;
+                if (s.path != 1) s.Delta = s.DeltaNext;   // converged: the radius is returned unchanged (:762-766)
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- outer-iteration boundary (columns whose inner loop just ended, or INIT): evaluation (utils.py:342-368),
+    //      log row, stop tests (base_solver.py:85-106), barrier update (:890-894) --------------------------------------
+    {
+        double part[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, CUDART_INF};
+        if (ps[myc].boundary) {
+            FOR_ELEMS(e) {
+                const double x = prm.X[e], y = prm.Y[e];
+                const double gi = -(x + prm.eps);
+                const double cv = y * gi, nv = fmax(-y, 0.0), iv = fmax(gi, 0.0);
+                part[0] = fma(x, y, part[0]);
+                part[1] = fma(x, x, part[1]);
+                part[2] = fma(prm.Xprev[e], x, part[2]);
+                part[3] = part[3] + cv * cv;
+                part[4] = part[4] + nv * nv;
+                part[5] = part[5] + iv * iv;
+                part[6] = part[6] + iv;
+                part[7] = fmin(part[7], -iv);
+            }
+        }
+        reduce_store_mixed<P, 7, 1>(prm, sm, part, buf);
+    }
+    grid.sync();
+    gather_mixed<P, 7, 1>(prm, sm, buf);
+    buf ^= 1;
+    __shared__ double ev[P][8];
+    if (tid < P && ps[tid].boundary) {
+        for (int q = 0; q < 8; ++q) ev[tid][q] = sm.scal[q * P + tid];
+    }
+    __syncthreads();
+    {
+        double part[1] = {0.0};
+        if (ps[myc].boundary) {
+            const double xSx = ps[myc].xSx, xy = ev[myc][0];
+            FOR_ELEMS(e) {
+                const double x = prm.X[e];
+                const double gl = (-prm.Sx[e] + xSx * x) - (prm.Y[e] - xy * x);
+                part[0] = fma(gl, gl, part[0]);
+            }
+        }
+        block_reduce_store<P, 1>(prm, sm, part, buf);
+    }
+    grid.sync();
+    gather_scalars<P, 1>(prm, sm, buf);
+    buf ^= 1;
+    if (tid < P && ps[tid].boundary) {
+        PostState& s = ps[tid];
+        const double gradnorm = sqrt(sm.scal[tid]);
+        const double p_compl = ev[tid][3], p_nonneg = ev[tid][4], p_ineq = ev[tid][5];
+        const double man_v = sqrt(ev[tid][1]) - 1.0;
+        const double residual = sqrt(((((gradnorm * gradnorm + p_compl) + p_nonneg) + p_ineq) + 0.0) + man_v * man_v);
+        const double max_v = -ev[tid][7], mean_v = ev[tid][6] / (double)n;
+        const double distance = acos(fmax(fmin(ev[tid][2], 1.0), -1.0));
+        const int it = (int)s.it;
+        const double mu_row = prm.mu_sched[it];  // the barrier parameter after the update (:890-893), mu_sched[0] at row 0
+        if (prm.trace_mode == 2 && prm.trace != nullptr && g == 0) {
+            if ((int)s.rows < prm.trace_capacity) {
+                double* row = prm.trace + ((size_t)tid * prm.trace_capacity + (size_t)s.rows) * RIPTRM_TRACE_FIELDS;
+                for (int f = 0; f < RIPTRM_TRACE_FIELDS; ++f) row[f] = CUDART_NAN;
+                row[RIPTRM_TR_ITERATION] = (double)it;
+                row[RIPTRM_TR_MU] = mu_row;
+                if (!INIT) {
+                    row[RIPTRM_TR_NUM_INNER] = s.k;
+                    row[RIPTRM_TR_RADIUS] = s.Delta;
+                    row[RIPTRM_TR_INNER_STATUS] = s.inner_status;
+                }
+                row[RIPTRM_TR_COST] = s.cost;
+                row[RIPTRM_TR_DISTANCE] = distance;
+                row[RIPTRM_TR_RESIDUAL] = residual;
+                row[RIPTRM_TR_GRADNORM] = gradnorm;
+                row[RIPTRM_TR_COMPLVIOLATION] = sqrt(p_compl);
+                row[RIPTRM_TR_DUALVIOLATION] = sqrt(p_nonneg);
+                row[RIPTRM_TR_MANVIOLATION] = man_v;
+                row[RIPTRM_TR_MAXVIOLATION] = max_v;
+                row[RIPTRM_TR_MEANVIOLATION] = mean_v;
+                row[RIPTRM_TR_TIME] = 0.0;
+            }
+        }
+        if (prm.trace_mode == 2) s.rows += 1.0;
+        int stop = RIPTRM_STOP_RUNNING;
+        if (it >= prm.maxiter) stop = RIPTRM_STOP_MAXITER;
+        if (residual <= prm.tolresid) stop = RIPTRM_STOP_TOLRESID;
+        if (g == 0 && prm.summary != nullptr) {
+            double* sm_ = prm.summary + (size_t)tid * RIPTRM_SUMMARY_FIELDS;
+            sm_[RIPTRM_SM_COST] = s.cost;
+            sm_[RIPTRM_SM_RESIDUAL] = residual;
+            sm_[RIPTRM_SM_GRADNORM] = gradnorm;
+            sm_[RIPTRM_SM_COMPLVIOLATION] = sqrt(p_compl);
+            sm_[RIPTRM_SM_DUALVIOLATION] = sqrt(p_nonneg);
+            sm_[RIPTRM_SM_MANVIOLATION] = man_v;
+            sm_[RIPTRM_SM_MAXVIOLATION] = max_v;
+            sm_[RIPTRM_SM_MEANVIOLATION] = mean_v;
+            sm_[RIPTRM_SM_MU] = mu_row;
+            sm_[RIPTRM_SM_RADIUS] = fmax(s.Delta, it > 0 ? prm.minimal_initial_tr_radius : s.Delta);
+            sm_[RIPTRM_SM_OUTER_ITERS] = (double)it;
+            sm_[RIPTRM_SM_INNER_ITERS] = s.cnt_inner;
+            sm_[RIPTRM_SM_TCG_ITERS] = s.cnt_tcg;
+            sm_[RIPTRM_SM_AUX_HESSVECS] = s.cnt_aux;
+            sm_[RIPTRM_SM_STOP_REASON] = (double)stop;
+            sm_[RIPTRM_SM_TRACE_ROWS] = s.rows;
+        }
+        if (it > 0) s.Delta = fmax(s.Delta, prm.minimal_initial_tr_radius);   // :894
+        if (stop != RIPTRM_STOP_RUNNING) {
+            s.finished = 1.0;
+            s.stop = (double)stop;
+        } else {
+            s.it = (double)(it + 1);
+            s.k = 0.0;
+            s.Delta_init = s.Delta;
+            s.xSx_init = s.xSx;
+            s.cost_init = s.cost;
+        }
+    }
+    __syncthreads();
+    // start-of-inner-run copies for the rollback (:794-796) and the previous outer iterate for `distance`
+    if (ps[myc].boundary && ps[myc].finished == 0.0) {
+        FOR_ELEMS(e) {
+            const double x = prm.X[e];
+            prm.Xinit[e] = x;
+            prm.Yinit[e] = prm.Y[e];
+            prm.Sxinit[e] = prm.Sx[e];
+            prm.Xprev[e] = x;
+        }
+    }
+    if (g == 0 && tid < P) {
+        const PostState& s = ps[tid];
+        double* st = prm.colstate + tid * CS_FIELDS;
+        st[CS_IT] = s.it; st[CS_K] = s.k; st[CS_DELTA] = s.Delta; st[CS_XSX] = s.xSx; st[CS_COST] = s.cost;
+        st[CS_CNT_INNER] = s.cnt_inner; st[CS_CNT_TCG] = s.cnt_tcg; st[CS_CNT_AUX] = s.cnt_aux; st[CS_ROWS] = s.rows;
+        st[CS_FINISHED] = s.finished; st[CS_STOP] = s.stop;
+        st[CS_DELTA_INIT] = s.Delta_init; st[CS_XSX_INIT] = s.xSx_init; st[CS_COST_INIT] = s.cost_init;
+    }
+    if (g == 0 && tid == 0) {
+        bool all = true;
+        for (int c = 0; c < prm.p; ++c) all = all && (ps[c].finished != 0.0);
+        *prm.all_done = all ? 1 : 0;
     }
 #undef FOR_ELEMS
 }

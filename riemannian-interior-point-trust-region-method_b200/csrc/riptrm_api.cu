@@ -307,6 +307,9 @@ extern "C" int riptrm_destroy(riptrm_handle* h) {
 // COLUMNS family (fam_columns.cuh): host side
 // ------------------------------------------------------------------------------------------
 static int finish_timing(riptrm_handle* h, bool sync);
+static int ensure(double*& p, size_t bytes);
+
+constexpr int kColArrays = 24;  // n_pad x P work arrays of the COLUMNS family
 
 static int columns_template_p(int p) {
     const int sizes[] = {1, 2, 4, 8, 10, 16};
@@ -352,7 +355,8 @@ static int columns_setup(riptrm_handle* h, const double* Z, double eps, int wher
     const size_t arr = (size_t)h->n_pad * h->colP;
     const size_t mv = (size_t)h->col_grid * h->col_slots * col::TW * h->colP;
     const size_t dots = (size_t)2 * h->col_grid * col::MAXQ * col::MAXP;
-    const size_t total_d = 17 * arr + mv + dots + 4 * col::MAXP + (size_t)2 * (h->col_grid + 2);
+    const size_t total_d = kColArrays * arr + mv + dots + 4 * col::MAXP + (size_t)2 * (h->col_grid + 2) +
+                           (size_t)col::MAXP * col::CS_FIELDS + (size_t)col::MAXP * RIPTRM_SUMMARY_FIELDS + 2;
     CUDA_TRY(cudaMalloc(&h->d_colbuf, total_d * sizeof(double)));
     CUDA_TRY(cudaMemset(h->d_colbuf, 0, total_d * sizeof(double)));
     {
@@ -361,7 +365,7 @@ static int columns_setup(riptrm_handle* h, const double* Z, double eps, int wher
         std::vector<int> ib0(h->col_grid + 2, 0);
         for (int g = 0; g <= h->col_grid; ++g) tb[g] = total * g / h->col_grid;
         for (int g = 0; g < h->col_grid; ++g) ib0[g] = (int)(tb[g] / NJT);
-        double* tail = h->d_colbuf + 17 * arr + mv + dots + 4 * col::MAXP;
+        double* tail = h->d_colbuf + kColArrays * arr + mv + dots + 4 * col::MAXP;
         CUDA_TRY(cudaMemcpy(tail, tb.data(), tb.size() * sizeof(long long), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(tail + (h->col_grid + 2), ib0.data(), ib0.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
@@ -415,11 +419,15 @@ static int columns_export(riptrm_handle* h, double* dst, const double* src, int 
     return RIPTRM_OK;
 }
 
-static int columns_run(riptrm_handle* h, int mode, const double* x, const double* y, double mu, double Delta,
-                       const double* v, double* out, double* info, int where, cudaStream_t st) {
+// pointers into the handle's COLUMNS workspace
+struct ColPtrs {
+    double *vin, *out, *info, *colstate, *summary;
+    int* all_done;
+};
+
+static ColPtrs columns_fill_params(riptrm_handle* h, col::Params& prm) {
     const size_t arr = (size_t)h->n_pad * h->colP;
     double* b = h->d_colbuf;
-    col::Params prm{};
     prm.n = h->n;
     prm.n_pad = h->n_pad;
     prm.ld = h->ld;
@@ -433,25 +441,44 @@ static int columns_run(riptrm_handle* h, int mode, const double* x, const double
     prm.eps = h->eps;
     prm.embedded = h->have_opts ? h->opts.is_euclidean_embedded : 0;
     double** fields[] = {&prm.X, &prm.Y, &prm.Sx, &prm.ys, &prm.c, &prm.V, &prm.Sv, &prm.t, &prm.Hd, &prm.eta,
-                         &prm.Heta, &prm.r, &prm.eta2, &prm.Heta2, &prm.r2};
-    for (int i = 0; i < 15; ++i) *fields[i] = b + i * arr;
-    double* d_vin = b + 15 * arr;
-    double* d_out = b + 16 * arr;
-    prm.mv_part = b + 17 * arr;
+                         &prm.Heta, &prm.r, &prm.eta2, &prm.Heta2, &prm.r2, &prm.XN, &prm.YN, &prm.SxN, &prm.Xinit,
+                         &prm.Yinit, &prm.Sxinit, &prm.Xprev};
+    for (int i = 0; i < 22; ++i) *fields[i] = b + i * arr;
+    ColPtrs q{};
+    q.vin = b + 22 * arr;
+    q.out = b + 23 * arr;
+    prm.mv_part = b + kColArrays * arr;
     prm.dot_part = prm.mv_part + (size_t)h->col_grid * h->col_slots * col::TW * h->colP;
-    double* d_info = prm.dot_part + (size_t)2 * h->col_grid * col::MAXQ * col::MAXP;
-    prm.tbeg = reinterpret_cast<const long long*>(d_info + 4 * col::MAXP);
-    prm.tib0 = reinterpret_cast<const int*>(d_info + 4 * col::MAXP + (h->col_grid + 2));
-    prm.mu = mu;
-    prm.Delta = Delta;
-    prm.vin = d_vin;
-    prm.out = d_out;
-    prm.info = d_info;
+    q.info = prm.dot_part + (size_t)2 * h->col_grid * col::MAXQ * col::MAXP;
+    prm.tbeg = reinterpret_cast<const long long*>(q.info + 4 * col::MAXP);
+    prm.tib0 = reinterpret_cast<const int*>(q.info + 4 * col::MAXP + (h->col_grid + 2));
+    q.colstate = q.info + 4 * col::MAXP + (size_t)2 * (h->col_grid + 2);
+    q.summary = q.colstate + (size_t)col::MAXP * col::CS_FIELDS;
+    q.all_done = reinterpret_cast<int*>(q.summary + (size_t)col::MAXP * RIPTRM_SUMMARY_FIELDS);
+    prm.vin = q.vin;
+    prm.out = q.out;
+    prm.info = q.info;
+    prm.colstate = q.colstate;
+    prm.summary = q.summary;
+    prm.all_done = q.all_done;
     prm.passes = h->d_passes;
     prm.tcg_mininner = h->have_opts ? h->opts.tcg_mininner : 1;
     prm.tcg_maxinner = h->have_opts ? h->opts.tcg_maxinner : -1;
     prm.tcg_theta = h->have_opts ? h->opts.tcg_theta : 1.0;
     prm.tcg_kappa = h->have_opts ? h->opts.tcg_kappa : 0.1;
+    return q;
+}
+
+static int columns_run(riptrm_handle* h, int mode, const double* x, const double* y, double mu, double Delta,
+                       const double* v, double* out, double* info, int where, cudaStream_t st) {
+    col::Params prm{};
+    const ColPtrs q = columns_fill_params(h, prm);
+    double* d_vin = q.vin;
+    double* d_out = q.out;
+    double* d_info = q.info;
+    prm.mu = mu;
+    prm.Delta = Delta;
+    prm.solve = 0;
     int rc;
     if ((rc = columns_import(h, prm.X, x, where, st)) || (rc = columns_import(h, prm.Y, y, where, st))) return rc;
     if (mode == 1 && (rc = columns_import(h, d_vin, v, where, st))) return rc;
@@ -465,6 +492,105 @@ static int columns_run(riptrm_handle* h, int mode, const double* x, const double
         CUDA_TRY(cudaMemcpyAsync(info, d_info, (size_t)h->p * 4 * sizeof(double), kind, st));
     }
     if (where == RIPTRM_DEVICE) return RIPTRM_OK;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return finish_timing(h, true);
+}
+
+
+template <int P, bool INIT>
+static int columns_launch_post(riptrm_handle* h, col::Params& prm, cudaStream_t st) {
+    auto kern = col::columns_post_kernel<P, INIT>;
+    const size_t smem = sizeof(col::Smem<P>);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* args[] = {&prm};
+    CUDA_TRY(cudaLaunchCooperativeKernel((void*)kern, dim3(h->col_grid), dim3(col::NT), args, smem, st));
+    h->launches += 1;
+    return RIPTRM_OK;
+}
+template <bool INIT>
+static int columns_dispatch_post(riptrm_handle* h, col::Params& prm, cudaStream_t st) {
+    switch (h->colP) {
+        case 1: return columns_launch_post<1, INIT>(h, prm, st);
+        case 2: return columns_launch_post<2, INIT>(h, prm, st);
+        case 4: return columns_launch_post<4, INIT>(h, prm, st);
+        case 8: return columns_launch_post<8, INIT>(h, prm, st);
+        case 10: return columns_launch_post<10, INIT>(h, prm, st);
+        case 16: return columns_launch_post<16, INIT>(h, prm, st);
+    }
+    return fail(RIPTRM_E_UNSUPPORTED, "unsupported column count");
+}
+
+// riptrm_solve on the COLUMNS family: p independent RIPTRM runs sharing S, advanced in lock-step.  The host only
+// sequences launches (tCG for all columns, then the rest of the trust-region iteration) and polls one flag.
+static int columns_solve(riptrm_handle* h, const double* x0, const double* y0, double* x, double* y, double* summary,
+                         double* trace, int where, cudaStream_t st) {
+    const riptrm_options& o = h->opts;
+    if (o.trace_mode == 1)
+        return fail(RIPTRM_E_UNSUPPORTED, "COLUMNS family: per-inner-iteration trace is not built (use trace_mode 0 or 2)");
+    col::Params prm{};
+    const ColPtrs q = columns_fill_params(h, prm);
+    prm.solve = 1;
+    prm.mu_sched = h->d_sched;
+    prm.tolL_sched = h->d_sched + h->sched_len;
+    prm.tolC_sched = h->d_sched + 2 * h->sched_len;
+    prm.maxiter = o.maxiter;
+    prm.inner_maxiter = o.inner_maxiter;
+    prm.trace_mode = o.trace_mode;
+    prm.trace_capacity = o.trace_capacity;
+    prm.tolresid = o.tolresid;
+    prm.initial_tr_radius = o.initial_tr_radius;
+    prm.minimal_initial_tr_radius = o.minimal_initial_tr_radius;
+    prm.maximal_tr_radius = o.maximal_tr_radius;
+    prm.rho = o.rho;
+    prm.reduction_regularization = o.reduction_regularization;
+    prm.gamma = o.gamma;
+    prm.const_left = o.const_left;
+    prm.const_right = o.const_right;
+    const size_t tb = (o.trace_mode == 2 && trace != nullptr)
+                          ? (size_t)h->p * o.trace_capacity * RIPTRM_TRACE_FIELDS * sizeof(double) : 0;
+    if (tb != 0) {
+        if (where == RIPTRM_DEVICE) {
+            prm.trace = trace;
+        } else {
+            if (h->d_trace != nullptr && h->trace_bytes != tb) free_dev(h->d_trace);
+            int rc0;
+            if ((rc0 = ensure(h->d_trace, tb))) return rc0;
+            h->trace_bytes = tb;
+            prm.trace = h->d_trace;
+        }
+    }
+    int rc;
+    if ((rc = columns_import(h, prm.X, x0, where, st)) || (rc = columns_import(h, prm.Y, y0, where, st))) return rc;
+    CUDA_TRY(cudaMemsetAsync(q.colstate, 0, (size_t)col::MAXP * col::CS_FIELDS * sizeof(double), st));
+    CUDA_TRY(cudaEventRecord(h->ev0, st));
+    if ((rc = columns_dispatch_post<true>(h, prm, st))) return rc;
+    const long long max_rounds = (long long)(o.maxiter + 1) * (o.inner_maxiter > 0 ? o.inner_maxiter : 100000);
+    for (long long round = 0; round < max_rounds; ++round) {
+        int done = 0;
+        CUDA_TRY(cudaMemcpyAsync(&done, q.all_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (done) break;
+        cudaEvent_t keep0 = h->ev0, keep1 = h->ev1;  // columns_dispatch records its own events: keep the solve's start
+        cudaEvent_t t0, t1;
+        CUDA_TRY(cudaEventCreate(&t0));
+        CUDA_TRY(cudaEventCreate(&t1));
+        h->ev0 = t0;
+        h->ev1 = t1;
+        rc = columns_dispatch<2>(h, prm, st);
+        h->ev0 = keep0;
+        h->ev1 = keep1;
+        cudaEventDestroy(t0);
+        cudaEventDestroy(t1);
+        if (rc) return rc;
+        if ((rc = columns_dispatch_post<false>(h, prm, st))) return rc;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev1, st));
+    if (x != nullptr && (rc = columns_export(h, x, prm.X, where, st))) return rc;
+    if (y != nullptr && (rc = columns_export(h, y, prm.Y, where, st))) return rc;
+    const cudaMemcpyKind kind = (where == RIPTRM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (summary != nullptr)
+        CUDA_TRY(cudaMemcpyAsync(summary, q.summary, (size_t)h->p * RIPTRM_SUMMARY_FIELDS * sizeof(double), kind, st));
+    if (tb != 0 && where != RIPTRM_DEVICE) CUDA_TRY(cudaMemcpyAsync(trace, h->d_trace, tb, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return finish_timing(h, true);
 }
@@ -820,8 +946,7 @@ extern "C" int riptrm_solve(riptrm_handle* h, const double* x0, const double* y0
     if (!h->have_opts) return fail(RIPTRM_E_STATE, "riptrm_set_options has not been called");
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (h->family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS)
-        return fail(RIPTRM_E_UNSUPPORTED, "COLUMNS family: use riptrm_hessvec / riptrm_tcg (whole solve not built yet)");
+    if (h->family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS) return columns_solve(h, x0, y0, x, y, summary, trace, where, st);
     const size_t B = h->batch;
     const size_t xb = B * h->vec_len * sizeof(double), yb = B * h->m * sizeof(double);
     const size_t sb = B * RIPTRM_SUMMARY_FIELDS * sizeof(double);

@@ -232,6 +232,31 @@ class ColumnsSolver:
                                        _lib.ptr(out), _lib.ptr(info), where, C.c_void_p(stream) if stream else None))
         return out, info
 
+    def solve(self, X0, Y0, option=None, per_outer_trace=False, stream=None):
+        """p independent RIPTRM runs (one per column, sharing Z) advanced in lock-step (RIPTRM.py:909-976 per column).
+        Returns (X [n, p], Y [n, p], summary [p, 16], trace [p, maxiter + 1, 25] | None); trace rows are per outer
+        iteration (`save_inner_iteration=False` layout)."""
+        if option is not None:
+            o, keep = _options.to_c_options(option, 2 if per_outer_trace else 0, int(option["maxiter"]) + 1)
+            _lib.check(self.lib.riptrm_set_options(self.handle.h, C.byref(o)))
+            cap = int(option["maxiter"]) + 1
+        else:
+            per_outer_trace, cap = False, 0
+        where = self._where(X0, Y0)
+        if where == _lib.HOST:
+            X0, Y0 = (np.ascontiguousarray(a, dtype=np.float64) for a in (X0, Y0))
+            X, Y = np.empty((self.n, self.p)), np.empty((self.n, self.p))
+            summary = np.empty((self.p, _lib.SUMMARY_FIELDS))
+            trace = np.full((self.p, cap, _lib.TRACE_FIELDS), np.nan) if per_outer_trace else None
+        else:
+            X, Y = X0.new_empty((self.n, self.p)), X0.new_empty((self.n, self.p))
+            summary = X0.new_empty((self.p, _lib.SUMMARY_FIELDS))
+            trace = X0.new_full((self.p, cap, _lib.TRACE_FIELDS), float("nan")) if per_outer_trace else None
+        _lib.check(self.lib.riptrm_solve(self.handle.h, _lib.ptr(X0), _lib.ptr(Y0), _lib.ptr(X), _lib.ptr(Y),
+                                         _lib.ptr(summary), _lib.ptr(trace), where,
+                                         C.c_void_p(stream) if stream else None))
+        return X, Y, summary, trace
+
     @property
     def kernel_ms(self):
         return float(self.lib.riptrm_last_kernel_ms(self.handle.h))
@@ -293,6 +318,16 @@ def columns_bench(n, p, dev, peak, launches_out, tcg_iters=40, reps=3):
     hv = solver.hessvec(X, Y, 0.1, V, stream=stream)
     torch.cuda.synchronize()
     hv_ms = solver.kernel_ms
+    # whole solve under a capped protocol (maxiter=2 outer iterations, inner_maxiter=5)
+    sopt = _options.default_option()
+    sopt.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=2, inner_maxiter=5, tolresid=0, maxtime=1e9)
+    l1 = solver.launches
+    p0 = solver.matvec_passes
+    Xs, Ys, sm, _ = solver.solve(X, Y, sopt, stream=stream)
+    torch.cuda.synchronize()
+    solve_ms, solve_passes = solver.kernel_ms, solver.matvec_passes - p0
+    launches_out.append(solver.launches - l1)
+    sm = sm.cpu().numpy()
     solver.close()
     alg = 8.0 * n * n + 40.0 * n * p
     ms = float(np.mean(times))
@@ -304,7 +339,12 @@ def columns_bench(n, p, dev, peak, launches_out, tcg_iters=40, reps=3):
     extra = {"n": n, "p": p, "tcg_launch_ms": ms, "matvec_passes_per_launch": float(np.mean(passes)),
              "ms_per_hessvec": ms / float(np.mean(passes)), "hessvec_hbm_gbs": ach,
              "column_tcg_iters_per_sec": float(np.mean(iters)) / (ms * 1e-3),
-             "hessvec_hook_ms": hv_ms, "finite": bool(torch.isfinite(hv).all())}
+             "hessvec_hook_ms": hv_ms, "finite": bool(torch.isfinite(hv).all()),
+             "capped_solve": {"protocol": "maxiter=2, inner_maxiter=5", "ms": solve_ms, "matvec_passes": int(solve_passes),
+                              "hbm_gbs": alg * solve_passes / (solve_ms * 1e-3) / 1e9,
+                              "inner_iters": float(sm[:, _lib.SM["inner_iters"]].sum()),
+                              "tcg_iters": float(sm[:, _lib.SM["tcg_iters"]].sum()),
+                              "finite": bool(np.isfinite(sm).all())}}
     return roofline, extra
 
 

@@ -94,3 +94,56 @@ def test_streaming_pass_is_linear_and_symmetric(rb):
     # determinism: same bits run to run
     assert np.array_equal(cs.hessvec(X, Y, 0.01, U), HU)
     cs.close()
+
+
+def test_whole_solve_matches_the_c_oracle_per_column(rb):
+    """riptrm_solve on the COLUMNS family: every column is an independent Sphere RIPTRM run.  n = 100, p = 4 against
+    the C oracle (reference operation order) run column by column: identical outer / inner / tCG iteration counts in
+    the well-conditioned window (8 outer iterations), final iterate / objective / multipliers to 1e-8 after 30."""
+    from oracle.c import binding as detc
+    n, p = 100, 4
+    Z, X0, Y0, rs = _instance(n, p, seed=77)
+    Y0 = np.ones((n, p))
+    cs = rb.ColumnsSolver(Z, p)
+    for K, exact_counts in ((8, True), (30, False)):
+        opt = rb.options.default_option()
+        opt.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=K, tolresid=0, maxtime=1e9, inner_maxiter=1000)
+        X, Y, sm, tr = cs.solve(X0, Y0, opt, per_outer_trace=True)
+        SM = rb._lib.SM
+        for c in range(p):
+            xo, yo, so, _ = detc.solve(Z, X0[:, c].copy(), Y0[:, c].copy(), {"maxiter": K, "tolresid": 0, "inner_maxiter": 1000},
+                                       faithful=True)
+            assert sm[c, SM["outer_iters"]] == so[10] == K and sm[c, SM["stop_reason"]] == 2
+            if exact_counts:
+                assert sm[c, SM["inner_iters"]] == so[11], (c, sm[c, SM["inner_iters"]], so[11])
+                # tCG counts hinge on the ulp-level test norm_r <= target (RIPTRM.py:183): a different summation
+                # order may stop one iteration apart
+                assert abs(sm[c, SM["tcg_iters"]] - so[12]) <= 2, (c, sm[c, SM["tcg_iters"]], so[12])
+                assert sm[c, SM["aux_hessvecs"]] == so[13]
+            assert abs(sm[c, SM["cost"]] - so[0]) < (1e-6 if exact_counts else 1e-8) * abs(so[0])
+            if not exact_counts:
+                assert np.max(np.abs(X[:, c] - xo)) < 1e-8
+                assert np.max(np.abs(Y[:, c] - yo)) < 1e-8 * max(1.0, np.max(np.abs(yo)))
+                assert sm[c, SM["residual"]] < 1e-9 and so[1] < 1e-9
+            assert abs(np.linalg.norm(X[:, c]) - 1) < 1e-14 and (X[:, c] > 0).all()
+            # per-outer trace rows: iteration 0..K, cost decreasing to the final value
+            rows = int(sm[c, SM["trace_rows"]])
+            assert rows == K + 1
+            assert list(tr[c, :rows, rb._lib.TR["iteration"]]) == list(range(K + 1))
+            assert tr[c, rows - 1, rb._lib.TR["cost"]] == sm[c, SM["cost"]]
+    cs.close()
+
+
+def test_whole_solve_columns_finish_independently(rb):
+    """Columns stop at their own time (tolresid reached at different outer iterations); finished columns are frozen."""
+    n, p = 300, 3
+    Z, X0, Y0, rs = _instance(n, p, seed=5)
+    Y0 = np.ones((n, p))
+    cs = rb.ColumnsSolver(Z, p)
+    opt = rb.options.default_option()
+    opt.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=40, tolresid=1e-6, maxtime=1e9, inner_maxiter=1000)
+    X, Y, sm, _ = cs.solve(X0, Y0, opt)
+    SM = rb._lib.SM
+    assert (sm[:, SM["stop_reason"]] == 3).all() and (sm[:, SM["residual"]] <= 1e-6).all()
+    assert (sm[:, SM["outer_iters"]] < 40).all()
+    cs.close()
