@@ -19,8 +19,9 @@
 //     order and written as a partial; the owner of each row later adds the partials in CTA order.
 //   * every other step of the tCG iteration is a "vector phase" over the n x p arrays (L2 resident, 1.6 MB
 //     each), rows dealt to CTAs in contiguous chunks, with per-column dot products reduced per CTA in a
-//     fixed order and then over CTAs in CTA order.  Phases are separated by grid-wide barriers; all CTAs
-//     compute the per-column scalars redundantly and bit-identically, so control flow stays uniform.
+//     fixed order and then over CTAs in CTA order.  Phases are separated by grid-wide barriers (four per tCG
+//     iteration, thanks to the merged reductions of fam_sphere.cuh); all CTAs compute the per-column scalars
+//     redundantly and bit-identically, so control flow stays uniform.
 // All sums have a fixed order for a given grid size: results are deterministic run to run.
 #pragma once
 #include <cooperative_groups.h>
@@ -290,7 +291,7 @@ __device__ __forceinline__ void gather_scalars(const Params& prm, Smem<P>& sm, i
 
 // per-column tCG state, identical in every CTA
 struct ColState {
-    double e_Pe, e_Pd, d_Pd, z_r, r_r, norm_r0, nr_theta, target, model_value, alpha, beta, kappa, xSx, a, b, d, mu, Delta2;
+    double e_Pe, e_Pd, d_Pd, z_r, r_r, norm_r0, nr_theta, target, model_value, alpha, beta, kappa, xSx, a, b, d, mu, Delta2, q, xd;
     int done, iters, stop;
 };
 
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(NT, 1) columns_kernel(Params prm) {
     __syncthreads();
     {
         // c = grad f - G_x(mu/s);  r = c, delta = -c, eta = Heta = 0;  r_r = <c, c>
-        double part[1] = {0.0};
+        double part[2] = {0.0, 0.0};
         const double xSx = cs[myc].xSx, xw = cs[myc].a, mu_c = cs[myc].mu;
         FOR_ELEMS(e) {
             const double x = prm.X[e];
@@ -400,21 +401,23 @@ __global__ void __launch_bounds__(NT, 1) columns_kernel(Params prm) {
                 prm.eta[e] = 0.0;
                 prm.Heta[e] = 0.0;
                 part[0] = fma(cc, cc, part[0]);
+                part[1] = fma(x * prm.ys[e], x, part[1]);  // q = <x*(y/s), x>
             } else {
                 prm.V[e] = prm.vin[e];
             }
         }
-        if (MODE == 2) block_reduce_store<P, 1>(prm, sm, part, buf);
+        if (MODE == 2) block_reduce_store<P, 2>(prm, sm, part, buf);
     }
     fence_proxy_async();
     grid.sync();
     int maxinner = prm.tcg_maxinner < 0 ? (n - 1) : prm.tcg_maxinner;
     if (MODE == 2) {
-        gather_scalars<P, 1>(prm, sm, buf);
+        gather_scalars<P, 2>(prm, sm, buf);
         buf ^= 1;
         if (tid < P) {
             ColState& s = cs[tid];
             s.r_r = sm.scal[tid];
+            s.q = sm.scal[P + tid];
             s.norm_r0 = sqrt(s.r_r);
             s.z_r = s.r_r;
             s.d_Pd = s.r_r;
@@ -429,7 +432,8 @@ __global__ void __launch_bounds__(NT, 1) columns_kernel(Params prm) {
         maxinner = 1;
     }
 
-    for (int j = 0; j < maxinner; ++j) {
+    // One Hessian-vector product in the reference's operation order (hook riptrm_hessvec)
+    for (int j = 0; MODE == 1 && j < maxinner; ++j) {
         // ---- T1: Sv = S V ------------------------------------------------------------------------------
         stream_pass<P>(prm, sm, pipe);
         grid.sync();
@@ -596,6 +600,157 @@ __global__ void __launch_bounds__(NT, 1) columns_kernel(Params prm) {
         if (cs[myc].done == 3) {
             const double xd = sm.scal[myc];
             FOR_ELEMS(e) prm.V[e] = prm.t[e] - xd * prm.X[e];
+        }
+        __syncthreads();
+        if (tid < P) {
+            ColState& s = cs[tid];
+            if (s.done == 3) {
+                s.e_Pd = s.beta * (s.e_Pd + s.alpha * s.d_Pd);
+                s.d_Pd = s.z_r + (s.beta * s.beta) * s.d_Pd;
+                s.done = 0;
+            } else if (s.done == 4) {
+                s.done = 1;
+            }
+        }
+        __syncthreads();
+        bool all_done = true;
+#pragma unroll
+        for (int c = 0; c < P; ++c) all_done = all_done && (cs[c].done == 1);
+        fence_proxy_async();
+        grid.sync();
+        if (all_done) break;
+    }
+
+    // Lock-step tCG with merged reductions (the arithmetic of SphereFam::tcg, fam_sphere.cuh): per iteration one S.V
+    // pass, one 6-value and one 4-value reduction round, three vector phases, four grid barriers.
+    for (int j = 0; MODE == 2 && j < maxinner; ++j) {
+        stream_pass<P>(prm, sm, pipe);
+        grid.sync();
+        // ---- M1: Sv; a=<x,Sv> b=<x,v> g1=<w,v> h1=<v,Sv> h2=<v,v> h3=<v,(y/s)v> ------------------------------------
+        {
+            double part[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            if (cs[myc].done != 1) {
+                FOR_ELEMS(e) {
+                    const double sv = gather_elem(prm, (int)(e / P), myc, P);
+                    const double x = prm.X[e], v = prm.V[e], ys = prm.ys[e];
+                    prm.Sv[e] = sv;
+                    part[0] = fma(x, sv, part[0]);
+                    part[1] = fma(x, v, part[1]);
+                    part[2] = fma(x * ys, v, part[2]);
+                    part[3] = fma(v, sv, part[3]);
+                    part[4] = fma(v, v, part[4]);
+                    part[5] = fma(v, ys * v, part[5]);
+                }
+            }
+            block_reduce_store<P, 6>(prm, sm, part, buf);
+        }
+        grid.sync();
+        gather_scalars<P, 6>(prm, sm, buf);
+        buf ^= 1;
+        if (tid < P && !cs[tid].done) {
+            ColState& s = cs[tid];
+            const double a = sm.scal[tid], b = sm.scal[P + tid], g1 = sm.scal[2 * P + tid], h1 = sm.scal[3 * P + tid],
+                         h2 = sm.scal[4 * P + tid], h3 = sm.scal[5 * P + tid];
+            s.a = a;
+            s.b = b;
+            s.d = prm.embedded ? g1 : (g1 - b * s.q);
+            const double dt = prm.embedded ? h3 : (h3 - b * g1);
+            const double d_Hd = (((-h1 + a * b) + s.kappa * h2) + dt) - s.d * b;
+            s.alpha = 0.0;
+            double e_Pe_new = s.e_Pe;
+            if (d_Hd != 0.0) {
+                s.alpha = s.z_r / d_Hd;
+                e_Pe_new = (s.e_Pe + (2.0 * s.alpha) * s.e_Pd) + (s.alpha * s.alpha) * s.d_Pd;
+            }
+            s.iters = j + 1;
+            if (d_Hd <= 0.0 || e_Pe_new >= s.Delta2) {
+                s.alpha = (-s.e_Pd + sqrt(s.e_Pd * s.e_Pd + s.d_Pd * (s.Delta2 - s.e_Pe))) / s.d_Pd;  // tau
+                s.stop = (d_Hd <= 0.0) ? RIPTRM_TCG_NEGATIVE_CURVATURE : RIPTRM_TCG_EXCEEDED_TR;
+                s.done = 2;
+            } else {
+                s.e_Pe = e_Pe_new;
+            }
+        }
+        __syncthreads();
+        // ---- M2: Hd = Hw[v]; tentative eta, Heta, r; <eta',c> <eta',Heta'> <r',r'> <x,r'> --------------------------
+        {
+            double part[4] = {0.0, 0.0, 0.0, 0.0};
+            const int done = cs[myc].done;
+            if (done != 1) {
+                const double a = cs[myc].a, b = cs[myc].b, d = cs[myc].d, kappa = cs[myc].kappa, al = cs[myc].alpha;
+                FOR_ELEMS(e) {
+                    const double x = prm.X[e], v = prm.V[e];
+                    const double ga = prm.embedded ? v : (v - x * b);
+                    const double tt = prm.ys[e] * ga;
+                    const double hl = (-prm.Sv[e] + a * x) + kappa * v;
+                    const double gg = tt - d * x;
+                    const double hd = hl + gg;
+                    const double ne = prm.eta[e] + al * v;
+                    const double nh = prm.Heta[e] + al * hd;
+                    if (done == 2) {
+                        prm.eta[e] = ne;
+                        prm.Heta[e] = nh;
+                    } else {
+                        const double nr = prm.r[e] + al * hd;
+                        prm.eta2[e] = ne;
+                        prm.Heta2[e] = nh;
+                        prm.r2[e] = nr;
+                        part[0] = fma(ne, prm.c[e], part[0]);
+                        part[1] = fma(ne, nh, part[1]);
+                        part[2] = fma(nr, nr, part[2]);
+                        part[3] = fma(x, nr, part[3]);
+                    }
+                }
+            }
+            block_reduce_store<P, 4>(prm, sm, part, buf);
+        }
+        grid.sync();
+        gather_scalars<P, 4>(prm, sm, buf);
+        buf ^= 1;
+        if (tid < P) {
+            ColState& s = cs[tid];
+            if (s.done == 2) {
+                s.done = 1;
+            } else if (!s.done) {
+                const double new_model = sm.scal[tid] + 0.5 * sm.scal[P + tid];
+                if (new_model >= s.model_value) {
+                    s.stop = RIPTRM_TCG_MODEL_INCREASED;
+                    s.done = 1;
+                } else {
+                    s.model_value = new_model;
+                    s.r_r = sm.scal[2 * P + tid];
+                    const double norm_r = sqrt(s.r_r);
+                    s.done = 3;
+                    if (j >= prm.tcg_mininner && norm_r <= s.target) {
+                        s.stop = (prm.tcg_kappa < s.nr_theta) ? RIPTRM_TCG_REACHED_TARGET_LINEAR
+                                                               : RIPTRM_TCG_REACHED_TARGET_SUPERLINEAR;
+                        s.done = 4;
+                    } else {
+                        const double zold = s.z_r;
+                        s.z_r = s.r_r;
+                        s.beta = s.z_r / zold;
+                        s.xd = -sm.scal[3 * P + tid] + s.beta * s.b;  // <x, -r' + beta v>
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- M3: commit; v = P_x(-r + beta v) ----------------------------------------------------------------------
+        {
+            const int done = cs[myc].done;
+            if (done >= 3) {
+                const double beta = cs[myc].beta, xd = cs[myc].xd;
+                FOR_ELEMS(e) {
+                    const double rr = prm.r2[e];
+                    prm.eta[e] = prm.eta2[e];
+                    prm.Heta[e] = prm.Heta2[e];
+                    prm.r[e] = rr;
+                    if (done == 3) {
+                        const double dn = -rr + beta * prm.V[e];
+                        prm.V[e] = dn - xd * prm.X[e];
+                    }
+                }
+            }
         }
         __syncthreads();
         if (tid < P) {

@@ -98,7 +98,7 @@ def test_streaming_pass_is_linear_and_symmetric(rb):
 
 def test_whole_solve_matches_the_c_oracle_per_column(rb):
     """riptrm_solve on the COLUMNS family: every column is an independent Sphere RIPTRM run.  n = 100, p = 4 against
-    the C oracle (reference operation order) run column by column: identical outer / inner / tCG iteration counts in
+    the C oracle (same merged-reduction tCG, different summation order) run column by column: identical outer / inner / tCG iteration counts in
     the well-conditioned window (8 outer iterations), final iterate / objective / multipliers to 1e-8 after 30."""
     from oracle.c import binding as detc
     n, p = 100, 4
@@ -111,8 +111,7 @@ def test_whole_solve_matches_the_c_oracle_per_column(rb):
         X, Y, sm, tr = cs.solve(X0, Y0, opt, per_outer_trace=True)
         SM = rb._lib.SM
         for c in range(p):
-            xo, yo, so, _ = detc.solve(Z, X0[:, c].copy(), Y0[:, c].copy(), {"maxiter": K, "tolresid": 0, "inner_maxiter": 1000},
-                                       faithful=True)
+            xo, yo, so, _ = detc.solve(Z, X0[:, c].copy(), Y0[:, c].copy(), {"maxiter": K, "tolresid": 0, "inner_maxiter": 1000})
             assert sm[c, SM["outer_iters"]] == so[10] == K and sm[c, SM["stop_reason"]] == 2
             if exact_counts:
                 assert sm[c, SM["inner_iters"]] == so[11], (c, sm[c, SM["inner_iters"]], so[11])
