@@ -83,3 +83,52 @@ except Exception as e:
         assert line == "RESULT solved"
     else:
         assert line.startswith("RESULT RiptrmError") and "riptrm error -2" in line, line
+
+
+def test_output_goes_through_the_reference_save_output_unchanged():
+    """Wire format: an `Output` built by the host mirror from solver trace rows (here the
+    rows come from the C oracle, which emits the device's trace layout) is written by the reference's own
+    `Simulator.save_output` (src/base/base_simulator.py:75-95) and read back: log.csv has the reference's columns in the
+    reference's order (+ tcg_iters), one row per logged iteration, and the analyzers' filter
+    `inner_status == "converged"` selects one row per outer iteration."""
+    script = r'''
+import sys, os, json, copy, tempfile
+sys.path.insert(0, {repo!r})
+import numpy as np, pandas as pd
+from oracle.run_reference import load_cfg, REFERENCE
+import riptrm_b200 as rb
+from oracle.c import binding as detc
+scratch = tempfile.mkdtemp(prefix="riptrm_save_")
+os.symlink(REFERENCE + "/src", scratch + "/src"); os.symlink(REFERENCE + "/dataset", scratch + "/dataset")
+os.chdir(scratch)
+sys.path[:0] = [{repo!r} + "/oracle/shims", "./src/NonnegPCA", "./src/solver", "./src/base"]
+import simulator
+cfg = load_cfg("NonnegPCA", {{"solver_name": ["RIPTRM"]}})
+sim = simulator.Simulator(cfg)
+os.makedirs(cfg.output_path, exist_ok=True)
+Z = np.loadtxt("dataset/NonnegPCA/1/Z.csv"); x0 = np.loadtxt("dataset/NonnegPCA/1/initx_a.csv"); y0 = np.loadtxt("dataset/NonnegPCA/1/initineqLagmult.csv")
+K = 6
+x, y, sm, tr = detc.solve(Z, x0, y0, {{"maxiter": K, "tolresid": 0}}, trace_capacity=128)
+option = rb.options.default_option(); option.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=K)
+option["stoppingcriterion"] = "Max iteration count reached; maxiter=6 after 0.00 seconds"
+out = rb.Output(name="RIPTRM_tCG", x=x, option=option, log=rb.trace_to_log(tr), ineqLagmult=y, eqLagmult=[])
+sim.save_output(out.name, copy.deepcopy(out))
+log = pd.read_csv(cfg.output_path + "/RIPTRM_tCG_log.csv")
+xs = np.loadtxt(cfg.output_path + "/RIPTRM_tCG_x.csv")
+res = {{"columns": list(log.columns), "rows": len(log), "conv": int((log["inner_status"] == "converged").sum()),
+       "x_equal": bool(np.array_equal(xs, x)), "iter_last": int(log["iteration"].iloc[-1]),
+       "files": sorted(os.listdir(cfg.output_path))}}
+print("RESULT " + json.dumps(res))
+'''.format(repo=REPO)
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, cwd=REPO, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    import json
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    ref_cols = ["iteration", "time", "cost", "distance", "residual", "gradnorm", "complviolation", "dualviolation",
+                "manviolation", "maxviolation", "meanviolation", "mu", "num_inner", "inner_status", "TR_radius", "dxtype",
+                "normdx", "minxfeasi", "minyfeasi", "compl", "mineigvalHw", "ared/pred", "radius_update", "dual_clipping",
+                "maxabsLagmult"]
+    assert res["columns"][:len(ref_cols)] == ref_cols and res["columns"][len(ref_cols):] == ["tcg_iters"]
+    assert res["conv"] == 6 and res["iter_last"] == 6 and res["x_equal"]
+    assert {"RIPTRM_tCG_log.csv", "RIPTRM_tCG_x.csv", "RIPTRM_tCG_option.csv", "RIPTRM_tCG_ineqLagmult.csv",
+            "RIPTRM_tCG_eqLagmult.csv", "RIPTRM_tCG_name.csv"} <= set(res["files"])
