@@ -18,7 +18,8 @@ namespace riptrm {
 // so one LDS.128 per lane fetches a lane's two entries of a row of S (shared-memory instruction issue, one
 // warp-wide load per 4 cycles per scheduler, is what bounds a single warp's S.v: 2x fewer instructions than
 // LDS.64 with the lane-strided layout; measured with scripts/microbench.cu).  K = 2 for n <= 64, 4 for n <= 128.
-template <int K_>
+// NFIX > 0 fixes n at compile time (the reference's dim = 50: S.v fully unrolled, no remainder loops).
+template <int K_, int NFIX = 0>
 struct SphereFam {
     static constexpr int K = K_;
     static constexpr int MK = K_;
@@ -46,11 +47,13 @@ struct SphereFam {
         double kappa;  // x'Sx + y'x
     };
 
+    static __device__ __forceinline__ int dimn(const Ctx& c) { return NFIX > 0 ? NFIX : c.n; }
+    static __device__ __forceinline__ int stride(const Ctx& c) { return NFIX > 0 ? ((NFIX + 1) & ~1) : c.ns; }
     static __device__ __forceinline__ int elem(int k) { return 64 * (k >> 1) + 2 * lane_id() + (k & 1); }
-    static __device__ __forceinline__ bool active(const Ctx& c, int k) { return elem(k) < c.n; }
+    static __device__ __forceinline__ bool active(const Ctx& c, int k) { return elem(k) < dimn(c); }
     static __device__ __forceinline__ bool cactive(const Ctx& c, int k) { return active(c, k); }
-    static __device__ __forceinline__ int dim(const Ctx& c) { return c.n - 1; }
-    static __device__ __forceinline__ int num_constraints(const Ctx& c) { return c.n; }
+    static __device__ __forceinline__ int dim(const Ctx& c) { return dimn(c) - 1; }
+    static __device__ __forceinline__ int num_constraints(const Ctx& c) { return dimn(c); }
     static __device__ __forceinline__ double typical_dist(const Ctx&) { return 3.141592653589793; }
     static __device__ __forceinline__ bool domain_ok(const Ctx&, const Pt&) { return true; }
 
@@ -59,7 +62,7 @@ struct SphereFam {
     // dependent-FMA chain; their sum order is part of the arithmetic specification.
     static __device__ __forceinline__ Vec matvec(const Ctx& c, const Vec& v) {
         const int lane = lane_id();
-        const int n = c.n;
+        const int n = dimn(c);
         double2* vb2 = reinterpret_cast<double2*>(c.vbuf);
 #pragma unroll
         for (int q = 0; q < K / 2; ++q) vb2[32 * q + lane] = make_double2(v.v[2 * q], v.v[2 * q + 1]);
@@ -67,10 +70,10 @@ struct SphereFam {
         double a0[K], a1[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) a0[k] = a1[k] = 0.0;
-        const int ns2 = c.ns >> 1;
+        const int ns2 = stride(c) >> 1;
         const double2* row = reinterpret_cast<const double2*>(c.S) + lane;
         int j = 0;
-#pragma unroll 5
+#pragma unroll(NFIX > 0 ? 32 : 5)
         for (; j + 1 < n; j += 2) {
             const double2 vj = *reinterpret_cast<const double2*>(c.vbuf + j);
 #pragma unroll
