@@ -55,6 +55,64 @@ __device__ __forceinline__ void wsumN(double (&v)[N]) {
         for (int i = 0; i < N; ++i) v[i] = v[i] + t[i];
     }
 }
+// Sums of 4 (8) values over the warp with half the shuffles of independent butterflies: at the xor-16 (and xor-8,
+// xor-4) level each lane keeps half of its values and trades the other half, so value i ends up being reduced by
+// the 8 (4) lanes whose bits 4,3(,2) spell i, through exactly the butterfly's pairing (l, l^16), (l, l^8), ...;
+// a final round of broadcasts hands every total to every lane.  Each total therefore has the same summation tree --
+// hence the same bits -- as wsum() of that value; the cost is 20 (30) SHFL.32 instead of 40 (80), which matters
+// because a single warp issues one shuffle per ~4 cycles (scripts/microbench.cu).
+__device__ __forceinline__ void wsum4x(double (&v)[4]) {
+    const int lane = lane_id();
+    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0;
+    double ka = h16 ? v[2] : v[0], kb = h16 ? v[3] : v[1];
+    const double sa = h16 ? v[0] : v[2], sb = h16 ? v[1] : v[3];
+    const double ra = __shfl_xor_sync(kFull, sa, 16), rb = __shfl_xor_sync(kFull, sb, 16);
+    ka = ka + ra;
+    kb = kb + rb;
+    double k = h8 ? kb : ka;
+    const double s = h8 ? ka : kb;
+    k = k + __shfl_xor_sync(kFull, s, 8);
+    k = k + __shfl_xor_sync(kFull, k, 4);
+    k = k + __shfl_xor_sync(kFull, k, 2);
+    k = k + __shfl_xor_sync(kFull, k, 1);
+    v[0] = __shfl_sync(kFull, k, 0);
+    v[1] = __shfl_sync(kFull, k, 8);
+    v[2] = __shfl_sync(kFull, k, 16);
+    v[3] = __shfl_sync(kFull, k, 24);
+}
+// 8 slots; only the first NV totals are broadcast back (the rest are padding the caller set to 0)
+template <int NV>
+__device__ __forceinline__ void wsum8x(double (&v)[8]) {
+    const int lane = lane_id();
+    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+    double k4[4], s4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        k4[i] = h16 ? v[4 + i] : v[i];
+        s4[i] = h16 ? v[i] : v[4 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s4[i] = __shfl_xor_sync(kFull, s4[i], 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) k4[i] = k4[i] + s4[i];
+    double k2[2], s2[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        k2[i] = h8 ? k4[2 + i] : k4[i];
+        s2[i] = h8 ? k4[i] : k4[2 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) s2[i] = __shfl_xor_sync(kFull, s2[i], 8);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) k2[i] = k2[i] + s2[i];
+    double k = h4 ? k2[1] : k2[0];
+    const double s = h4 ? k2[0] : k2[1];
+    k = k + __shfl_xor_sync(kFull, s, 4);
+    k = k + __shfl_xor_sync(kFull, k, 2);
+    k = k + __shfl_xor_sync(kFull, k, 1);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = __shfl_sync(kFull, k, ((i & 4) ? 16 : 0) + ((i & 2) ? 8 : 0) + ((i & 1) ? 4 : 0));
+}
 __device__ __forceinline__ double wmin(double p) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) p = fmin(p, __shfl_xor_sync(kFull, p, off));

@@ -214,9 +214,9 @@ struct SphereFam {
             Vec tmp;
 #pragma unroll
             for (int k = 0; k < K; ++k) tmp.v[k] = st.ys.v[k] * delta.v[k];
-            double s6[6] = {wdot_partial(pt.x, Sv), wdot_partial(pt.x, delta), wdot_partial(wv, delta),
-                            wdot_partial(delta, Sv), wdot_partial(delta, delta), wdot_partial(delta, tmp)};
-            wsumN<6>(s6);
+            double s6[8] = {wdot_partial(pt.x, Sv), wdot_partial(pt.x, delta), wdot_partial(wv, delta),
+                            wdot_partial(delta, Sv), wdot_partial(delta, delta), wdot_partial(delta, tmp), 0.0, 0.0};
+            wsum8x<6>(s6);
             const double a = s6[0], b = s6[1], g1 = s6[2], h1 = s6[3], h2 = s6[4], h3 = s6[5];
             const double d = ctx.embedded ? g1 : (g1 - b * q);
             Vec Hd;
@@ -256,7 +256,7 @@ struct SphereFam {
             }
             double s4[4] = {wdot_partial(new_eta, st.c), wdot_partial(new_eta, new_Heta), wdot_partial(r_new, r_new),
                             wdot_partial(pt.x, r_new)};
-            wsumN<4>(s4);
+            wsum4x(s4);
             const double new_model = s4[0] + 0.5 * s4[1];      // :86-87, :162
             if (new_model >= model_value) {                    // :163
                 res.stop = RIPTRM_TCG_MODEL_INCREASED;
