@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libriptrm_b200.so")
 SOURCES = ["riptrm_api.cu"]
 NVCC_FLAGS = [
-    "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo", "-fmad=false",
+    "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo", "-fmad=false", "--split-compile", "0",
     "-gencode", "arch=compute_100a,code=sm_100a",
 ]
 
