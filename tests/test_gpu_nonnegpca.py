@@ -185,3 +185,68 @@ def test_gpu_batch_is_bit_identical_to_the_c_oracle_on_generated_pairs(rb, split
     assert np.array_equal(x, xo) and np.array_equal(y, yo)
     assert np.array_equal(sm[:, :15], smo[:, :15])
     assert (sm[:, 1] < 1e-9).all()
+
+
+@pytest.mark.parametrize("n", [7, 33, 64, 100, 128])
+def test_other_sizes_are_bit_identical_to_the_c_oracle(rb, n):
+    """Edge sizes of the Sphere family: tiny, odd (padded row stride), the K=2 / K=4 boundary (64), K=4, the maximum
+    (128).  Three pairs each under a 12-outer-iteration protocol: x, y and summaries equal the C oracle bit for bit."""
+    from oracle.c import binding as detc
+    B = 3
+    Z, x0, y0 = rb.datagen.nonnegpca_batch(500 + n, B, n)
+    opt = rb.options.default_option()
+    opt.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=12, inner_maxiter=1000, tolresid=0, maxtime=1e9)
+    bs = rb.BatchSolver.nonnegpca_from_arrays(Z, x0, y0)
+    bs.set_options(opt, 0, 0)
+    x, y, sm, _ = bs.solve()
+    bs.close()
+    xo, yo, smo = detc.solve_many(Z, x0, y0, {"maxiter": 12, "inner_maxiter": 1000, "tolresid": 0})
+    assert np.array_equal(x, xo) and np.array_equal(y, yo)
+    assert np.array_equal(sm[:, :15], smo[:, :15])
+    assert np.allclose(np.linalg.norm(x, axis=1), 1.0, atol=1e-14) and (x > 0).all()
+
+
+def test_shared_Z_many_initial_points(rb, datasets):
+    """'instances x initial points': one Z (batch_z = 1) shared by 32 feasible starting points (generator.py:46-51
+    law).  Same results as 32 separate pairs carrying their own copy of Z; all reach the same KKT quality."""
+    d = datasets["NonnegPCA/1"]
+    pts = rb.datagen.more_initial_points(d["initx_a"], seed=1, count=32)
+    y0 = np.ones((32, 50))
+    opt = rb.options.default_option()
+    opt.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=30, inner_maxiter=1000, tolresid=0, maxtime=1e9)
+    shared = rb.BatchSolver.nonnegpca_from_arrays(d["Z"][None], pts, y0)
+    shared.set_options(opt, 0, 0)
+    xs, ys, sms, _ = shared.solve()
+    shared.close()
+    own = rb.BatchSolver.nonnegpca_from_arrays(np.repeat(d["Z"][None], 32, axis=0), pts, y0)
+    own.set_options(opt, 0, 0)
+    xo, yo, smo, _ = own.solve()
+    own.close()
+    assert np.array_equal(xs, xo) and np.array_equal(ys, yo) and np.array_equal(sms[:, :15], smo[:, :15])
+    assert (sms[:, 1] < 1e-9).all()
+    # a nonconvex problem: different starts may end in different KKT points, each a feasible unit vector
+    assert np.allclose(np.linalg.norm(xs, axis=1), 1.0, atol=1e-14) and (xs > -1e-12).all()
+
+
+def test_error_paths_through_the_c_abi(rb):
+    """Call-order and argument errors come back as codes + messages (RiptrmError), never as a crash."""
+    import ctypes as C
+    lib = rb.load_library()
+    h = C.c_void_p()
+    rb._lib.check(lib.riptrm_create(1, 50, 1, 50, 4, 0, C.byref(h)))
+    x = np.ones((4, 50)) / np.sqrt(50)
+    with pytest.raises(rb.RiptrmError, match="riptrm_set_<family>"):
+        rb._lib.check(lib.riptrm_solve(h, rb._lib.ptr(x), rb._lib.ptr(x), None, None, None, None, 0, None))
+    Z = np.zeros((4, 50, 50))
+    rb._lib.check(lib.riptrm_set_nonnegpca(h, rb._lib.ptr(Z), 4, C.c_double(0.0), 0))
+    with pytest.raises(rb.RiptrmError, match="riptrm_set_options"):
+        rb._lib.check(lib.riptrm_solve(h, rb._lib.ptr(x), rb._lib.ptr(x), None, None, None, None, 0, None))
+    with pytest.raises(rb.RiptrmError, match="batch_z"):
+        rb._lib.check(lib.riptrm_set_nonnegpca(h, rb._lib.ptr(Z), 3, C.c_double(0.0), 0))
+    with pytest.raises(rb.RiptrmError):
+        rb._lib.check(lib.riptrm_set_rosenbrock(h, C.c_double(1.0), C.c_double(0.01)))
+    assert lib.riptrm_destroy(h) == 0
+    with pytest.raises(rb.RiptrmError, match="n <= 128"):
+        rb._lib.check(lib.riptrm_create(1, 129, 1, 129, 1, 0, C.byref(h)))
+    with pytest.raises(NotImplementedError):
+        rb.RIPTRM({"TRS_solver": "Exact_RepMat"}).run_batch([None], structures=[rb.NonnegPCAStructure(Z=Z[0], x0=x[0], y0=x[0])])
