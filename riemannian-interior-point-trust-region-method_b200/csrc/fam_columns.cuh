@@ -132,6 +132,10 @@ struct Smem {
     double scal[MAXQ * P];
     alignas(8) uint64_t full[STAGES];
     alignas(8) uint64_t empty[STAGES];
+    // who contributes partials to the column blocks this CTA's rows fall into (built once per launch)
+    unsigned long long gt_base[4][8];
+    int gt_n[4];
+    int gt_ib_first, gt_ok;
 };
 
 struct Pipe {
@@ -257,6 +261,48 @@ __device__ __forceinline__ double gather_elem(const Params& prm, int row, int c,
     return out;
 }
 
+// The same sum through a per-CTA table of contributors (no index arithmetic or schedule loads per element)
+template <int P>
+__device__ __forceinline__ void build_gather_tab(const Params& prm, Smem<P>& sm, int row_lo, int row_hi) {
+    if (threadIdx.x == 0) {
+        const int G = gridDim.x;
+        sm.gt_ok = 1;
+        sm.gt_ib_first = row_lo / TW;
+        const int ib_last = (row_hi > row_lo) ? (row_hi - 1) / TW : sm.gt_ib_first;
+        if (ib_last - sm.gt_ib_first >= 4) sm.gt_ok = 0;
+        for (int ib = sm.gt_ib_first; sm.gt_ok && ib <= ib_last; ++ib) {
+            const long long tb = (long long)ib * prm.NJT, te = tb + prm.NJT;
+            int g = (int)(((double)tb * G) / (double)prm.total_tiles);
+            g = min(max(g, 0), G - 1);
+            while (g > 0 && prm.tbeg[g] > tb) --g;
+            while (g < G - 1 && prm.tbeg[g + 1] <= tb) ++g;
+            int cnt = 0;
+            for (; g < G; ++g) {
+                const long long b = prm.tbeg[g], e = prm.tbeg[g + 1];
+                if (b >= te) break;
+                if (e <= b) continue;
+                if (cnt == 8) {
+                    sm.gt_ok = 0;
+                    break;
+                }
+                sm.gt_base[ib - sm.gt_ib_first][cnt++] =
+                    ((unsigned long long)g * prm.slots + (unsigned long long)(ib - prm.tib0[g])) * TW * P;
+            }
+            sm.gt_n[ib - sm.gt_ib_first] = cnt;
+        }
+    }
+    __syncthreads();
+}
+template <int P>
+__device__ __forceinline__ double gather_fast(const Params& prm, const Smem<P>& sm, int row, int c) {
+    if (!sm.gt_ok) return gather_elem(prm, row, c, P);
+    const int ib = row / TW, ii = row - ib * TW, k = ib - sm.gt_ib_first;
+    const int cnt = sm.gt_n[k];
+    double out = prm.mv_part[sm.gt_base[k][0] + (size_t)ii * P + c];
+    for (int q = 1; q < cnt; ++q) out = out + prm.mv_part[sm.gt_base[k][q] + (size_t)ii * P + c];
+    return out;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Vector phases: thread `tid` < NTV = (NT / P) * P owns the elements e = ebeg + tid + k * NTV of the CTA's
 // row chunk, all of column c = tid % P.  Per-thread partial dot products are summed per column in thread
@@ -276,15 +322,21 @@ __device__ __forceinline__ void block_reduce_store(const Params& prm, Smem<P>& s
     }
 }
 
+// after a grid barrier: scal[q*P+c] = sum over CTAs.  Four lanes per value (lane-strided partial sums over the CTAs,
+// then a two-level butterfly), eight values per warp: all Q*P <= 72 totals in one round.
 template <int P, int Q>
 __device__ __forceinline__ void gather_scalars(const Params& prm, Smem<P>& sm, int buf) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x;
-    for (int k = warp; k < Q * P; k += NCW + 1) {
+#pragma unroll
+    for (int base = 0; base < Q * P; base += 8 * (NCW + 1)) {
+        const int k = base + warp * 8 + (lane >> 2), sub = lane & 3;
         double s = 0.0;
-        for (int g = lane; g < G; g += 32) s = s + prm.dot_part[((size_t)buf * G + g) * (MAXQ * MAXP) + k];
-        s = wsum(s);
-        if (lane == 0) sm.scal[k] = s;
+        if (k < Q * P)
+            for (int g = sub; g < G; g += 4) s = s + prm.dot_part[((size_t)buf * G + g) * (MAXQ * MAXP) + k];
+        s = s + __shfl_xor_sync(kFull, s, 1);
+        s = s + __shfl_xor_sync(kFull, s, 2);
+        if (k < Q * P && sub == 0) sm.scal[k] = s;
     }
     __syncthreads();
 }
@@ -323,6 +375,7 @@ __global__ void __launch_bounds__(NT, 1) columns_kernel(Params prm) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    build_gather_tab<P>(prm, sm, row_lo, row_hi);
     Pipe pipe{0, 0u};
     int buf = 0;
     if (MODE == 3) {
@@ -360,7 +413,7 @@ __global__ void __launch_bounds__(NT, 1) columns_kernel(Params prm) {
         double part[3] = {0.0, 0.0, 0.0};
         const double mu_c = cs[myc].mu;
         FOR_ELEMS(e) {
-            const double sx = prm.solve ? prm.Sx[e] : gather_elem(prm, (int)(e / P), myc, P);
+            const double sx = prm.solve ? prm.Sx[e] : gather_fast<P>(prm, sm, (int)(e / P), myc);
             const double x = prm.X[e], y = prm.Y[e];
             const double s = x + prm.eps;
             const double w = mu_c * (1.0 / s);
@@ -441,7 +494,7 @@ __global__ void __launch_bounds__(NT, 1) columns_kernel(Params prm) {
         {
             double part[2] = {0.0, 0.0};
             FOR_ELEMS(e) {
-                const double sv = gather_elem(prm, (int)(e / P), myc, P);
+                const double sv = gather_fast<P>(prm, sm, (int)(e / P), myc);
                 const double x = prm.X[e];
                 prm.Sv[e] = sv;
                 part[0] = fma(x, sv, part[0]);
@@ -624,14 +677,24 @@ __global__ void __launch_bounds__(NT, 1) columns_kernel(Params prm) {
     // Lock-step tCG with merged reductions (the arithmetic of SphereFam::tcg, fam_sphere.cuh): per iteration one S.V
     // pass, one 6-value and one 4-value reduction round, three vector phases, four grid barriers.
     for (int j = 0; MODE == 2 && j < maxinner; ++j) {
+#ifdef RIPTRM_COLUMNS_TIMING  // build with -DRIPTRM_COLUMNS_TIMING: CTA 0 prints the phase times of iteration 5
+        const bool dbg = g == 0 && tid == 0 && j == 5;
+        uint64_t tdbg[8];
+#define TDBG(i) if (dbg) tdbg[i] = global_timer_ns()
+#else
+#define TDBG(i)
+#endif
+        TDBG(0);
         stream_pass<P>(prm, sm, pipe);
+        TDBG(1);
         grid.sync();
+        TDBG(2);
         // ---- M1: Sv; a=<x,Sv> b=<x,v> g1=<w,v> h1=<v,Sv> h2=<v,v> h3=<v,(y/s)v> ------------------------------------
         {
             double part[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
             if (cs[myc].done != 1) {
                 FOR_ELEMS(e) {
-                    const double sv = gather_elem(prm, (int)(e / P), myc, P);
+                    const double sv = gather_fast<P>(prm, sm, (int)(e / P), myc);
                     const double x = prm.X[e], v = prm.V[e], ys = prm.ys[e];
                     prm.Sv[e] = sv;
                     part[0] = fma(x, sv, part[0]);
@@ -644,8 +707,10 @@ __global__ void __launch_bounds__(NT, 1) columns_kernel(Params prm) {
             }
             block_reduce_store<P, 6>(prm, sm, part, buf);
         }
+        TDBG(3);
         grid.sync();
         gather_scalars<P, 6>(prm, sm, buf);
+        TDBG(4);
         buf ^= 1;
         if (tid < P && !cs[tid].done) {
             ColState& s = cs[tid];
@@ -704,8 +769,10 @@ __global__ void __launch_bounds__(NT, 1) columns_kernel(Params prm) {
             }
             block_reduce_store<P, 4>(prm, sm, part, buf);
         }
+        TDBG(5);
         grid.sync();
         gather_scalars<P, 4>(prm, sm, buf);
+        TDBG(6);
         buf ^= 1;
         if (tid < P) {
             ColState& s = cs[tid];
@@ -769,6 +836,17 @@ __global__ void __launch_bounds__(NT, 1) columns_kernel(Params prm) {
         for (int c = 0; c < P; ++c) all_done = all_done && (cs[c].done == 1);
         fence_proxy_async();
         grid.sync();
+#ifdef RIPTRM_COLUMNS_TIMING
+        if (dbg) {
+            tdbg[7] = global_timer_ns();
+            printf("columns tCG it 5 (CTA 0, ns): stream %llu | sync %llu | M1 %llu | sync+gather %llu | M2 %llu | sync+gather %llu | M3+sync %llu | total %llu\n",
+                   (unsigned long long)(tdbg[1] - tdbg[0]), (unsigned long long)(tdbg[2] - tdbg[1]),
+                   (unsigned long long)(tdbg[3] - tdbg[2]), (unsigned long long)(tdbg[4] - tdbg[3]),
+                   (unsigned long long)(tdbg[5] - tdbg[4]), (unsigned long long)(tdbg[6] - tdbg[5]),
+                   (unsigned long long)(tdbg[7] - tdbg[6]), (unsigned long long)(tdbg[7] - tdbg[0]));
+        }
+#endif
+#undef TDBG
         if (all_done) break;
     }
 
@@ -828,15 +906,20 @@ template <int P, int QS, int QM>
 __device__ __forceinline__ void gather_mixed(const Params& prm, Smem<P>& sm, int buf) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x;
-    for (int k = warp; k < (QS + QM) * P; k += NCW + 1) {
+    for (int base = 0; base < (QS + QM) * P; base += 8 * (NCW + 1)) {
+        const int k = base + warp * 8 + (lane >> 2), sub = lane & 3;
         const bool is_sum = k < QS * P;
         double s = is_sum ? 0.0 : CUDART_INF;
-        for (int g = lane; g < G; g += 32) {
-            const double v = prm.dot_part[((size_t)buf * G + g) * (MAXQ * MAXP) + k];
-            s = is_sum ? (s + v) : fmin(s, v);
-        }
-        s = is_sum ? wsum(s) : wmin(s);
-        if (lane == 0) sm.scal[k] = s;
+        if (k < (QS + QM) * P)
+            for (int g = sub; g < G; g += 4) {
+                const double v = prm.dot_part[((size_t)buf * G + g) * (MAXQ * MAXP) + k];
+                s = is_sum ? (s + v) : fmin(s, v);
+            }
+        const double t1 = __shfl_xor_sync(kFull, s, 1);
+        s = is_sum ? (s + t1) : fmin(s, t1);
+        const double t2 = __shfl_xor_sync(kFull, s, 2);
+        s = is_sum ? (s + t2) : fmin(s, t2);
+        if (k < (QS + QM) * P && sub == 0) sm.scal[k] = s;
     }
     __syncthreads();
 }
@@ -888,6 +971,7 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
         s.normdx = s.minx = s.miny = s.compl_v = CUDART_NAN;
     }
     __syncthreads();
+    build_gather_tab<P>(prm, sm, row_lo, row_hi);
     Pipe pipe{0, 0u};
     int buf = 0;
     const double nan = CUDART_NAN;
@@ -903,7 +987,7 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
         {
             double part[1] = {0.0};
             FOR_ELEMS(e) {
-                const double sx = gather_elem(prm, (int)(e / P), myc, P);
+                const double sx = gather_fast<P>(prm, sm, (int)(e / P), myc);
                 prm.Sx[e] = sx;
                 prm.Xprev[e] = prm.X[e];
                 part[0] = fma(prm.X[e], sx, part[0]);
@@ -974,7 +1058,7 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
             double part[1] = {0.0};
             if (ps[myc].path) {
                 FOR_ELEMS(e) {
-                    const double sx = gather_elem(prm, (int)(e / P), myc, P);
+                    const double sx = gather_fast<P>(prm, sm, (int)(e / P), myc);
                     prm.SxN[e] = sx;
                     part[0] = fma(prm.XN[e], sx, part[0]);
                 }
@@ -1073,7 +1157,7 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
                 double part[2] = {0.0, 0.0};
                 if (ps[myc].path == 3) {
                     FOR_ELEMS(e) {
-                        const double sv = gather_elem(prm, (int)(e / P), myc, P);
+                        const double sv = gather_fast<P>(prm, sm, (int)(e / P), myc);
                         const double x = prm.X[e];
                         prm.Sv[e] = sv;
                         part[0] = fma(x, sv, part[0]);
