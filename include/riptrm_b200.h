@@ -172,7 +172,9 @@ int riptrm_destroy(riptrm_handle* h);
 
 /* ---- problem data (replaces the coordinator's closures) -------------------------------- */
 /* NonnegPCA (families 1 and 4): Z is [batch_z][n][n] row-major, NOT symmetric
- * (src/NonnegPCA/coordinator.py:50-54); batch_z is `batch` (one Z per instance) or 1 (shared).
+ * (src/NonnegPCA/coordinator.py:50-54); batch_z divides `batch`: the batch is batch_z problem instances times
+ * batch / batch_z initial points each, pair i using Z[i / (batch / batch_z)] (batch_z == batch: one Z per pair;
+ * batch_z == 1: one Z shared by all pairs).
  * eps is the constraint offset: g_i = -x_i - eps (0 in the reference). */
 int riptrm_set_nonnegpca(riptrm_handle* h, const double* Z, int batch_z, double eps, int where);
 

@@ -156,28 +156,30 @@ def solve_many(Z, x0, y0, option=None, eps=0.0, threads=1):
     return x, y, sm
 
 
-def run_sample(protocol, dim, first_seed, target_seconds, threads, max_pairs):
-    """bench.py's CPU leg: pairs first_seed.. of the bench workload on `threads` host threads."""
-    from oracle.problems import nonnegpca_generate_instance
+def run_sample(protocol, dim, first_seed, target_seconds, threads, max_pairs, points_per_instance=1):
+    """bench.py's CPU leg: the first pairs of the bench sweep (instances first_seed.., `points_per_instance` initial
+    points each) on `threads` host threads, sized for about `target_seconds`."""
+    from oracle.problems import nonnegpca_generate_sweep
     opt = {k: v for k, v in protocol.items() if k not in ("TRS_solver", "second_order_stationarity", "maxtime")}
-    # calibrate on a few pairs, then size the sample for ~target_seconds
-    def gen(lo, cnt):
-        Z, X, Y = np.empty((cnt, dim, dim)), np.empty((cnt, dim)), np.empty((cnt, dim))
-        for i in range(cnt):
-            Z[i], X[i], Y[i] = nonnegpca_generate_instance(dim, seed=lo + i)
-        return Z, X, Y
-    ncal = min(max_pairs, 2 * threads)
-    Zc, Xc, Yc = gen(first_seed, ncal)
+    ipp = points_per_instance
+
+    def gen(n_inst):
+        Z, X, Y = nonnegpca_generate_sweep(first_seed, n_inst, ipp, dim)
+        return np.repeat(Z, ipp, axis=0), X, Y
+    ncal = max(1, min(max_pairs, 2 * threads) // ipp)
+    Zc, Xc, Yc = gen(ncal)
     t = time.perf_counter()
     solve_many(Zc, Xc, Yc, opt, threads=threads)
-    rate = ncal / (time.perf_counter() - t)
-    n = int(min(max_pairs, max(ncal, rate * target_seconds)))
-    Z, X, Y = gen(first_seed, n)
+    rate = ncal * ipp / (time.perf_counter() - t)
+    n_inst = int(min(max_pairs // ipp, max(ncal, rate * target_seconds / ipp)))
+    Z, X, Y = gen(n_inst)
     t = time.perf_counter()
     x, y, sm = solve_many(Z, X, Y, opt, threads=threads)
     secs = time.perf_counter() - t
+    n = n_inst * ipp
     return {"pairs": n, "seconds": secs, "tcg_iters": int(sm[:, 12].sum()), "threads": threads, "kind": "port",
             "engine": "c",
-            "sample": f"{n} pairs (seeds {first_seed}..{first_seed + n - 1}) of the bench workload, C oracle "
-                      f"(oracle/c/riptrm_det.c, closed-form derivatives, gcc -O2), {threads} host threads, full protocol",
+            "sample": f"{n} pairs (instances {first_seed}..{first_seed + n_inst - 1} x {ipp} initial points) of the bench "
+                      f"workload, C oracle (oracle/c/riptrm_det.c, closed-form derivatives, gcc -O2), {threads} host "
+                      "threads, full protocol",
             "max_residual": float(sm[:, 1].max())}

@@ -38,7 +38,8 @@ def _c_available():
         return False
 
 
-def run_sample(protocol, dim, first_seed=0, target_seconds=20.0, threads=None, max_pairs=4096, engine=None):
+def run_sample(protocol, dim, first_seed=0, target_seconds=20.0, threads=None, max_pairs=4096, engine=None,
+               points_per_instance=1):
     """Solves pairs first_seed.. on `threads` host threads for about `target_seconds` of wall time.
     Returns {"pairs", "seconds", "tcg_iters", "threads", "kind", "sample", "max_residual"}."""
     threads = threads or os.cpu_count() or 1
@@ -46,7 +47,7 @@ def run_sample(protocol, dim, first_seed=0, target_seconds=20.0, threads=None, m
         engine = "c" if _c_available() else "numpy"
     if engine == "c":
         from oracle.c import binding
-        return binding.run_sample(protocol, dim, first_seed, target_seconds, threads, max_pairs)
+        return binding.run_sample(protocol, dim, first_seed, target_seconds, threads, max_pairs, points_per_instance)
     threads = min(threads, 64, max_pairs)
     # the NumPy oracle needs ~10-20 s per pair: one pair per worker
     per_pair_guess = 15.0

@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(32, (K == 2) ? 8 : 4) sphere_kernel(SpherePara
         if (P.order != nullptr) inst = P.order[inst];
         double* pause = (P.pause != nullptr) ? P.pause + (size_t)inst * kPauseFields : nullptr;
         if (MODE == 0 && P.resume && pause[7] == 0.0) continue;  // finished in the first launch
-        const int zi = (P.batch_z == 1) ? 0 : inst;
+        const int zi = inst / (P.batch / P.batch_z);  // consecutive pairs of one instance share its Z
         if (zi != loaded_z) {
             load_S(P.Z + (size_t)zi * n * n, smem, n, ns, pad);
             loaded_z = zi;
@@ -599,7 +599,7 @@ extern "C" int riptrm_set_nonnegpca(riptrm_handle* h, const double* Z, int batch
     if (h == nullptr || Z == nullptr) return fail(RIPTRM_E_INVALID, "NULL argument");
     if (h->family != RIPTRM_FAMILY_NONNEGPCA_SPHERE && h->family != RIPTRM_FAMILY_NONNEGPCA_COLUMNS)
         return fail(RIPTRM_E_INVALID, "handle is not a NonnegPCA family");
-    if (batch_z != 1 && batch_z != h->batch) return fail(RIPTRM_E_INVALID, "batch_z must be 1 or batch");
+    if (batch_z < 1 || h->batch % batch_z != 0) return fail(RIPTRM_E_INVALID, "batch_z must divide batch (batch_z instances x batch/batch_z initial points)");
     CUDA_TRY(cudaSetDevice(h->device));
     if (h->family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS) return columns_setup(h, Z, eps, where);
     const size_t bytes = (size_t)batch_z * h->n * h->n * sizeof(double);

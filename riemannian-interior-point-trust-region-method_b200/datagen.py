@@ -46,3 +46,21 @@ def more_initial_points(x0, seed, count):
     rs = np.random.RandomState(seed)
     pts = rs.rand(count, x0.shape[0])
     return np.abs(pts / np.linalg.norm(pts, axis=1, keepdims=True))
+
+
+def nonnegpca_sweep(first_instance, instances, points_per_instance, dim=50, out=None):
+    """A sweep of `instances` problem instances x `points_per_instance` initial points (instance-major pair order):
+    Z [instances, dim, dim], x0 / y0 [instances * points_per_instance, dim].  Point 0 of an instance is the
+    generator's own x0 (seed = instance id); points k >= 1 follow the same law from seed 1000003 * (id + 1) + k."""
+    pairs = instances * points_per_instance
+    if out is None:
+        Z, x0, y0 = np.empty((instances, dim, dim)), np.empty((pairs, dim)), np.empty((pairs, dim))
+    else:
+        Z, x0, y0 = out
+    for i in range(instances):
+        inst = first_instance + i
+        Z[i], x0[i * points_per_instance], _ = nonnegpca_instance(dim, seed=inst)
+        for k in range(1, points_per_instance):
+            x0[i * points_per_instance + k] = more_initial_points(x0[0], 1000003 * (inst + 1) + k, 1)[0]
+    y0[:] = 1.0
+    return Z, x0, y0

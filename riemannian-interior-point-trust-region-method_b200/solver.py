@@ -98,8 +98,9 @@ class BatchSolver:
 
     @classmethod
     def nonnegpca_from_arrays(cls, Z, x0, y0, eps=0.0, device=0):
-        """Batch of NonnegPCA/Sphere pairs straight from arrays: Z [B or 1, n, n], x0 [B, n], y0 [B, n]
-        (host ndarrays; the sweep path of bench.py, no per-instance Python objects)."""
+        """Batch of NonnegPCA/Sphere pairs straight from arrays: Z [I, n, n] with I dividing B (I instances x B/I
+        initial points each, pair i uses Z[i // (B // I)]), x0 [B, n], y0 [B, n] (host ndarrays; the sweep path of
+        bench.py, no per-instance Python objects)."""
         self = cls.__new__(cls)
         Z = np.ascontiguousarray(Z, dtype=np.float64)
         self.x0 = np.ascontiguousarray(x0, dtype=np.float64)
