@@ -156,7 +156,7 @@ __device__ __forceinline__ void store_vec(double* g, const WVec<K>& r, int len) 
 
 // mode 0: whole solve; 1: one Hessian-vector product; 2: one tCG solve
 template <int K, int MODE, int NFIX>
-__global__ void __launch_bounds__(32, (K == 2) ? 8 : 4) sphere_kernel(SphereParams P, DevOpts o, int* counter) {
+__global__ void __launch_bounds__(32, (K == 2) ? 10 : 4) sphere_kernel(SphereParams P, DevOpts o, int* counter) {
     using F = SphereFam<K, NFIX>;
     extern __shared__ __align__(16) double smem[];
     const int n = P.n;
@@ -888,7 +888,7 @@ static SmallParams small_params(const riptrm_handle* h) {
 // iterations for every pair first, then the rest, longest first.  Bit-identical results either way.
 static int solve_scheduled(riptrm_handle* h, SphereParams P, const DevOpts& o, cudaStream_t st) {
     int split = h->opts.schedule_split;  //: 0 auto, < 0 off, > 0 outer iteration
-    const int resident = h->num_sms * 8;
+    const int resident = h->num_sms * 10;
     if (split == 0) split = (h->batch > resident && h->opts.maxiter > 12) ? 6 : -1;
     if (split <= 0 || split >= h->opts.maxiter) {
         P.order = nullptr;
