@@ -394,7 +394,7 @@ def nonnegpca_generate_instance(dim=50, snr=0.5, delta=0.7, seed=0):
 
 def nonnegpca_generate_sweep(first_instance, instances, points_per_instance, dim=50):
     """`instances` x `points_per_instance` (instance, initialpoint) pairs, instance-major: point 0 of an instance is
-    the generator's x0 (seed = instance id), points k >= 1 follow generator.py:46-51 from seed 1000003*(id+1)+k.
+    the generator's x0 (seed = instance id), points k >= 1 follow generator.py:46-51 from seed 2e9 + 16*id + k (k < 16).
     Returns Z [instances, dim, dim], x0 / y0 [pairs, dim]."""
     pairs = instances * points_per_instance
     Z, x0, y0 = np.empty((instances, dim, dim)), np.empty((pairs, dim)), np.ones((pairs, dim))
@@ -402,6 +402,6 @@ def nonnegpca_generate_sweep(first_instance, instances, points_per_instance, dim
         inst = first_instance + i
         Z[i], x0[i * points_per_instance], _ = nonnegpca_generate_instance(dim, seed=inst)
         for k in range(1, points_per_instance):
-            u = np.random.RandomState(1000003 * (inst + 1) + k).rand(1, dim)
+            u = np.random.RandomState(2000000000 + 16 * inst + k).rand(1, dim)
             x0[i * points_per_instance + k] = np.abs(u / np.linalg.norm(u, axis=1, keepdims=True))[0]
     return Z, x0, y0

@@ -51,7 +51,9 @@ def more_initial_points(x0, seed, count):
 def nonnegpca_sweep(first_instance, instances, points_per_instance, dim=50, out=None):
     """A sweep of `instances` problem instances x `points_per_instance` initial points (instance-major pair order):
     Z [instances, dim, dim], x0 / y0 [instances * points_per_instance, dim].  Point 0 of an instance is the
-    generator's own x0 (seed = instance id); points k >= 1 follow the same law from seed 1000003 * (id + 1) + k."""
+    generator's own x0 (seed = instance id); points k >= 1 follow the same law from seed 2e9 + 16 * id + k (k < 16)."""
+    if not 1 <= points_per_instance <= 16:
+        raise ValueError("1 <= points_per_instance <= 16")
     pairs = instances * points_per_instance
     if out is None:
         Z, x0, y0 = np.empty((instances, dim, dim)), np.empty((pairs, dim)), np.empty((pairs, dim))
@@ -61,6 +63,6 @@ def nonnegpca_sweep(first_instance, instances, points_per_instance, dim=50, out=
         inst = first_instance + i
         Z[i], x0[i * points_per_instance], _ = nonnegpca_instance(dim, seed=inst)
         for k in range(1, points_per_instance):
-            x0[i * points_per_instance + k] = more_initial_points(x0[0], 1000003 * (inst + 1) + k, 1)[0]
+            x0[i * points_per_instance + k] = more_initial_points(x0[0], 2000000000 + 16 * inst + k, 1)[0]
     y0[:] = 1.0
     return Z, x0, y0

@@ -126,3 +126,20 @@ def test_stableid_conspec_expansion(datasets):
     cs = rb.StableIdStructure.conspec_from_constset(datasets["StableIdentification/1"]["constset"])
     assert cs.shape == (16, 5)
     assert sorted(set(cs[:, 0])) == [0.0, 1.0, 2.0]
+
+
+def test_sweep_generator_matches_oracle_and_scales_to_8_gpus():
+    """Instance ids of rank 7 of an 8-GPU sweep (28672..32767) must still give valid NumPy seeds; product and oracle
+    generators agree; the initial points of an instance are distinct feasible unit vectors sharing its Z."""
+    from oracle.problems import nonnegpca_generate_sweep
+    for first in (0, 7 * 4096 + 4000, 10 ** 6):
+        a = rb.datagen.nonnegpca_sweep(first, 3, 4)
+        b = nonnegpca_generate_sweep(first, 3, 4)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        Z, x0, y0 = a
+        assert Z.shape == (3, 50, 50) and x0.shape == (12, 50)
+        assert np.allclose(np.linalg.norm(x0, axis=1), 1.0) and (x0 > 0).all()
+        assert len({tuple(r) for r in x0}) == 12
+        assert np.array_equal(x0[4], rb.datagen.nonnegpca_instance(50, seed=first + 1)[1])
+    with pytest.raises(ValueError):
+        rb.datagen.nonnegpca_sweep(0, 2, 17)
