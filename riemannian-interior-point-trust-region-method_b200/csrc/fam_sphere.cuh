@@ -11,6 +11,7 @@
 //   c           = grad f - G_x(mu / s)                     (:730)
 #pragma once
 #include "solver_warp.cuh"
+#include "tmem.cuh"
 
 namespace riptrm {
 
@@ -19,8 +20,13 @@ namespace riptrm {
 // warp-wide load per 4 cycles per scheduler, is what bounds a single warp's S.v: 2x fewer instructions than
 // LDS.64 with the lane-strided layout; measured with scripts/microbench.cu).  K = 2 for n <= 64, 4 for n <= 128.
 // NFIX > 0 fixes n at compile time (the reference's dim = 50: S.v fully unrolled, no remainder loops).
-template <int K_, int NFIX = 0>
+// TM = true keeps S in Tensor Memory instead of shared memory (n = 50 only): lane l's two columns of S are 200
+// consecutive 32-bit TMEM columns of the warp's own TMEM lane l, fetched with tcgen05.ld.32x32b (SASS LDTM).  With
+// every SM full, S.v from shared memory costs ~1890 cycles (the shared-memory pipe is the bottleneck: 83 % busy),
+// from TMEM ~630 (scripts/tmem_test.cu); the values and their order are the same, so results stay bit-identical.
+template <int K_, int NFIX = 0, bool TM = false>
 struct SphereFam {
+    static_assert(!TM || (NFIX == 50 && K_ == 2), "the TMEM layout is built for n = 50");
     static constexpr int K = K_;
     static constexpr int MK = K_;
     static_assert(K_ == 2 || K_ == 4, "pair layout: K is 2 or 4");
@@ -33,6 +39,7 @@ struct SphereFam {
         int n, ns;
         double eps;
         bool embedded;    // 'is_euclidean_embedded'
+        uint32_t taddr;   // TM: TMEM address of this warp's copy of S (lane field = 32 * (warp % 4))
     };
     struct Pt {
         Vec x;
@@ -41,6 +48,73 @@ struct SphereFam {
         Vec Sx;
         double xSx;
     };
+
+    // TM: move S from the staging buffer (shared memory, row-major) into this warp's TMEM lanes:
+    // TMEM column 4j + 2k (+1 for the high word) of lane l holds S[j][2l + k]
+    static __device__ __forceinline__ void stage_to_tmem(const Ctx& c) {
+        const double2* row = reinterpret_cast<const double2*>(c.S) + lane_id();
+        constexpr int H = NFIX > 0 ? NFIX / 2 : 1;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            uint32_t r[64];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const double2 sv = row[(16 * ch + jj) * H];
+                r[4 * jj + 0] = (uint32_t)__double2loint(sv.x);
+                r[4 * jj + 1] = (uint32_t)__double2hiint(sv.x);
+                r[4 * jj + 2] = (uint32_t)__double2loint(sv.y);
+                r[4 * jj + 3] = (uint32_t)__double2hiint(sv.y);
+            }
+            tmem::tmem_st_x64(c.taddr + 64 * ch, r);
+        }
+        uint32_t r[8];
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const double2 sv = row[(48 + jj) * H];
+            r[4 * jj + 0] = (uint32_t)__double2loint(sv.x);
+            r[4 * jj + 1] = (uint32_t)__double2hiint(sv.x);
+            r[4 * jj + 2] = (uint32_t)__double2loint(sv.y);
+            r[4 * jj + 3] = (uint32_t)__double2hiint(sv.y);
+        }
+        tmem::tmem_st_x8(c.taddr + 192, r);
+        tmem::wait_st();
+    }
+
+    static __device__ __forceinline__ Vec matvec_tmem(const Ctx& c, const Vec& v) {
+        const int lane = lane_id();
+        reinterpret_cast<double2*>(c.vbuf)[lane] = make_double2(v.v[0], v.v[1]);
+        __syncwarp();
+        double a0x = 0.0, a0y = 0.0, a1x = 0.0, a1y = 0.0;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            uint32_t r[64];
+            tmem::tmem_ld_x64(c.taddr + 64 * ch, r);
+            tmem::wait_ld();
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 2) {
+                const double2 vj = *reinterpret_cast<const double2*>(c.vbuf + 16 * ch + jj);
+                a0x = fma(__hiloint2double((int)r[4 * jj + 1], (int)r[4 * jj + 0]), vj.x, a0x);
+                a0y = fma(__hiloint2double((int)r[4 * jj + 3], (int)r[4 * jj + 2]), vj.x, a0y);
+                a1x = fma(__hiloint2double((int)r[4 * jj + 5], (int)r[4 * jj + 4]), vj.y, a1x);
+                a1y = fma(__hiloint2double((int)r[4 * jj + 7], (int)r[4 * jj + 6]), vj.y, a1y);
+            }
+        }
+        {
+            uint32_t r[8];
+            tmem::tmem_ld_x8(c.taddr + 192, r);
+            tmem::wait_ld();
+            const double2 vj = *reinterpret_cast<const double2*>(c.vbuf + 48);
+            a0x = fma(__hiloint2double((int)r[1], (int)r[0]), vj.x, a0x);
+            a0y = fma(__hiloint2double((int)r[3], (int)r[2]), vj.x, a0y);
+            a1x = fma(__hiloint2double((int)r[5], (int)r[4]), vj.y, a1x);
+            a1y = fma(__hiloint2double((int)r[7], (int)r[6]), vj.y, a1y);
+        }
+        __syncwarp();
+        Vec out;
+        out.v[0] = active(c, 0) ? (a0x + a1x) : 0.0;
+        out.v[1] = active(c, 1) ? (a0y + a1y) : 0.0;
+        return out;
+    }
     struct Step {
         Vec c;
         CVec ys;       // y / s
@@ -61,6 +135,7 @@ struct SphereFam {
     // row j, v_j broadcast from shared memory.  Two accumulators per element (even j / odd j) halve the
     // dependent-FMA chain; their sum order is part of the arithmetic specification.
     static __device__ __forceinline__ Vec matvec(const Ctx& c, const Vec& v) {
+        if (TM) return matvec_tmem(c, v);
         const int lane = lane_id();
         const int n = dimn(c);
         double2* vb2 = reinterpret_cast<double2*>(c.vbuf);

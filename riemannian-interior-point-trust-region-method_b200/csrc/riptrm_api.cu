@@ -715,6 +715,101 @@ static int ensure(double*& p, size_t bytes) {
     return RIPTRM_OK;
 }
 
+// n = 50 with S in Tensor Memory: 4 independent warps per CTA (one per TMEM sub-partition), 2 CTAs per SM (each
+// allocates 256 of the 512 TMEM columns), every warp pulling pairs from the same atomic queue as sphere_kernel.
+template <int MODE>
+__global__ void __launch_bounds__(128, 2) sphere_tmem_kernel(SphereParams P, DevOpts o, int* counter) {
+    using F = SphereFam<2, 50, true>;
+    constexpr int K = 2;
+    extern __shared__ __align__(16) double smem[];
+    __shared__ uint32_t tmem_base;
+    const int n = 50, ns = 50, pad = 64;
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    double* my = smem + (size_t)warp * (n * ns + pad + 64);
+    if (warp == 0) tmem::alloc(&tmem_base, 256);
+    tmem::fence_before_sync();
+    __syncthreads();
+    tmem::fence_after_sync();
+    typename F::Ctx ctx;
+    ctx.S = my;                       // staging copy; S.v reads the TMEM copy
+    ctx.vbuf = my + n * ns + pad;
+    ctx.n = n;
+    ctx.ns = ns;
+    ctx.eps = P.eps;
+    ctx.embedded = o.is_euclidean_embedded != 0;
+    ctx.taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
+    int loaded_z = -1;
+    while (true) {
+        int inst = 0;
+        if (lane == 0) inst = atomicAdd(counter, 1);
+        inst = __shfl_sync(kFull, inst, 0);
+        if (inst >= P.batch) break;
+        if (P.order != nullptr) inst = P.order[inst];
+        double* pause = (P.pause != nullptr) ? P.pause + (size_t)inst * kPauseFields : nullptr;
+        if (MODE == 0 && P.resume && pause[7] == 0.0) continue;
+        const int zi = inst / (P.batch / P.batch_z);
+        if (zi != loaded_z) {
+            load_S(P.Z + (size_t)zi * n * n, my, n, ns, pad);
+            F::stage_to_tmem(ctx);
+            loaded_z = zi;
+        }
+        const bool resume = (MODE == 0) && P.resume;
+        const typename F::Vec x0 = load_vec<K>((resume ? P.x : P.x0) + (size_t)inst * n, n);
+        const typename F::CVec y0 = load_vec<K>((resume ? P.y : P.y0) + (size_t)inst * n, n);
+        if (MODE == 0) {
+            typename F::Pt pt;
+            typename F::CVec y;
+            double* tr = (P.trace != nullptr && o.trace_mode != 0)
+                             ? P.trace + (size_t)inst * o.trace_capacity * RIPTRM_TRACE_FIELDS
+                             : nullptr;
+            solve_instance<F>(ctx, o, x0, y0, pt, y, P.summary ? P.summary + (size_t)inst * RIPTRM_SUMMARY_FIELDS : nullptr,
+                              tr, pause, resume, P.pause_at);
+            if (P.x) store_vec<K>(P.x + (size_t)inst * n, pt.x, n);
+            if (P.y) store_vec<K>(P.y + (size_t)inst * n, y, n);
+        } else {
+            typename F::Pt pt;
+            F::eval_point(ctx, x0, pt);
+            typename F::Step st;
+            F::begin_step(ctx, pt, y0, P.mu, st);
+            if (MODE == 1) {
+                const typename F::Vec v = load_vec<K>(P.v + (size_t)inst * n, n);
+                const typename F::Vec hv = F::Hw(ctx, pt, y0, st, v);
+                store_vec<K>(P.out + (size_t)inst * n, hv, n);
+            } else {
+                typename F::Vec eta, Heta;
+                const TcgResult r = F::tcg(ctx, o, pt, y0, st, P.Delta, eta, Heta);
+                store_vec<K>(P.out + (size_t)inst * n, eta, n);
+                const double nrm = sqrt(F::inner(ctx, pt, eta, eta));
+                if (P.info != nullptr && lane < 4) {
+                    const double val = (lane == 0) ? (double)r.iters : (lane == 1) ? (double)r.stop : (lane == 2) ? nrm : r.model_value;
+                    P.info[(size_t)inst * 4 + lane] = val;
+                }
+            }
+        }
+    }
+    tmem::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem::dealloc(tmem_base, 256);
+}
+
+template <int MODE>
+static int launch_sphere_tmem(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
+    const size_t smem = (size_t)4 * (50 * 50 + 64 + 64) * sizeof(double);
+    auto kern = sphere_tmem_kernel<MODE>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int grid = h->num_sms * 2;
+    const int need = (h->batch + 3) / 4;
+    if (grid > need) grid = need;
+    CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
+    CUDA_TRY(cudaEventRecord(h->ev0, st));
+    kern<<<grid, 128, smem, st>>>(P, o, h->d_counter);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->ev1, st));
+    h->launches += 1;
+    return RIPTRM_OK;
+}
+
 template <int K, int MODE, int NFIX>
 static int launch_sphere(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
     const int n = h->n;
@@ -750,6 +845,8 @@ __global__ void schedule_keys_kernel(const double* __restrict__ pause, float* ke
 template <int MODE>
 static int dispatch_sphere(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
     const int n = h->n;
+    static const bool no_tmem = getenv("RIPTRM_SPHERE_NO_TMEM") != nullptr;  // A/B switch for measurements
+    if (n == 50 && !no_tmem) return launch_sphere_tmem<MODE>(h, P, o, st);      // the reference's dim, S in TMEM
     if (n == 50) return launch_sphere<2, MODE, 50>(h, P, o, st);  // the reference's dim (config_dataset.yaml:6)
     if (n <= 64) return launch_sphere<2, MODE, 0>(h, P, o, st);
     return launch_sphere<4, MODE, 0>(h, P, o, st);
