@@ -845,7 +845,7 @@ __global__ void schedule_keys_kernel(const double* __restrict__ pause, float* ke
 template <int MODE>
 static int dispatch_sphere(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
     const int n = h->n;
-    static const bool no_tmem = getenv("RIPTRM_SPHERE_NO_TMEM") != nullptr;  // A/B switch for measurements
+    const bool no_tmem = getenv("RIPTRM_SPHERE_NO_TMEM") != nullptr;  // A/B switch (measurements, tests)
     if (n == 50 && !no_tmem) return launch_sphere_tmem<MODE>(h, P, o, st);      // the reference's dim, S in TMEM
     if (n == 50) return launch_sphere<2, MODE, 50>(h, P, o, st);  // the reference's dim (config_dataset.yaml:6)
     if (n <= 64) return launch_sphere<2, MODE, 0>(h, P, o, st);

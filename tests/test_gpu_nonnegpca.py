@@ -250,3 +250,31 @@ def test_error_paths_through_the_c_abi(rb):
         rb._lib.check(lib.riptrm_create(1, 129, 1, 129, 1, 0, C.byref(h)))
     with pytest.raises(NotImplementedError):
         rb.RIPTRM({"TRS_solver": "Exact_RepMat"}).run_batch([None], structures=[rb.NonnegPCAStructure(Z=Z[0], x0=x[0], y0=x[0])])
+
+
+def test_tmem_and_shared_memory_kernels_agree_bit_for_bit(rb, monkeypatch):
+    """n = 50 runs with S in Tensor Memory by default; RIPTRM_SPHERE_NO_TMEM=1 selects the shared-memory kernel.  Same
+    arithmetic, same order: identical x, y, summaries and trace rows (96 pairs, two-launch schedule forced)."""
+    Z, x0, y0 = rb.datagen.nonnegpca_sweep(321, 24, 4)
+    opt = rb.options.default_option()
+    opt.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=20, inner_maxiter=1000, tolresid=0, maxtime=1e9,
+               schedule_split=4)
+    res = []
+    for no_tmem in (False, True):
+        if no_tmem:
+            monkeypatch.setenv("RIPTRM_SPHERE_NO_TMEM", "1")
+        else:
+            monkeypatch.delenv("RIPTRM_SPHERE_NO_TMEM", raising=False)
+        bs = rb.BatchSolver.nonnegpca_from_arrays(Z, x0, y0)
+        bs.set_options(opt, 1, 400)
+        x, y, sm, tr = bs.solve()
+        bs.close()
+        res.append((x, y, sm, tr))
+    (xa, ya, sa, ta), (xb, yb, sb, tb) = res
+    assert np.array_equal(xa, xb) and np.array_equal(ya, yb) and np.array_equal(sa, sb)
+    T = rb._lib.TR
+    cols = [i for name, i in T.items() if name != "time"]
+    rows = sa[:, rb._lib.SM["trace_rows"]].astype(int)
+    for i in range(len(rows)):
+        a, b = ta[i, :rows[i]][:, cols], tb[i, :rows[i]][:, cols]
+        assert ((a == b) | (np.isnan(a) & np.isnan(b))).all()
