@@ -256,6 +256,8 @@ static TcgResult tcg(const Ctx* c, const det_options* o, const Pt* pt, const Ste
      * reduction rounds per iteration instead of five dependent ones.  -DFAITHFUL_TCG compiles the loop in the
      * reference's operation order instead (same results to rounding; tests/test_oracle_c.py compares both). */
     double wv[MAXN], Sv[MAXN], tmp[MAXN], r_new[MAXN];
+    const double target_sq = target * target;
+    double inv_zr = 1.0 / z_r;
     for (int e = 0; e < N; ++e) wv[e] = pt->x[e] * st->ys[e];
     const double q = vdot(c, wv, pt->x);
     for (; j < maxinner; ++j) {
@@ -307,15 +309,16 @@ static TcgResult tcg(const Ctx* c, const det_options* o, const Pt* pt, const Ste
         memcpy(r, r_new, sizeof(double) * N);
         model_value = new_model;
         r_r = rr_new;
-        const double norm_r = sqrt(r_r);
-        if (j >= o->tcg_mininner && norm_r <= target) {
+        /* residual test on squares (||r|| <= target <=> r_r <= target^2): no square root on the critical path */
+        if (j >= o->tcg_mininner && r_r <= target_sq) {
             res.stop = (o->tcg_kappa < nr_theta) ? TCG_REACHED_TARGET_LINEAR : TCG_REACHED_TARGET_SUPERLINEAR;
             ++j;
             break;
         }
-        const double zold_rold = z_r;
+        /* beta = z_r / z_r_old as a product with the reciprocal formed one iteration earlier (off the critical path) */
+        const double beta = r_r * inv_zr;
         z_r = r_r;
-        const double beta = z_r / zold_rold;
+        inv_zr = 1.0 / z_r;
         const double xd = -xr + beta * b; /* <x, -r + beta delta> */
         for (int e = 0; e < N; ++e) {
             const double dn = -r[e] + beta * delta[e];

@@ -283,6 +283,8 @@ struct SphereFam {
         const double Delta2 = Delta * Delta;
         const double nr_theta = (o.tcg_theta == 1.0) ? norm_r0 : pow(norm_r0, o.tcg_theta);
         const double target = norm_r0 * fmin(nr_theta, o.tcg_kappa);
+        const double target_sq = target * target;
+        double inv_zr = 1.0 / z_r;
         int j = 0;
         for (; j < maxinner; ++j) {                            // :98
             const Vec Sv = matvec(ctx, delta);                 // :100
@@ -343,16 +345,18 @@ struct SphereFam {
             r = r_new;
             model_value = new_model;
             r_r = s4[2];                                       // :175
-            const double norm_r = sqrt(r_r);
-            if (j >= o.tcg_mininner && norm_r <= target) {     // :183-191
+            // ||r|| <= target tested on squares: no square root on the critical path
+            if (j >= o.tcg_mininner && r_r <= target_sq) {     // :183-191
                 res.stop = (o.tcg_kappa < nr_theta) ? RIPTRM_TCG_REACHED_TARGET_LINEAR
                                                     : RIPTRM_TCG_REACHED_TARGET_SUPERLINEAR;
                 ++j;
                 break;
             }
-            const double zold_rold = z_r;                      // :200
-            z_r = r_r;                                         // :202
-            const double beta = z_r / zold_rold;               // :205
+            // beta = z_r / z_r_old (:205) as a product with the reciprocal formed one iteration earlier: the division
+            // for the next iteration overlaps with the next S.delta instead of sitting on the critical path
+            const double beta = r_r * inv_zr;
+            z_r = r_r;                                         // :200-202
+            inv_zr = 1.0 / z_r;
             const double xd = -s4[3] + beta * b;               // <x, -r + beta delta>
 #pragma unroll
             for (int k = 0; k < K; ++k) {
