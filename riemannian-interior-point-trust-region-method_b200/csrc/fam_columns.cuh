@@ -174,6 +174,67 @@ __device__ __forceinline__ void stream_pass(const Params& prm, Smem<P>& sm, Pipe
             __syncwarp();
             pipe.advance();
         }
+    } else if (P == 16) {
+        // ---- FP64 tensor-core consumers (mma.sync.m8n8k4.f64, SASS DMMA): out[i, c] = sum_j S[j][i] V[j][c] with
+        //      M <-> i (8), K <-> j (4), N <-> c (8).  Warp w owns the column groups ig = 2w, 2w+1 of the tile; per row
+        //      group jg it loads two A fragments (one coalesced LDS.64 each: S is stored in fragment order) and two B
+        //      fragments (V slice, row-major) and issues four DMMAs.  8 accumulator doubles per thread instead of 64.
+        double acc[2][2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        const int ib0 = prm.tib0[g];
+        int cur_ib = ib0;
+        int jt = (int)(t0 - (long long)ib0 * prm.NJT), ibn = ib0;
+        for (long long t = t0; t <= t1; ++t) {
+            const int ib = (t < t1) ? ibn : -1;
+            if (++jt == prm.NJT) {
+                jt = 0;
+                ++ibn;
+            }
+            if (t > t0 && ib != cur_ib) {
+                // accumulator (a, b, h): i = 8 (2 warp + a) + (lane >> 2), c = 8 b + 2 (lane & 3) + h; warps own
+                // disjoint columns i, so the flush needs no cross-warp sum
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        const int col = 8 * (2 * warp + a) + (lane >> 2), c0 = 8 * b + 2 * (lane & 3);
+                        sm.flush[col][c0] = acc[a][b][0];
+                        sm.flush[col][c0 + 1] = acc[a][b][1];
+                        acc[a][b][0] = acc[a][b][1] = 0.0;
+                    }
+                consumer_bar();
+                double* dst = prm.mv_part + ((size_t)g * prm.slots + (cur_ib - ib0)) * (TW * P);
+                const double* src = &sm.flush[0][0];
+                for (int e = threadIdx.x; e < TW * P; e += NCW * 32) dst[e] = src[e];
+                consumer_bar();
+                cur_ib = ib;
+            }
+            if (t == t1) break;
+            mbar_wait(&sm.full[pipe.stage], pipe.phase);
+            const double* St = &sm.S[pipe.stage][0][0];
+            const double* Vt = &sm.V[pipe.stage][0][0];
+#pragma unroll
+            for (int jg = 0; jg < TJ / 4; ++jg) {
+                const double a0 = St[(jg * 16 + 2 * warp) * 32 + lane];
+                const double a1 = St[(jg * 16 + 2 * warp + 1) * 32 + lane];
+                const double b0 = Vt[(4 * jg + (lane & 3)) * P + (lane >> 2)];
+                const double b1 = Vt[(4 * jg + (lane & 3)) * P + 8 + (lane >> 2)];
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(acc[0][0][0]), "+d"(acc[0][0][1]) : "d"(a0), "d"(b0));
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(acc[0][1][0]), "+d"(acc[0][1][1]) : "d"(a0), "d"(b1));
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(acc[1][0][0]), "+d"(acc[1][0][1]) : "d"(a1), "d"(b0));
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(acc[1][1][0]), "+d"(acc[1][1][1]) : "d"(a1), "d"(b1));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[pipe.stage]);
+            pipe.advance();
+        }
     } else {
         double acc[4][P];
 #pragma unroll
@@ -1447,7 +1508,9 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
 
 // S = Z + Z' into the streaming layout: tile (ib, jt) = rows [jt*TJ, +TJ) x columns [ib*TW, +TW) stored
 // contiguously ([TJ][TW] row-major) at tile index ib * NJT + jt; padding stays zero.
-__global__ void build_S_kernel(const double* __restrict__ Z, double* __restrict__ S, int n, int NJT) {
+// frag = 1 (P = 16, DMMA consumers): inside a tile the 4 x 8 blocks (rows 4jg.., columns 8ig..) are stored as the 32
+// consecutive doubles of an mma.m8n8k4 A-fragment: entry (jj, ii) of block (jg, ig) at ((jg*16 + ig)*32 + ii*4 + jj).
+__global__ void build_S_kernel(const double* __restrict__ Z, double* __restrict__ S, int n, int NJT, int frag) {
     __shared__ double tile[32][33];
     const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
@@ -1460,7 +1523,10 @@ __global__ void build_S_kernel(const double* __restrict__ Z, double* __restrict_
         const int i = bi + k, j = bj + tx;
         if (i < n && j < n) {
             const size_t tile_id = (size_t)(j / TW) * NJT + (i / TJ);
-            S[(tile_id * TJ + (i % TJ)) * TW + (j % TW)] = Z[(size_t)i * n + j] + tile[tx][k];
+            const int r = i % TJ, cidx = j % TW;
+            const size_t within = frag ? (size_t)(((r >> 2) * 16 + (cidx >> 3)) * 32 + (cidx & 7) * 4 + (r & 3))
+                                       : (size_t)r * TW + cidx;
+            S[tile_id * (TJ * TW) + within] = Z[(size_t)i * n + j] + tile[tx][k];
         }
     }
 }

@@ -28,7 +28,7 @@ def _closed_form_hw(Z, x, y, mu, v):
     return P(-S @ v) + (x @ S @ x + y @ x) * v + P((y / x) * (v - x * (x @ v)))
 
 
-@pytest.mark.parametrize("n,p", [(96, 1), (500, 4), (1000, 10), (777, 3)])
+@pytest.mark.parametrize("n,p", [(96, 1), (500, 4), (1000, 10), (777, 3), (640, 16), (1000, 12)])
 def test_hessvec_matches_closed_form_and_oracle(rb, n, p):
     from oracle import riptrm_oracle as O
     from oracle.problems import NonnegPCAProblem
@@ -50,7 +50,7 @@ def test_hessvec_matches_closed_form_and_oracle(rb, n, p):
     cs.close()
 
 
-@pytest.mark.parametrize("n,p,Delta", [(300, 4, 0.3), (300, 4, 5.0), (1000, 10, 0.05), (641, 2, 1.0)])
+@pytest.mark.parametrize("n,p,Delta", [(300, 4, 0.3), (300, 4, 5.0), (1000, 10, 0.05), (641, 2, 1.0), (520, 16, 0.5)])
 def test_lockstep_tcg_matches_oracle_tcg(rb, n, p, Delta):
     """Each column's tCG (iteration count, stop reason, eta) equals the oracle's Steihaug-Toint tCG
     (RIPTRM.py:41-216) run on that column with the closed-form operator."""
