@@ -40,6 +40,7 @@ constexpr int STAGES = 5;   // shared-memory ring depth (5 x 32 KB in flight per
 constexpr int NCW = 8;      // consumer warps
 constexpr int NT = (NCW + 1) * 32;
 constexpr int MAXP = 16;
+constexpr bool kTensorP10 = true;  // experiment: DMMA consumers for p = 10 as well (N padded to 16)
 constexpr int MAXQ = 10;    // reductions per phase and column (sums first, then mins)
 
 struct Params {
@@ -174,7 +175,7 @@ __device__ __forceinline__ void stream_pass(const Params& prm, Smem<P>& sm, Pipe
             __syncwarp();
             pipe.advance();
         }
-    } else if (P == 16) {
+    } else if (P == 16 || (P == 10 && kTensorP10)) {
         // ---- FP64 tensor-core consumers (mma.sync.m8n8k4.f64, SASS DMMA): out[i, c] = sum_j S[j][i] V[j][c] with
         //      M <-> i (8), K <-> j (4), N <-> c (8).  Warp w owns the column groups ig = 2w, 2w+1 of the tile; per row
         //      group jg it loads two A fragments (one coalesced LDS.64 each: S is stored in fragment order) and two B
@@ -201,8 +202,8 @@ __device__ __forceinline__ void stream_pass(const Params& prm, Smem<P>& sm, Pipe
 #pragma unroll
                     for (int b = 0; b < 2; ++b) {
                         const int col = 8 * (2 * warp + a) + (lane >> 2), c0 = 8 * b + 2 * (lane & 3);
-                        sm.flush[col][c0] = acc[a][b][0];
-                        sm.flush[col][c0 + 1] = acc[a][b][1];
+                        if (c0 < P) sm.flush[col][c0] = acc[a][b][0];
+                        if (c0 + 1 < P) sm.flush[col][c0 + 1] = acc[a][b][1];
                         acc[a][b][0] = acc[a][b][1] = 0.0;
                     }
                 consumer_bar();
@@ -221,7 +222,7 @@ __device__ __forceinline__ void stream_pass(const Params& prm, Smem<P>& sm, Pipe
                 const double a0 = St[(jg * 16 + 2 * warp) * 32 + lane];
                 const double a1 = St[(jg * 16 + 2 * warp + 1) * 32 + lane];
                 const double b0 = Vt[(4 * jg + (lane & 3)) * P + (lane >> 2)];
-                const double b1 = Vt[(4 * jg + (lane & 3)) * P + 8 + (lane >> 2)];
+                const double b1 = (8 + (lane >> 2) < P) ? Vt[(4 * jg + (lane & 3)) * P + 8 + (lane >> 2)] : 0.0;
                 asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                              : "+d"(acc[0][0][0]), "+d"(acc[0][0][1]) : "d"(a0), "d"(b0));
                 asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
