@@ -40,7 +40,9 @@ constexpr int STAGES = 5;   // shared-memory ring depth (5 x 32 KB in flight per
 constexpr int NCW = 8;      // consumer warps
 constexpr int NT = (NCW + 1) * 32;
 constexpr int MAXP = 16;
-constexpr bool kTensorP10 = true;  // experiment: DMMA consumers for p = 10 as well (N padded to 16)
+// FP64 tensor-core (DMMA) consumers for P >= 8 (N = 8 or 16, padded); plain DFMA consumers for P = 1, 2, 4
+template <int P>
+constexpr bool kTensor = (P >= 8);
 constexpr int MAXQ = 10;    // reductions per phase and column (sums first, then mins)
 
 struct Params {
@@ -175,16 +177,18 @@ __device__ __forceinline__ void stream_pass(const Params& prm, Smem<P>& sm, Pipe
             __syncwarp();
             pipe.advance();
         }
-    } else if (P == 16 || (P == 10 && kTensorP10)) {
+    } else if (kTensor<P>) {
         // ---- FP64 tensor-core consumers (mma.sync.m8n8k4.f64, SASS DMMA): out[i, c] = sum_j S[j][i] V[j][c] with
         //      M <-> i (8), K <-> j (4), N <-> c (8).  Warp w owns the column groups ig = 2w, 2w+1 of the tile; per row
         //      group jg it loads two A fragments (one coalesced LDS.64 each: S is stored in fragment order) and two B
-        //      fragments (V slice, row-major) and issues four DMMAs.  8 accumulator doubles per thread instead of 64.
-        double acc[2][2][2];
+        //      fragments (V slice, row-major; columns >= P masked) and issues four DMMAs.  At most 8 accumulator
+        //      doubles per thread instead of 4 P.
+        constexpr int NCG = (P + 7) / 8;  // column groups of V (N tiles)
+        double acc[2][NCG][2];
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+            for (int b = 0; b < NCG; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
         const int ib0 = prm.tib0[g];
         int cur_ib = ib0;
         int jt = (int)(t0 - (long long)ib0 * prm.NJT), ibn = ib0;
@@ -200,7 +204,7 @@ __device__ __forceinline__ void stream_pass(const Params& prm, Smem<P>& sm, Pipe
 #pragma unroll
                 for (int a = 0; a < 2; ++a)
 #pragma unroll
-                    for (int b = 0; b < 2; ++b) {
+                    for (int b = 0; b < NCG; ++b) {
                         const int col = 8 * (2 * warp + a) + (lane >> 2), c0 = 8 * b + 2 * (lane & 3);
                         if (c0 < P) sm.flush[col][c0] = acc[a][b][0];
                         if (c0 + 1 < P) sm.flush[col][c0 + 1] = acc[a][b][1];
@@ -221,16 +225,15 @@ __device__ __forceinline__ void stream_pass(const Params& prm, Smem<P>& sm, Pipe
             for (int jg = 0; jg < TJ / 4; ++jg) {
                 const double a0 = St[(jg * 16 + 2 * warp) * 32 + lane];
                 const double a1 = St[(jg * 16 + 2 * warp + 1) * 32 + lane];
-                const double b0 = Vt[(4 * jg + (lane & 3)) * P + (lane >> 2)];
-                const double b1 = (8 + (lane >> 2) < P) ? Vt[(4 * jg + (lane & 3)) * P + 8 + (lane >> 2)] : 0.0;
-                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                             : "+d"(acc[0][0][0]), "+d"(acc[0][0][1]) : "d"(a0), "d"(b0));
-                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                             : "+d"(acc[0][1][0]), "+d"(acc[0][1][1]) : "d"(a0), "d"(b1));
-                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                             : "+d"(acc[1][0][0]), "+d"(acc[1][0][1]) : "d"(a1), "d"(b0));
-                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                             : "+d"(acc[1][1][0]), "+d"(acc[1][1][1]) : "d"(a1), "d"(b1));
+#pragma unroll
+                for (int b = 0; b < NCG; ++b) {
+                    const int cc = 8 * b + (lane >> 2);
+                    const double bf = (cc < P) ? Vt[(4 * jg + (lane & 3)) * P + cc] : 0.0;
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(acc[0][b][0]), "+d"(acc[0][b][1]) : "d"(a0), "d"(bf));
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(acc[1][b][0]), "+d"(acc[1][b][1]) : "d"(a1), "d"(bf));
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty[pipe.stage]);

@@ -347,7 +347,7 @@ static int columns_setup(riptrm_handle* h, const double* Z, double eps, int wher
         dZ = tmpZ;
     }
     dim3 grid((n + 31) / 32, (n + 31) / 32), block(32, 8);
-    col::build_S_kernel<<<grid, block>>>(dZ, h->dS, n, h->n_pad / col::TJ, (h->colP == 16 || (h->colP == 10 && col::kTensorP10)) ? 1 : 0);
+    col::build_S_kernel<<<grid, block>>>(dZ, h->dS, n, h->n_pad / col::TJ, h->colP >= 8 ? 1 : 0);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());
     h->launches += 1;
