@@ -434,6 +434,32 @@ class RIPTRM:
         self.log = out.log
         return out
 
+    def run_columns(self, Z, X0, Y0, eps=0.0):
+        """p unit-norm columns sharing one (large) Z -- BASELINE config 4: every column is an independent
+        NonnegPCA/Sphere RIPTRM run (family COLUMNS, lock-step on the device).  Returns one `Output` per column; the
+        log has one row per outer iteration (the reference's `save_inner_iteration=False` layout)."""
+        option = self.option
+        _options.check_supported(option)
+        n, p = X0.shape
+        cs = ColumnsSolver(Z, p, eps=eps, device=self.device)
+        try:
+            X, Y, summary, trace = cs.solve(X0, Y0, option, per_outer_trace=True)
+            run_time = cs.kernel_ms * 1e-3
+        finally:
+            cs.close()
+        to_np = lambda a: a.cpu().numpy() if hasattr(a, "cpu") else np.asarray(a)
+        X, Y, summary, trace = to_np(X), to_np(Y), to_np(summary), to_np(trace)
+        self.last_summary = summary
+        outs = []
+        for c in range(p):
+            rows = int(summary[c, _lib.SM["trace_rows"]])
+            opt = copy.copy(option)
+            opt["stoppingcriterion"] = _stop_message(summary[c], option, run_time)
+            outs.append(Output(name=self.name, x=np.array(X[:, c]), option=opt,
+                               log=trace_to_log(trace[c, :rows], save_inner_iteration=False),
+                               ineqLagmult=np.array(Y[:, c]), eqLagmult=[]))
+        return outs
+
     def run_batch(self, problems, structures=None):
         """Solves many (instance, initialpoint) pairs of one family in one launch; returns one
         Output per problem.  `structures` bypasses closure recognition."""

@@ -146,3 +146,20 @@ def test_whole_solve_columns_finish_independently(rb):
     assert (sm[:, SM["stop_reason"]] == 3).all() and (sm[:, SM["residual"]] <= 1e-6).all()
     assert (sm[:, SM["outer_iters"]] < 40).all()
     cs.close()
+
+
+def test_run_columns_returns_reference_style_outputs(rb):
+    """RIPTRM(option).run_columns: one Output per column with the reference's per-outer-iteration log layout."""
+    n, p = 128, 3
+    Z, X0, Y0, rs = _instance(n, p, seed=21)
+    solver = rb.RIPTRM({"TRS_solver": "tCG", "second_order_stationarity": False, "maxiter": 12, "tolresid": 0, "maxtime": 1e9})
+    outs = solver.run_columns(Z, X0, np.ones((n, p)))
+    assert len(outs) == p
+    for c, o in enumerate(outs):
+        assert o.name == "RIPTRM_tCG" and o.x.shape == (n,) and o.ineqLagmult.shape == (n,)
+        assert o.log["iteration"] == list(range(13))
+        assert list(o.log)[:11] == ["iteration", "time", "cost", "distance", "residual", "gradnorm", "complviolation",
+                                    "dualviolation", "manviolation", "maxviolation", "meanviolation"]
+        assert all(b <= a + 1e-12 for a, b in zip(o.log["cost"][1:], o.log["cost"][2:]))   # objective decreases
+        assert o.option["stoppingcriterion"].startswith("Max iteration count reached; maxiter=12")
+        assert abs(np.linalg.norm(o.x) - 1) < 1e-14
