@@ -993,8 +993,10 @@ struct PostState {  // per column, identical in every CTA
     double it, k, Delta, xSx, cost, cnt_inner, cnt_tcg, cnt_aux, rows, finished, stop, Delta_init, xSx_init, cost_init;
     double mu, tolL, tolC, kappa, normdx, nrm, bdot, xSxN, costN, minx, miny, compl_v, xy, ngl, pl_cur, pl_new, a, b, d;
     double ared_pred, radius_update, inner_status, dual_clipping, tcg_iters, tcg_stop, DeltaNext;
+    double radius0;  // trust-region radius before the step (the log's TR_radius)
     int path;      // 0 idle (finished), 1 converged, 2 primal infeasible, 3 normal (rho test)
     int accept, boundary, rollback;
+    int evalc;     // evaluate (utils.py:342-368) this column in this call: boundary, or every step with trace_mode 1
 };
 
 template <int P, bool INIT>
@@ -1030,7 +1032,9 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
         s.tolL = prm.tolL_sched[it > 0 ? it - 1 : 0];
         s.tolC = prm.tolC_sched[it > 0 ? it - 1 : 0];
         s.path = (s.finished != 0.0) ? 0 : 3;
+        s.radius0 = s.Delta;
         s.accept = s.boundary = s.rollback = 0;
+        s.evalc = 0;
         s.ared_pred = s.radius_update = s.dual_clipping = CUDART_NAN;
         s.inner_status = CUDART_NAN;
         s.normdx = s.minx = s.miny = s.compl_v = CUDART_NAN;
@@ -1371,11 +1375,14 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
         __syncthreads();
     }
 
-    // ---- outer-iteration boundary (columns whose inner loop just ended, or INIT): evaluation (utils.py:342-368),
-    //      log row, stop tests (base_solver.py:85-106), barrier update (:890-894) --------------------------------------
+    // ---- evaluation (utils.py:342-368) of the columns at an outer-iteration boundary (inner loop just ended, or INIT) and,
+    //      with trace_mode 1, of every running column (one log row per trust-region iteration, RIPTRM.py:812-818);
+    //      then the log row, the stop tests (base_solver.py:85-106) and the barrier update (:890-894) -----------------------
+    if (tid < P) ps[tid].evalc = ps[tid].boundary || (prm.trace_mode == 1 && !INIT && ps[tid].path != 0);
+    __syncthreads();
     {
-        double part[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, CUDART_INF};
-        if (ps[myc].boundary) {
+        double part[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, CUDART_INF, CUDART_INF};
+        if (ps[myc].evalc) {
             FOR_ELEMS(e) {
                 const double x = prm.X[e], y = prm.Y[e];
                 const double gi = -(x + prm.eps);
@@ -1388,21 +1395,22 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
                 part[5] = part[5] + iv * iv;
                 part[6] = part[6] + iv;
                 part[7] = fmin(part[7], -iv);
+                part[8] = fmin(part[8], -fabs(y));
             }
         }
-        reduce_store_mixed<P, 7, 1>(prm, sm, part, buf);
+        reduce_store_mixed<P, 7, 2>(prm, sm, part, buf);
     }
     grid.sync();
-    gather_mixed<P, 7, 1>(prm, sm, buf);
+    gather_mixed<P, 7, 2>(prm, sm, buf);
     buf ^= 1;
-    __shared__ double ev[P][8];
-    if (tid < P && ps[tid].boundary) {
-        for (int q = 0; q < 8; ++q) ev[tid][q] = sm.scal[q * P + tid];
+    __shared__ double ev[P][9];
+    if (tid < P && ps[tid].evalc) {
+        for (int q = 0; q < 9; ++q) ev[tid][q] = sm.scal[q * P + tid];
     }
     __syncthreads();
     {
         double part[1] = {0.0};
-        if (ps[myc].boundary) {
+        if (ps[myc].evalc) {
             const double xSx = ps[myc].xSx, xy = ev[myc][0];
             FOR_ELEMS(e) {
                 const double x = prm.X[e];
@@ -1415,7 +1423,7 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
     grid.sync();
     gather_scalars<P, 1>(prm, sm, buf);
     buf ^= 1;
-    if (tid < P && ps[tid].boundary) {
+    if (tid < P && ps[tid].evalc) {
         PostState& s = ps[tid];
         const double gradnorm = sqrt(sm.scal[tid]);
         const double p_compl = ev[tid][3], p_nonneg = ev[tid][4], p_ineq = ev[tid][5];
@@ -1424,18 +1432,34 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
         const double max_v = -ev[tid][7], mean_v = ev[tid][6] / (double)n;
         const double distance = acos(fmax(fmin(ev[tid][2], 1.0), -1.0));
         const int it = (int)s.it;
-        const double mu_row = prm.mu_sched[it];  // the barrier parameter after the update (:890-893), mu_sched[0] at row 0
-        if (prm.trace_mode == 2 && prm.trace != nullptr && g == 0) {
-            if ((int)s.rows < prm.trace_capacity) {
+        const double mu_next = prm.mu_sched[it];  // the barrier parameter after the update (:890-893), mu_sched[0] at row 0
+        // trace_mode 1: row 0 and one row per trust-region iteration; trace_mode 2: one row per outer iteration
+        const bool inner_row = prm.trace_mode == 1 && !INIT;
+        const bool write_row = (prm.trace_mode == 1) || (prm.trace_mode == 2 && s.boundary);
+        if (write_row) {
+            if (prm.trace != nullptr && g == 0 && (int)s.rows < prm.trace_capacity) {
                 double* row = prm.trace + ((size_t)tid * prm.trace_capacity + (size_t)s.rows) * RIPTRM_TRACE_FIELDS;
                 for (int f = 0; f < RIPTRM_TRACE_FIELDS; ++f) row[f] = CUDART_NAN;
                 row[RIPTRM_TR_ITERATION] = (double)it;
-                row[RIPTRM_TR_MU] = mu_row;
+                row[RIPTRM_TR_MU] = inner_row ? s.mu : mu_next;
                 if (!INIT) {
                     row[RIPTRM_TR_NUM_INNER] = s.k;
-                    row[RIPTRM_TR_RADIUS] = s.Delta;
                     row[RIPTRM_TR_INNER_STATUS] = s.inner_status;
+                    row[RIPTRM_TR_RADIUS] = inner_row ? s.radius0 : s.Delta;
                 }
+                if (inner_row) {
+                    row[RIPTRM_TR_NUM_INNER] = s.rollback ? (double)prm.inner_maxiter : s.k;
+                    row[RIPTRM_TR_DXTYPE] = s.tcg_stop;
+                    row[RIPTRM_TR_TCG_ITERS] = s.tcg_iters;
+                    row[RIPTRM_TR_NORMDX] = s.normdx;
+                    row[RIPTRM_TR_MINXFEASI] = s.minx;
+                    row[RIPTRM_TR_MINYFEASI] = s.miny;
+                    row[RIPTRM_TR_COMPL] = s.compl_v;
+                    row[RIPTRM_TR_ARED_PRED] = s.ared_pred;
+                    row[RIPTRM_TR_RADIUS_UPDATE] = s.radius_update;
+                    row[RIPTRM_TR_DUAL_CLIPPING] = s.dual_clipping;
+                }
+                row[RIPTRM_TR_MAXABSLAGMULT] = -ev[tid][8];
                 row[RIPTRM_TR_COST] = s.cost;
                 row[RIPTRM_TR_DISTANCE] = distance;
                 row[RIPTRM_TR_RESIDUAL] = residual;
@@ -1447,44 +1471,46 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
                 row[RIPTRM_TR_MEANVIOLATION] = mean_v;
                 row[RIPTRM_TR_TIME] = 0.0;
             }
+            s.rows += 1.0;
         }
-        if (prm.trace_mode == 2) s.rows += 1.0;
-        int stop = RIPTRM_STOP_RUNNING;
-        if (it >= prm.maxiter) stop = RIPTRM_STOP_MAXITER;
-        if (residual <= prm.tolresid) stop = RIPTRM_STOP_TOLRESID;
-        if (g == 0 && prm.summary != nullptr) {
-            double* sm_ = prm.summary + (size_t)tid * RIPTRM_SUMMARY_FIELDS;
-            sm_[RIPTRM_SM_COST] = s.cost;
-            sm_[RIPTRM_SM_RESIDUAL] = residual;
-            sm_[RIPTRM_SM_GRADNORM] = gradnorm;
-            sm_[RIPTRM_SM_COMPLVIOLATION] = sqrt(p_compl);
-            sm_[RIPTRM_SM_DUALVIOLATION] = sqrt(p_nonneg);
-            sm_[RIPTRM_SM_MANVIOLATION] = man_v;
-            sm_[RIPTRM_SM_MAXVIOLATION] = max_v;
-            sm_[RIPTRM_SM_MEANVIOLATION] = mean_v;
-            sm_[RIPTRM_SM_MU] = mu_row;
-            sm_[RIPTRM_SM_RADIUS] = fmax(s.Delta, it > 0 ? prm.minimal_initial_tr_radius : s.Delta);
-            sm_[RIPTRM_SM_OUTER_ITERS] = (double)it;
-            sm_[RIPTRM_SM_INNER_ITERS] = s.cnt_inner;
-            sm_[RIPTRM_SM_TCG_ITERS] = s.cnt_tcg;
-            sm_[RIPTRM_SM_AUX_HESSVECS] = s.cnt_aux;
-            sm_[RIPTRM_SM_STOP_REASON] = (double)stop;
-            sm_[RIPTRM_SM_TRACE_ROWS] = s.rows;
-        }
-        if (it > 0) s.Delta = fmax(s.Delta, prm.minimal_initial_tr_radius);   // :894
-        if (stop != RIPTRM_STOP_RUNNING) {
-            s.finished = 1.0;
-            s.stop = (double)stop;
-        } else {
-            s.it = (double)(it + 1);
-            s.k = 0.0;
-            s.Delta_init = s.Delta;
-            s.xSx_init = s.xSx;
-            s.cost_init = s.cost;
+        if (s.boundary) {
+            int stop = RIPTRM_STOP_RUNNING;
+            if (it >= prm.maxiter) stop = RIPTRM_STOP_MAXITER;
+            if (residual <= prm.tolresid) stop = RIPTRM_STOP_TOLRESID;
+            if (g == 0 && prm.summary != nullptr) {
+                double* sm_ = prm.summary + (size_t)tid * RIPTRM_SUMMARY_FIELDS;
+                sm_[RIPTRM_SM_COST] = s.cost;
+                sm_[RIPTRM_SM_RESIDUAL] = residual;
+                sm_[RIPTRM_SM_GRADNORM] = gradnorm;
+                sm_[RIPTRM_SM_COMPLVIOLATION] = sqrt(p_compl);
+                sm_[RIPTRM_SM_DUALVIOLATION] = sqrt(p_nonneg);
+                sm_[RIPTRM_SM_MANVIOLATION] = man_v;
+                sm_[RIPTRM_SM_MAXVIOLATION] = max_v;
+                sm_[RIPTRM_SM_MEANVIOLATION] = mean_v;
+                sm_[RIPTRM_SM_MU] = mu_next;
+                sm_[RIPTRM_SM_RADIUS] = fmax(s.Delta, it > 0 ? prm.minimal_initial_tr_radius : s.Delta);
+                sm_[RIPTRM_SM_OUTER_ITERS] = (double)it;
+                sm_[RIPTRM_SM_INNER_ITERS] = s.cnt_inner;
+                sm_[RIPTRM_SM_TCG_ITERS] = s.cnt_tcg;
+                sm_[RIPTRM_SM_AUX_HESSVECS] = s.cnt_aux;
+                sm_[RIPTRM_SM_STOP_REASON] = (double)stop;
+                sm_[RIPTRM_SM_TRACE_ROWS] = s.rows;
+            }
+            if (it > 0) s.Delta = fmax(s.Delta, prm.minimal_initial_tr_radius);   // :894
+            if (stop != RIPTRM_STOP_RUNNING) {
+                s.finished = 1.0;
+                s.stop = (double)stop;
+            } else {
+                s.it = (double)(it + 1);
+                s.k = 0.0;
+                s.Delta_init = s.Delta;
+                s.xSx_init = s.xSx;
+                s.cost_init = s.cost;
+            }
         }
     }
     __syncthreads();
-    // start-of-inner-run copies for the rollback (:794-796) and the previous outer iterate for `distance`
+    // start-of-inner-run copies for the rollback (:794-796) and the previous iterate for `distance`
     if (ps[myc].boundary && ps[myc].finished == 0.0) {
         FOR_ELEMS(e) {
             const double x = prm.X[e];
@@ -1493,6 +1519,8 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
             prm.Sxinit[e] = prm.Sx[e];
             prm.Xprev[e] = x;
         }
+    } else if (prm.trace_mode == 1 && ps[myc].evalc) {
+        FOR_ELEMS(e) prm.Xprev[e] = prm.X[e];  // previous inner iterate for the next row's `distance` (RIPTRM.py:819)
     }
     if (g == 0 && tid < P) {
         const PostState& s = ps[tid];

@@ -525,8 +525,6 @@ static int columns_dispatch_post(riptrm_handle* h, col::Params& prm, cudaStream_
 static int columns_solve(riptrm_handle* h, const double* x0, const double* y0, double* x, double* y, double* summary,
                          double* trace, int where, cudaStream_t st) {
     const riptrm_options& o = h->opts;
-    if (o.trace_mode == 1)
-        return fail(RIPTRM_E_UNSUPPORTED, "COLUMNS family: per-inner-iteration trace is not built (use trace_mode 0 or 2)");
     col::Params prm{};
     const ColPtrs q = columns_fill_params(h, prm);
     prm.solve = 1;
@@ -546,7 +544,7 @@ static int columns_solve(riptrm_handle* h, const double* x0, const double* y0, d
     prm.gamma = o.gamma;
     prm.const_left = o.const_left;
     prm.const_right = o.const_right;
-    const size_t tb = (o.trace_mode == 2 && trace != nullptr)
+    const size_t tb = (o.trace_mode != 0 && trace != nullptr)
                           ? (size_t)h->p * o.trace_capacity * RIPTRM_TRACE_FIELDS * sizeof(double) : 0;
     if (tb != 0) {
         if (where == RIPTRM_DEVICE) {

@@ -233,14 +233,17 @@ class ColumnsSolver:
                                        _lib.ptr(out), _lib.ptr(info), where, C.c_void_p(stream) if stream else None))
         return out, info
 
-    def solve(self, X0, Y0, option=None, per_outer_trace=False, stream=None):
+    def solve(self, X0, Y0, option=None, per_outer_trace=False, stream=None, per_inner_trace=False, trace_capacity=None):
         """p independent RIPTRM runs (one per column, sharing Z) advanced in lock-step (RIPTRM.py:909-976 per column).
-        Returns (X [n, p], Y [n, p], summary [p, 16], trace [p, maxiter + 1, 25] | None); trace rows are per outer
-        iteration (`save_inner_iteration=False` layout)."""
+        Returns (X [n, p], Y [n, p], summary [p, 16], trace [p, capacity, 25] | None); trace rows are per outer
+        iteration (`save_inner_iteration=False` layout) or, with `per_inner_trace`, row 0 plus one row per trust-region
+        iteration (the reference's default layout); summary[:, trace_rows] tells how many rows a column produced."""
         if option is not None:
-            o, keep = _options.to_c_options(option, 2 if per_outer_trace else 0, int(option["maxiter"]) + 1)
+            mode = 1 if per_inner_trace else (2 if per_outer_trace else 0)
+            cap = int(option["maxiter"]) + 1 if mode != 1 else int(trace_capacity or (12 * int(option["maxiter"]) + 64))
+            o, keep = _options.to_c_options(option, mode, cap)
             _lib.check(self.lib.riptrm_set_options(self.handle.h, C.byref(o)))
-            cap = int(option["maxiter"]) + 1
+            per_outer_trace = mode != 0
         else:
             per_outer_trace, cap = False, 0
         where = self._where(X0, Y0)
@@ -436,14 +439,23 @@ class RIPTRM:
 
     def run_columns(self, Z, X0, Y0, eps=0.0):
         """p unit-norm columns sharing one (large) Z -- BASELINE config 4: every column is an independent
-        NonnegPCA/Sphere RIPTRM run (family COLUMNS, lock-step on the device).  Returns one `Output` per column; the
-        log has one row per outer iteration (the reference's `save_inner_iteration=False` layout)."""
+        NonnegPCA/Sphere RIPTRM run (family COLUMNS, lock-step on the device).  Returns one `Output` per column with the
+        reference's log layout (`save_inner_iteration` True: row 0 + one row per trust-region iteration; False: one row per
+        outer iteration)."""
         option = self.option
         _options.check_supported(option)
         n, p = X0.shape
+        save_inner = bool(option["save_inner_iteration"])
         cs = ColumnsSolver(Z, p, eps=eps, device=self.device)
         try:
-            X, Y, summary, trace = cs.solve(X0, Y0, option, per_outer_trace=True)
+            cap = None
+            while True:
+                X, Y, summary, trace = cs.solve(X0, Y0, option, per_outer_trace=not save_inner,
+                                                per_inner_trace=save_inner, trace_capacity=cap)
+                need = int(np.max((summary.cpu().numpy() if hasattr(summary, "cpu") else summary)[:, _lib.SM["trace_rows"]]))
+                if need <= trace.shape[1]:
+                    break
+                cap = need  # deterministic: rerun with room for every row
             run_time = cs.kernel_ms * 1e-3
         finally:
             cs.close()
@@ -456,7 +468,7 @@ class RIPTRM:
             opt = copy.copy(option)
             opt["stoppingcriterion"] = _stop_message(summary[c], option, run_time)
             outs.append(Output(name=self.name, x=np.array(X[:, c]), option=opt,
-                               log=trace_to_log(trace[c, :rows], save_inner_iteration=False),
+                               log=trace_to_log(trace[c, :rows], save_inner_iteration=save_inner),
                                ineqLagmult=np.array(Y[:, c]), eqLagmult=[]))
         return outs
 

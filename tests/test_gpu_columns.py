@@ -152,7 +152,8 @@ def test_run_columns_returns_reference_style_outputs(rb):
     """RIPTRM(option).run_columns: one Output per column with the reference's per-outer-iteration log layout."""
     n, p = 128, 3
     Z, X0, Y0, rs = _instance(n, p, seed=21)
-    solver = rb.RIPTRM({"TRS_solver": "tCG", "second_order_stationarity": False, "maxiter": 12, "tolresid": 0, "maxtime": 1e9})
+    solver = rb.RIPTRM({"TRS_solver": "tCG", "second_order_stationarity": False, "maxiter": 12, "tolresid": 0, "maxtime": 1e9,
+                        "save_inner_iteration": False})
     outs = solver.run_columns(Z, X0, np.ones((n, p)))
     assert len(outs) == p
     for c, o in enumerate(outs):
@@ -163,3 +164,30 @@ def test_run_columns_returns_reference_style_outputs(rb):
         assert all(b <= a + 1e-12 for a, b in zip(o.log["cost"][1:], o.log["cost"][2:]))   # objective decreases
         assert o.option["stoppingcriterion"].startswith("Max iteration count reached; maxiter=12")
         assert abs(np.linalg.norm(o.x) - 1) < 1e-14
+
+
+def test_per_inner_iteration_log_matches_the_c_oracle(rb):
+    """run_columns with the reference's default save_inner_iteration=True: one log row per trust-region iteration and
+    column.  Against the C oracle's trace of the same column (n = 100): identical discrete columns (status, tCG stop reason,
+    radius update, clipping flag) and radii in the well-conditioned window, float columns to 1e-8 there."""
+    from helpers import DISCRETE_COLUMNS, first_discrete_mismatch, max_rel_diff
+    from oracle.c import binding as detc
+    n, p = 100, 3
+    Z, X0, Y0, rs = _instance(n, p, seed=31)
+    Y0 = np.ones((n, p))
+    K = 10
+    solver = rb.RIPTRM({"TRS_solver": "tCG", "second_order_stationarity": False, "maxiter": K, "tolresid": 0, "maxtime": 1e9})
+    outs = solver.run_columns(Z, X0, Y0)
+    for c, o in enumerate(outs):
+        xo, yo, so, tr = detc.solve(Z, X0[:, c].copy(), Y0[:, c].copy(), {"maxiter": K, "tolresid": 0}, trace_capacity=400)
+        ref = rb.trace_to_log(tr)
+        assert o.log["iteration"][0] == 0 and o.log["inner_status"][0] is None
+        first = first_discrete_mismatch(o.log, ref)
+        outer = ref["iteration"][min(first, len(ref["iteration"]) - 1)]
+        assert outer >= 7 or first == len(ref["iteration"]), (c, first, outer)
+        m = min(first, 25)
+        assert max_rel_diff(o.log, ref, "TR_radius", rows=m) < 1e-12
+        for col in ("cost", "mu", "normdx", "maxabsLagmult", "minxfeasi", "compl"):
+            assert max_rel_diff(o.log, ref, col, rows=m, floor=1e-12) < 1e-6, (c, col)
+        assert max_rel_diff(o.log, ref, "residual", rows=m, floor=1e-10) < 1e-5
+        assert abs(o.log["cost"][-1] - ref["cost"][-1]) < 1e-7 * abs(ref["cost"][-1])
