@@ -8,15 +8,19 @@
 // S = Z + Z' (n x n), V = [delta_1 .. delta_p]: the HBM-bound Hessian-vector product.
 //
 // Kernel shape: a persistent cooperative grid, one CTA of 9 warps per SM.
-//   * S.V pass ("stream"): S is cut into tiles of TJ=32 rows x TW=128 columns (32 KB).  The tiles, linearised
-//     (column block major, row block minor), are dealt to the CTAs in equal contiguous ranges (stream-K), so
-//     148 SMs stay equally loaded for any n.  Warp 8 is the producer: its 32 lanes issue one 1 KB bulk
-//     async copy (TMA, cp.async.bulk -> SASS UBLKCP) per tile row plus one for the 32 x p slice of V into a
-//     5-stage shared-memory ring guarded by full/empty mbarriers.  Warps 0..7 consume: S is symmetric, so
-//     (S V)[i,:] = sum_j S[j,i] V[j,:] and a warp reads row j of the tile with lanes along i (conflict-free
-//     LDS.128) while V[j,0..p) is a shared-memory broadcast; each thread owns 4 columns i x p accumulators
-//     (40 DFMA per 7 LDS.128).  At a column-block boundary the 8 warps' accumulators are summed in warp
-//     order and written as a partial; the owner of each row later adds the partials in CTA order.
+//   * S.V pass ("stream"): S is cut into tiles of TJ=32 rows x TW=128 columns (32 KB), stored tile by tile in
+//     streaming order.  The tiles, linearised (column block major, row block minor), are dealt to the CTAs in
+//     equal contiguous ranges (stream-K), so 148 SMs stay equally loaded for any n.  Warp 8 is the producer: one
+//     32 KB bulk async copy (TMA, cp.async.bulk -> SASS UBLKCP) per tile plus one for the 32 x p slice of V into a
+//     5-stage shared-memory ring guarded by full/empty mbarriers.  Warps 0..7 consume.  S is symmetric, so
+//     (S V)[i,:] = sum_j S[j,i] V[j,:].
+//       P >= 8: FP64 tensor cores, mma.sync.m8n8k4.f64 (SASS DMMA) with M <-> i, K <-> j, N <-> column of V; inside a
+//       tile S is stored in A-fragment order, so a fragment is one coalesced LDS.64; a warp owns 16 columns i of the
+//       tile and at most 8 accumulator doubles per thread.
+//       P = 1, 2, 4: DFMA; a warp reads row j of the tile with lanes along i (conflict-free LDS.128) while V[j,0..p)
+//       is a shared-memory broadcast; each thread owns 4 columns i x p accumulators, the 8 warps' accumulators are
+//       summed in warp order at a column-block boundary.
+//     The partial of a column block is written per CTA; the owner of each row later adds the partials in CTA order.
 //   * every other step of the tCG iteration is a "vector phase" over the n x p arrays (L2 resident, 1.6 MB
 //     each), rows dealt to CTAs in contiguous chunks, with per-column dot products reduced per CTA in a
 //     fixed order and then over CTAs in CTA order.  Phases are separated by grid-wide barriers (four per tCG
@@ -1043,8 +1047,6 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
     build_gather_tab<P>(prm, sm, row_lo, row_hi);
     Pipe pipe{0, 0u};
     int buf = 0;
-    const double nan = CUDART_NAN;
-    (void)nan;
 
     if (INIT) {
         // x0 -> X, V; S x0; cost, x'Sx; the first outer iteration starts after the evaluation below

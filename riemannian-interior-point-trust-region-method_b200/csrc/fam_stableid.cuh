@@ -327,8 +327,6 @@ struct StableIdFam {
         CVec ydc;
         ydc.v[0] = y.v[0] * dcoef.v[0];
         const LM dPhiL = scatter(c, ydc, ones, dga);
-        const LM Qt_dummy = 0.0;
-        (void)Qt_dummy;
         // pull_d: hJ = dPhi Q' + Phi dQ' ; hR = -hJ ; hQ = (dJ - dR)' Phi + (J - R)' dPhi
         const LM hJ = mul(c, dPhiL, pt.x.v[2], false, true) + mul(c, st.PhiL, v.v[2], false, true);
         const LM hQ = mul(c, v.v[0] - v.v[1], st.PhiL, true, false) + mul(c, pt.JmR, dPhiL, true, false);
