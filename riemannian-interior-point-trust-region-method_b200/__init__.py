@@ -2,7 +2,7 @@
 trust-region method, behind the reference's `RIPTRM(option).run(problem) -> Output` interface.
 
 The directory name carries the reference's name; import it as `riptrm_b200` (repo-root shim)."""
-from . import _lib, datagen, options, sharding, structure
+from . import _lib, datagen, io, options, sharding, structure
 from ._lib import RiptrmError, load_library
 from .solver import RIPTRM, BatchSolver, ColumnsSolver, Output, columns_bench, trace_to_log
 from .structure import (NonnegPCAStructure, RosenbrockStructure, StableIdStructure,

@@ -177,6 +177,8 @@ def _original_constraints(problem):
 
 def structure_from_problem(problem):
     """Returns the structure of a reference-style NonlinearProblem or raises NotImplementedError."""
+    if isinstance(problem, (NonnegPCAStructure, RosenbrockStructure, StableIdStructure)):
+        return problem
     st = getattr(problem, "riptrm_structure", None)
     if st is not None:
         return st

@@ -29,6 +29,16 @@ elif {name!r} == "Rosenbrock":
     out["alpha"] = st.alpha; out["offset"] = st.offset
 else:
     out["conspec_rows"] = len(st.conspec); out["kinds"] = sorted(set(st.conspec[:, 0].tolist())); out["N"] = st.X.shape[1]
+ld = rb.io.load_structure({name!r}, "/root/reference/dataset", 1, "a")
+same = type(ld) is type(st) and np.array_equal(np.hstack([np.ravel(a) for a in ([ld.x0] if not isinstance(ld.x0, list) else ld.x0)]),
+                                               np.hstack([np.ravel(a) for a in ([st.x0] if not isinstance(st.x0, list) else st.x0)]))
+if {name!r} == "NonnegPCA":
+    same = same and np.array_equal(ld.Z, st.Z)
+elif {name!r} == "Rosenbrock":
+    same = same and ld.alpha == st.alpha and ld.shape == st.shape
+else:
+    same = same and np.array_equal(ld.X, st.X) and np.array_equal(ld.XP, st.XP) and np.array_equal(ld.conspec, st.conspec) and ld.h == st.h
+out["loader_agrees"] = bool(same)
 print("RESULT " + json.dumps(out))
 '''
 
@@ -45,19 +55,20 @@ def _run(name):
 def test_nonnegpca_problem_is_recognised():
     out = _run("NonnegPCA")
     assert out["type"] == "NonnegPCAStructure" and out["shape"] == [50, 1, 50] and out["family"] == 1
-    assert out["Z_equal"] and out["x0_equal"]
+    assert out["Z_equal"] and out["x0_equal"] and out["loader_agrees"]
 
 
 def test_rosenbrock_problem_is_recognised():
     out = _run("Rosenbrock")
     assert out["type"] == "RosenbrockStructure" and out["shape"] == [5, 3, 15]
-    assert out["alpha"] == 1e7 and out["offset"] == 0.01
+    assert out["alpha"] == 1e7 and out["offset"] == 0.01 and out["loader_agrees"]
 
 
 def test_stableid_problem_is_recognised():
     out = _run("StableIdentification")
     assert out["type"] == "StableIdStructure" and out["shape"] == [5, 3, 16]
     assert out["conspec_rows"] == 16 and out["kinds"] == [0.0, 1.0, 2.0] and out["N"] == 95
+    assert out["loader_agrees"]
 
 
 def test_reference_simulator_reaches_the_c_abi_through_the_dropin_module():

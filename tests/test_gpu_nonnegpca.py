@@ -278,3 +278,23 @@ def test_tmem_and_shared_memory_kernels_agree_bit_for_bit(rb, monkeypatch):
     for i in range(len(rows)):
         a, b = ta[i, :rows[i]][:, cols], tb[i, :rows[i]][:, cols]
         assert ((a == b) | (np.isnan(a) & np.isnan(b))).all()
+
+
+def test_dataset_files_in_output_files_out(rb, datasets, tmp_path):
+    """The reference's file formats either side of the path: dataset CSVs -> `run` on the loaded structure -> the
+    `save_output` file set; same result as the in-memory route, final cost equal to the golden run's to 1e-8."""
+    import pandas as pd
+    g = load_golden("nonnegpca_1_a_K40")
+    d = datasets["NonnegPCA/1"]
+    rb.io.save_dataset(str(tmp_path / "dataset" / "NonnegPCA" / "1"), dim=[[50]], Z=d["Z"], initx_a=d["initx_a"],
+                       initineqLagmult=d["initineqLagmult"])
+    st = rb.io.load_structure("NonnegPCA", str(tmp_path / "dataset"), 1, "a")
+    option = {"TRS_solver": "tCG", "second_order_stationarity": False, "tolresid": 0, "maxtime": 1e9, "maxiter": 40}
+    out = rb.RIPTRM(option).run(st)
+    mem, _ = _solve(rb, rb.NonnegPCAStructure(Z=d["Z"], x0=d["initx_a"], y0=d["initineqLagmult"]), maxiter=40)
+    assert np.array_equal(out.x, mem.x) and out.log["cost"] == mem.log["cost"]
+    path = rb.io.save_output(out, str(tmp_path / "intermediate" / "NonnegPCA" / "1" / "a"))
+    log = pd.read_csv(path + "/RIPTRM_tCG_log.csv")
+    assert int((log["inner_status"] == "converged").sum()) == 40
+    assert abs(log["cost"].iloc[-1] - g["log"]["cost"][-1]) < REL_TOL * abs(g["log"]["cost"][-1])
+    assert np.array_equal(np.loadtxt(path + "/RIPTRM_tCG_x.csv"), out.x)

@@ -1,6 +1,7 @@
 """Host-side logic that needs no GPU: option defaults / schedules, log reconstruction from trace rows,
 the synthetic-instance generator, structure recognition of reference-style closures."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -143,3 +144,50 @@ def test_sweep_generator_matches_oracle_and_scales_to_8_gpus():
         assert np.array_equal(x0[4], rb.datagen.nonnegpca_instance(50, seed=first + 1)[1])
     with pytest.raises(ValueError):
         rb.datagen.nonnegpca_sweep(0, 2, 17)
+
+
+def test_dataset_csv_roundtrip_and_loader(tmp_path, datasets):
+    """The reference's dataset format (np.savetxt '%.18e' files under dataset/<problem>/<instance>/) round-trips
+    exactly and loads into the structured problem descriptions."""
+    d = datasets["NonnegPCA/1"]
+    root = tmp_path / "dataset"
+    rb.io.save_dataset(str(root / "NonnegPCA" / "7"), dim=[[50]], Z=d["Z"], initx_a=d["initx_a"],
+                       initineqLagmult=d["initineqLagmult"])
+    st = rb.io.load_structure("NonnegPCA", str(root), instance=7, initialpoint="a")
+    assert np.array_equal(st.Z, d["Z"]) and np.array_equal(st.x0, d["initx_a"]) and st.shape == (50, 1, 50)
+    s = datasets["StableIdentification/1"]
+    sid = str(root / "StableIdentification" / "1")
+    rb.io.save_dataset(sid, constset=s["constset"], initineqLagmult=s["initineqLagmult"],
+                       **{f"noisyX_{k}": s[f"noisyX_{k}"] for k in range(1, 6)},
+                       **{f"init{c}_b": s[f"init{c}_b"] for c in "JRQ"})
+    st = rb.io.load_structure("StableIdentification", str(root), instance=1, initialpoint="b")
+    assert st.X.shape == (5, 95) and st.XP.shape == (5, 95) and st.conspec.shape == (16, 5)
+    assert np.array_equal(st.X[:, :19], s["noisyX_1"][:, :-1]) and np.array_equal(st.XP[:, :19], s["noisyX_1"][:, 1:])
+    assert np.array_equal(st.x0[1], s["initR_b"])
+    ros = rb.io.load_structure("Rosenbrock", str(root))
+    assert ros.shape == (5, 3, 15) and ros.alpha == 1e7
+    with pytest.raises(NotImplementedError):
+        rb.io.load_structure("Unknown", str(root))
+
+
+def test_save_output_writes_the_reference_file_set(tmp_path):
+    import pandas as pd
+    nan = float("nan")
+    T = _lib.TR
+    rows = np.full((3, _lib.TRACE_FIELDS), nan)
+    rows[:, T["iteration"]] = [0, 1, 1]
+    rows[:, T["cost"]] = [-0.5, -0.7, -0.9]
+    rows[1:, T["inner_status"]] = [3, 1]
+    rows[:, T["maxabsLagmult"]] = 1.0
+    opt = options.default_option()
+    opt["stoppingcriterion"] = "Max iteration count reached; maxiter=1 after 0.00 seconds"
+    out = rb.Output(name="RIPTRM_tCG", x=np.arange(3.0), option=opt, log=rb.trace_to_log(rows),
+                    ineqLagmult=np.ones(3), eqLagmult=[])
+    path = rb.io.save_output(out, str(tmp_path / "intermediate" / "NonnegPCA" / "1" / "a"))
+    files = sorted(os.listdir(path))
+    assert files == [f"RIPTRM_tCG_{a}.csv" for a in sorted(("name", "x", "option", "log", "ineqLagmult", "eqLagmult"))]
+    log = pd.read_csv(os.path.join(path, "RIPTRM_tCG_log.csv"))
+    assert list(log["cost"]) == [-0.5, -0.7, -0.9] and list(log["inner_status"])[1:] == ["successful", "converged"]
+    assert np.array_equal(np.loadtxt(os.path.join(path, "RIPTRM_tCG_x.csv")), np.arange(3.0))
+    optcsv = pd.read_csv(os.path.join(path, "RIPTRM_tCG_option.csv"))
+    assert len(optcsv) == 1 and optcsv["maxiter"][0] == 100
