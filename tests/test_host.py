@@ -191,3 +191,24 @@ def test_save_output_writes_the_reference_file_set(tmp_path):
     assert np.array_equal(np.loadtxt(os.path.join(path, "RIPTRM_tCG_x.csv")), np.arange(3.0))
     optcsv = pd.read_csv(os.path.join(path, "RIPTRM_tCG_option.csv"))
     assert len(optcsv) == 1 and optcsv["maxiter"][0] == 100
+
+
+def test_save_output_product_point_is_block_file(tmp_path):
+    """For a Product-manifold point (list of matrices) the reference's writer falls into csv.writer.writerows: one line per
+    component, one cell per matrix row holding numpy's str() of that row (8 significant digits).  The strict-complementarity
+    analyzer parses exactly that (src/StableIdentification/analyzer_strict_complementarity.py:6-34): strip the brackets,
+    split on blanks, stack."""
+    import csv
+    rs = np.random.RandomState(3)
+    x = [rs.randn(5, 5) for _ in range(3)]
+    out = rb.Output(name="RIPTRM_tCG", x=x, option={"maxiter": 1}, log={"iteration": [0]}, ineqLagmult=np.ones(16), eqLagmult=[])
+    path = rb.io.save_output(out, str(tmp_path))
+    mats = []
+    with open(os.path.join(path, "RIPTRM_tCG_x.csv"), newline="") as f:
+        for row in csv.reader(f):
+            vecs = [np.array(cell.strip().lstrip("[").rstrip("]").split(), dtype=float) for cell in row if cell.strip()]
+            mats.append(np.vstack(vecs))
+    got = np.stack(mats)
+    assert got.shape == (3, 5, 5) and np.max(np.abs(got - np.stack(x))) < 1e-7
+    assert np.loadtxt(os.path.join(path, "RIPTRM_tCG_ineqLagmult.csv")).shape == (16,)
+    assert os.path.getsize(os.path.join(path, "RIPTRM_tCG_eqLagmult.csv")) == 0
