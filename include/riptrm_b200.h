@@ -53,7 +53,11 @@ typedef enum {
     RIPTRM_FAMILY_STABLEID_PRODUCT = 3,
     /* min -tr(X'ZX), X n x p with unit columns sharing one large Z (Oblique / multi-start
      * reading of BASELINE config 4): the HBM-bound path */
-    RIPTRM_FAMILY_NONNEGPCA_COLUMNS = 4
+    RIPTRM_FAMILY_NONNEGPCA_COLUMNS = 4,
+    /* min -tr(X'ZX) on Stiefel(n,p), X_ij + eps >= 0, one large Z (the Stiefel reading of BASELINE config 4;
+     * SURVEY.md App. A.4): ONE run with n x p matrix iterates; batch = 1, m = n*p; x, y, v, out are [n][p]
+     * row-major, info is [4], summary [1][..], trace [1][capacity][..].  Same streaming kernel as COLUMNS. */
+    RIPTRM_FAMILY_NONNEGPCA_STIEFEL = 5
 } riptrm_family;
 
 /* tCG stop reasons -- RIPTRM.py:95,143,145,164,188,190 (dxtype = "tCG_" + name) */

@@ -150,13 +150,16 @@ class NonnegPCAStiefelProblem(OracleProblem):
 
     family = "nonnegpca_matrix"
 
-    def __init__(self, Z, X0, y0=None, eps=0.01, manifold="stiefel"):
+    def __init__(self, Z, X0, y0=None, eps=0.01, manifold="stiefel", closed_form=False):
         Z = np.asarray(Z, dtype=float)
         X0 = np.asarray(X0, dtype=float)
         n, p = X0.shape
         self.Z, self.eps, self.n, self.p = Z, float(eps), n, p
         man = M.Stiefel(n, p) if manifold == "stiefel" else M.Oblique(n, p)
         super().__init__(man, X0, np.ones(n * p) if y0 is None else y0)
+        # closed_form: the aggregate operators of riptrm_oracle.py in matrix form instead of
+        # m = n p per-constraint closures; checked against the per-constraint path in tests/test_oracle_stiefel.py
+        self.closed = _StiefelClosedForm(self) if (closed_form and manifold == "stiefel") else None
 
     def cost(self, X):
         return -np.trace(X.T @ self.Z @ X)
@@ -183,6 +186,37 @@ class NonnegPCAStiefelProblem(OracleProblem):
         if isinstance(problem.manifold, M.Oblique):
             return np.linalg.norm(np.linalg.norm(X, axis=0) - 1)
         return np.linalg.norm(X.T @ X - np.eye(X.shape[1]))
+
+
+class _StiefelClosedForm:
+    """Matrix forms of the RIPTRM operators for NonnegPCAStiefelProblem: g_ij = -X_ij - eps, so
+    egrad g_ij = -E_ij, ehess g_ij = 0, grad s_ij = P_X(E_ij), and every sum over constraints is one projection."""
+
+    def __init__(self, problem):
+        self.pb = problem
+        self.S = problem.Z + problem.Z.T
+
+    def _Y(self, y):
+        return np.asarray(y).reshape(self.pb.n, self.pb.p)
+
+    def slack(self, X):
+        return (X + self.pb.eps).reshape(-1)
+
+    def grad_lagrangian(self, X, y):                      # grad f + sum y_i grad g_i
+        man = self.pb.manifold
+        return man.projection(X, -self.S @ X) + man.projection(X, -self._Y(y))
+
+    def hess_lagrangian(self, X, y, V):                   # Hess f[V] + sum y_i Hess g_i[V]
+        man = self.pb.manifold
+        hf = man.euclidean_to_riemannian_hessian(X, -self.S @ X, -self.S @ V, V)
+        hg = man.euclidean_to_riemannian_hessian(X, -self._Y(y), np.zeros_like(X), V)
+        return hf + hg
+
+    def G_apply(self, X, w):                              # sum w_i grad s_i
+        return self.pb.manifold.projection(X, self._Y(w))
+
+    def Gadj_apply(self, X, V, euclidean_embedded):       # <grad s_i, V>
+        return (V if euclidean_embedded else self.pb.manifold.projection(X, V)).reshape(-1)
 
 
 class RosenbrockProblem(OracleProblem):

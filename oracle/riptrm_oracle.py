@@ -172,6 +172,8 @@ def egrad_lagrangian(problem, x, y):
 
 def grad_lagrangian(problem, x, y, lincomb=False):
     """RIPTRM.py:475-489."""
+    if getattr(problem, "closed", None) is not None:
+        return problem.closed.grad_lagrangian(x, y)
     man = problem.manifold
     if lincomb:
         return man.euclidean_to_riemannian_gradient(x, egrad_lagrangian(problem, x, y))
@@ -184,6 +186,8 @@ def grad_lagrangian(problem, x, y, lincomb=False):
 
 def hess_lagrangian(problem, x, y, dx, lincomb=False):
     """RIPTRM.py:491-523."""
+    if getattr(problem, "closed", None) is not None:
+        return problem.closed.hess_lagrangian(x, y, dx)
     man = problem.manifold
     if lincomb:
         eg = egrad_lagrangian(problem, x, y)
@@ -201,6 +205,8 @@ def hess_lagrangian(problem, x, y, dx, lincomb=False):
 
 def G_apply(problem, x, w, lincomb=False):
     """G_x(w) = sum_i w_i grad s_i(x), s_i = -g_i.  RIPTRM.py:525-551."""
+    if getattr(problem, "closed", None) is not None:
+        return problem.closed.G_apply(x, w)
     man = problem.manifold
     if lincomb:
         negs = [-_amb(man, eg(x)) for eg in problem.ineqconstraints_euclidean_gradient_all]
@@ -217,6 +223,8 @@ def G_apply(problem, x, w, lincomb=False):
 
 def Gadj_apply(problem, x, dx, euclidean_embedded=False):
     """G*_x[dx]_i = <grad s_i(x), dx>_x.  RIPTRM.py:553-571."""
+    if getattr(problem, "closed", None) is not None:
+        return problem.closed.Gadj_apply(x, dx, euclidean_embedded)
     man = problem.manifold
     if euclidean_embedded:
         negs = [-_amb(man, eg(x)) for eg in problem.ineqconstraints_euclidean_gradient_all]
@@ -227,6 +235,8 @@ def Gadj_apply(problem, x, dx, euclidean_embedded=False):
 
 def slack(problem, x):
     """costineqconstvecfun: s(x) = -g(x).  RIPTRM.py:576,721."""
+    if getattr(problem, "closed", None) is not None:
+        return problem.closed.slack(x)
     return np.array([-g(x) for g in problem.ineqconstraints_all])
 
 
@@ -236,12 +246,17 @@ def slack(problem, x):
 def kkt_residual(problem, x, y, manviofun):
     """utils.compute_residual (utils.py:269-340), inequality-only."""
     man = problem.manifold
-    vec = problem.riemannian_gradient(x)
-    grads = problem.ineqconstraints_riemannian_gradient_all
-    for i in range(problem.num_ineqconstraints):
-        vec = vec + y[i] * grads[i](x)
+    closed = getattr(problem, "closed", None)
+    if closed is not None:
+        vec = closed.grad_lagrangian(x, y)
+        gvals = list(-closed.slack(x))
+    else:
+        vec = problem.riemannian_gradient(x)
+        grads = problem.ineqconstraints_riemannian_gradient_all
+        for i in range(problem.num_ineqconstraints):
+            vec = vec + y[i] * grads[i](x)
+        gvals = [g(x) for g in problem.ineqconstraints_all]
     gradnorm = man.norm(x, vec)
-    gvals = [g(x) for g in problem.ineqconstraints_all]
     sq_compl = 0
     for i, gv in enumerate(gvals):
         sq_compl += (y[i] * gv) ** 2
@@ -259,12 +274,17 @@ def kkt_residual(problem, x, y, manviofun):
 def evaluate(problem, xPrev, x, y, manviofun, callbackfun):
     """utils.evaluation (utils.py:342-368) + compute_maxmeanviolations (:237-267)."""
     cost = problem.cost(x)
-    dist = problem.manifold.dist(xPrev, x)
+    try:
+        dist = problem.manifold.dist(xPrev, x)
+    except NotImplementedError:   # pymanopt's Stiefel: the reference's evaluation would stop here; the log gets NaN
+        dist = float("nan")
     residual, gradnorm, compl, nonneg, manvio = kkt_residual(problem, x, y, manviofun)
     maxv = 0
     meanv = 0
-    for g in problem.ineqconstraints_all:
-        v = max(g(x), 0)
+    closed = getattr(problem, "closed", None)
+    gvals = list(-closed.slack(x)) if closed is not None else [g(x) for g in problem.ineqconstraints_all]
+    for gv in gvals:
+        v = max(gv, 0)
         maxv = max(maxv, v)
         meanv += v
     if problem.num_ineqconstraints > 0:

@@ -4,9 +4,9 @@ trust-region method, behind the reference's `RIPTRM(option).run(problem) -> Outp
 The directory name carries the reference's name; import it as `riptrm_b200` (repo-root shim)."""
 from . import _lib, datagen, io, options, sharding, structure
 from ._lib import RiptrmError, load_library
-from .solver import RIPTRM, BatchSolver, ColumnsSolver, Output, columns_bench, trace_to_log
+from .solver import RIPTRM, BatchSolver, ColumnsSolver, StiefelSolver, Output, columns_bench, trace_to_log
 from .structure import (NonnegPCAStructure, RosenbrockStructure, StableIdStructure,
                         structure_from_problem)
 
-__all__ = ["RIPTRM", "BatchSolver", "ColumnsSolver", "columns_bench", "Output", "trace_to_log", "RiptrmError", "load_library",
+__all__ = ["RIPTRM", "BatchSolver", "ColumnsSolver", "StiefelSolver", "columns_bench", "Output", "trace_to_log", "RiptrmError", "load_library",
            "NonnegPCAStructure", "RosenbrockStructure", "StableIdStructure", "structure_from_problem"]

@@ -13,6 +13,7 @@ FAMILY_NONNEGPCA_SPHERE = 1
 FAMILY_ROSENBROCK_GRASSMANN = 2
 FAMILY_STABLEID_PRODUCT = 3
 FAMILY_NONNEGPCA_COLUMNS = 4
+FAMILY_NONNEGPCA_STIEFEL = 5
 TRACE_FIELDS = 25
 SUMMARY_FIELDS = 16
 

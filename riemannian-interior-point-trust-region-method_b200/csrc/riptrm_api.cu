@@ -17,6 +17,7 @@
 
 #include "../../include/riptrm_b200.h"
 #include "fam_columns.cuh"
+#include "fam_stiefel.cuh"
 #include "fam_grassmann.cuh"
 #include "fam_sphere.cuh"
 #include "fam_stableid.cuh"
@@ -242,6 +243,10 @@ extern "C" int riptrm_create(int family, int n, int p, int m, int batch, int dev
         if (batch != 1) return fail(RIPTRM_E_INVALID, "COLUMNS family: batch must be 1 (the p columns are the batch)");
         if (m != n * p) return fail(RIPTRM_E_INVALID, "COLUMNS family needs m == n * p");
         if (p > col::MAXP) return fail(RIPTRM_E_UNSUPPORTED, "COLUMNS family: p <= 16");
+    } else if (family == RIPTRM_FAMILY_NONNEGPCA_STIEFEL) {
+        if (batch != 1) return fail(RIPTRM_E_INVALID, "STIEFEL family: batch must be 1 (one n x p matrix iterate)");
+        if (m != n * p) return fail(RIPTRM_E_INVALID, "STIEFEL family needs m == n * p");
+        if (p > col::MAXP || p > n) return fail(RIPTRM_E_UNSUPPORTED, "STIEFEL family: p <= 16, p <= n");
     } else {
         return fail(RIPTRM_E_UNSUPPORTED, "family not built into this library");
     }
@@ -318,9 +323,13 @@ static int columns_template_p(int p) {
     return -1;
 }
 
+static bool is_stiefel(const riptrm_handle* h) { return h->family == RIPTRM_FAMILY_NONNEGPCA_STIEFEL; }
+// the Stiefel kernels are built for P = 4, 10, 16
+static int stiefel_template_p(int p) { return p <= 4 ? 4 : (p <= 10 ? 10 : 16); }
+
 static int columns_setup(riptrm_handle* h, const double* Z, double eps, int where) {
     const int n = h->n;
-    h->colP = columns_template_p(h->p);
+    h->colP = is_stiefel(h) ? stiefel_template_p(h->p) : columns_template_p(h->p);
     h->n_pad = (n + col::TJ - 1) / col::TJ * col::TJ;
     h->ld = (n + col::TW - 1) / col::TW * col::TW;
     h->col_grid = h->num_sms;
@@ -354,7 +363,7 @@ static int columns_setup(riptrm_handle* h, const double* Z, double eps, int wher
     if (tmpZ) cudaFree(tmpZ);
     const size_t arr = (size_t)h->n_pad * h->colP;
     const size_t mv = (size_t)h->col_grid * h->col_slots * col::TW * h->colP;
-    const size_t dots = (size_t)2 * h->col_grid * col::MAXQ * col::MAXP;
+    const size_t dots = (size_t)2 * h->col_grid * stf::DOT_STRIDE;
     const size_t total_d = kColArrays * arr + mv + dots + 4 * col::MAXP + (size_t)2 * (h->col_grid + 2) +
                            (size_t)col::MAXP * col::CS_FIELDS + (size_t)col::MAXP * RIPTRM_SUMMARY_FIELDS + 2;
     CUDA_TRY(cudaMalloc(&h->d_colbuf, total_d * sizeof(double)));
@@ -392,8 +401,34 @@ static int columns_launch(riptrm_handle* h, col::Params& prm, cudaStream_t st) {
     return RIPTRM_OK;
 }
 
+template <int P, int MODE>
+static int stiefel_launch(riptrm_handle* h, col::Params& prm, cudaStream_t st) {
+    auto kern = stf::stiefel_kernel<P, MODE>;
+    const size_t smem = sizeof(col::Smem<P>);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, col::NT, smem));
+    if (per_sm < 1) return fail(RIPTRM_E_UNSUPPORTED, "stiefel kernel does not fit on an SM");
+    void* args[] = {&prm};
+    CUDA_TRY(cudaEventRecord(h->ev0, st));
+    CUDA_TRY(cudaLaunchCooperativeKernel((void*)kern, dim3(h->col_grid), dim3(col::NT), args, smem, st));
+    CUDA_TRY(cudaEventRecord(h->ev1, st));
+    h->launches += 1;
+    return RIPTRM_OK;
+}
+
 template <int MODE>
 static int columns_dispatch(riptrm_handle* h, col::Params& prm, cudaStream_t st) {
+    if (is_stiefel(h)) {
+        if (MODE == 3) return fail(RIPTRM_E_UNSUPPORTED, "stream-only diagnostic: COLUMNS family only");
+        constexpr int M = (MODE == 3) ? 2 : MODE;
+        switch (h->colP) {
+            case 4: return stiefel_launch<4, M>(h, prm, st);
+            case 10: return stiefel_launch<10, M>(h, prm, st);
+            case 16: return stiefel_launch<16, M>(h, prm, st);
+        }
+        return fail(RIPTRM_E_UNSUPPORTED, "unsupported column count");
+    }
     switch (h->colP) {
         case 1: return columns_launch<1, MODE>(h, prm, st);
         case 2: return columns_launch<2, MODE>(h, prm, st);
@@ -449,7 +484,7 @@ static ColPtrs columns_fill_params(riptrm_handle* h, col::Params& prm) {
     q.out = b + 23 * arr;
     prm.mv_part = b + kColArrays * arr;
     prm.dot_part = prm.mv_part + (size_t)h->col_grid * h->col_slots * col::TW * h->colP;
-    q.info = prm.dot_part + (size_t)2 * h->col_grid * col::MAXQ * col::MAXP;
+    q.info = prm.dot_part + (size_t)2 * h->col_grid * stf::DOT_STRIDE;
     prm.tbeg = reinterpret_cast<const long long*>(q.info + 4 * col::MAXP);
     prm.tib0 = reinterpret_cast<const int*>(q.info + 4 * col::MAXP + (h->col_grid + 2));
     q.colstate = q.info + 4 * col::MAXP + (size_t)2 * (h->col_grid + 2);
@@ -489,7 +524,7 @@ static int columns_run(riptrm_handle* h, int mode, const double* x, const double
     if ((rc = columns_export(h, out, d_out, where, st))) return rc;
     if (info != nullptr && mode == 2) {
         const cudaMemcpyKind kind = (where == RIPTRM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-        CUDA_TRY(cudaMemcpyAsync(info, d_info, (size_t)h->p * 4 * sizeof(double), kind, st));
+        CUDA_TRY(cudaMemcpyAsync(info, d_info, (size_t)(is_stiefel(h) ? 1 : h->p) * 4 * sizeof(double), kind, st));
     }
     if (where == RIPTRM_DEVICE) return RIPTRM_OK;
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -507,8 +542,26 @@ static int columns_launch_post(riptrm_handle* h, col::Params& prm, cudaStream_t 
     h->launches += 1;
     return RIPTRM_OK;
 }
+template <int P, bool INIT>
+static int stiefel_launch_post(riptrm_handle* h, col::Params& prm, cudaStream_t st) {
+    auto kern = stf::stiefel_post_kernel<P, INIT>;
+    const size_t smem = sizeof(col::Smem<P>);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* args[] = {&prm};
+    CUDA_TRY(cudaLaunchCooperativeKernel((void*)kern, dim3(h->col_grid), dim3(col::NT), args, smem, st));
+    h->launches += 1;
+    return RIPTRM_OK;
+}
 template <bool INIT>
 static int columns_dispatch_post(riptrm_handle* h, col::Params& prm, cudaStream_t st) {
+    if (is_stiefel(h)) {
+        switch (h->colP) {
+            case 4: return stiefel_launch_post<4, INIT>(h, prm, st);
+            case 10: return stiefel_launch_post<10, INIT>(h, prm, st);
+            case 16: return stiefel_launch_post<16, INIT>(h, prm, st);
+        }
+        return fail(RIPTRM_E_UNSUPPORTED, "unsupported column count");
+    }
     switch (h->colP) {
         case 1: return columns_launch_post<1, INIT>(h, prm, st);
         case 2: return columns_launch_post<2, INIT>(h, prm, st);
@@ -544,8 +597,9 @@ static int columns_solve(riptrm_handle* h, const double* x0, const double* y0, d
     prm.gamma = o.gamma;
     prm.const_left = o.const_left;
     prm.const_right = o.const_right;
+    const int nruns = is_stiefel(h) ? 1 : h->p;  // STIEFEL: one run; COLUMNS: one per column
     const size_t tb = (o.trace_mode != 0 && trace != nullptr)
-                          ? (size_t)h->p * o.trace_capacity * RIPTRM_TRACE_FIELDS * sizeof(double) : 0;
+                          ? (size_t)nruns * o.trace_capacity * RIPTRM_TRACE_FIELDS * sizeof(double) : 0;
     if (tb != 0) {
         if (where == RIPTRM_DEVICE) {
             prm.trace = trace;
@@ -587,7 +641,7 @@ static int columns_solve(riptrm_handle* h, const double* x0, const double* y0, d
     if (y != nullptr && (rc = columns_export(h, y, prm.Y, where, st))) return rc;
     const cudaMemcpyKind kind = (where == RIPTRM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     if (summary != nullptr)
-        CUDA_TRY(cudaMemcpyAsync(summary, q.summary, (size_t)h->p * RIPTRM_SUMMARY_FIELDS * sizeof(double), kind, st));
+        CUDA_TRY(cudaMemcpyAsync(summary, q.summary, (size_t)nruns * RIPTRM_SUMMARY_FIELDS * sizeof(double), kind, st));
     if (tb != 0 && where != RIPTRM_DEVICE) CUDA_TRY(cudaMemcpyAsync(trace, h->d_trace, tb, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return finish_timing(h, true);
@@ -595,11 +649,11 @@ static int columns_solve(riptrm_handle* h, const double* x0, const double* y0, d
 
 extern "C" int riptrm_set_nonnegpca(riptrm_handle* h, const double* Z, int batch_z, double eps, int where) {
     if (h == nullptr || Z == nullptr) return fail(RIPTRM_E_INVALID, "NULL argument");
-    if (h->family != RIPTRM_FAMILY_NONNEGPCA_SPHERE && h->family != RIPTRM_FAMILY_NONNEGPCA_COLUMNS)
+    if (h->family != RIPTRM_FAMILY_NONNEGPCA_SPHERE && h->family != RIPTRM_FAMILY_NONNEGPCA_COLUMNS && !is_stiefel(h))
         return fail(RIPTRM_E_INVALID, "handle is not a NonnegPCA family");
     if (batch_z < 1 || h->batch % batch_z != 0) return fail(RIPTRM_E_INVALID, "batch_z must divide batch (batch_z instances x batch/batch_z initial points)");
     CUDA_TRY(cudaSetDevice(h->device));
-    if (h->family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS) return columns_setup(h, Z, eps, where);
+    if (h->family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS || is_stiefel(h)) return columns_setup(h, Z, eps, where);
     const size_t bytes = (size_t)batch_z * h->n * h->n * sizeof(double);
     if (where == RIPTRM_DEVICE) {
         if (h->ownZ) free_dev(h->dZ);
@@ -1042,7 +1096,7 @@ extern "C" int riptrm_solve(riptrm_handle* h, const double* x0, const double* y0
     if (!h->have_opts) return fail(RIPTRM_E_STATE, "riptrm_set_options has not been called");
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (h->family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS) return columns_solve(h, x0, y0, x, y, summary, trace, where, st);
+    if (h->family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS || is_stiefel(h)) return columns_solve(h, x0, y0, x, y, summary, trace, where, st);
     const size_t B = h->batch;
     const size_t xb = B * h->vec_len * sizeof(double), yb = B * h->m * sizeof(double);
     const size_t sb = B * RIPTRM_SUMMARY_FIELDS * sizeof(double);
@@ -1107,7 +1161,7 @@ static int run_hook(riptrm_handle* h, int mode, const double* x, const double* y
     if (!h->have_problem) return fail(RIPTRM_E_STATE, "riptrm_set_<family> has not been called");
     if (mode == 2 && !h->have_opts) return fail(RIPTRM_E_STATE, "riptrm_set_options has not been called");
     CUDA_TRY(cudaSetDevice(h->device));
-    if (h->family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS) return columns_run(h, mode, x, y, mu, Delta, v, out, info, where, st);
+    if (h->family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS || is_stiefel(h)) return columns_run(h, mode, x, y, mu, Delta, v, out, info, where, st);
     const size_t B = h->batch;
     const size_t xb = B * h->vec_len * sizeof(double), yb = B * h->m * sizeof(double), ib = B * 4 * sizeof(double);
     SphereParams P{};

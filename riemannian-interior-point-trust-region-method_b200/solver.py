@@ -181,10 +181,13 @@ class ColumnsSolver:
     config 4; each column is a reference-exact Sphere problem, src/NonnegPCA/coordinator.py:37-95).
     X, Y, V are [n, p] arrays; host ndarrays are staged, torch CUDA tensors are used in place."""
 
+    FAMILY = _lib.FAMILY_NONNEGPCA_COLUMNS
+
     def __init__(self, Z, p, eps=0.0, device=0, option=None):
         n = Z.shape[0]
         self.n, self.p, self.device = n, p, device
-        self.handle = _Handle(_lib.FAMILY_NONNEGPCA_COLUMNS, n, p, n * p, 1, device)
+        self.runs = p if self.FAMILY == _lib.FAMILY_NONNEGPCA_COLUMNS else 1   # independent RIPTRM runs in the handle
+        self.handle = _Handle(self.FAMILY, n, p, n * p, 1, device)
         self.lib = self.handle.lib
         where = _lib.HOST if isinstance(Z, np.ndarray) else _lib.DEVICE
         if where == _lib.HOST:
@@ -225,10 +228,10 @@ class ColumnsSolver:
         if where == _lib.HOST:
             X, Y = (np.ascontiguousarray(a, dtype=np.float64) for a in (X, Y))
             out = np.empty((self.n, self.p)) if out is None else out
-            info = np.empty((self.p, 4)) if info is None else info
+            info = np.empty((self.runs, 4)) if info is None else info
         else:
             out = X.new_empty((self.n, self.p)) if out is None else out
-            info = X.new_empty((self.p, 4)) if info is None else info
+            info = X.new_empty((self.runs, 4)) if info is None else info
         _lib.check(self.lib.riptrm_tcg(self.handle.h, _lib.ptr(X), _lib.ptr(Y), float(mu), float(Delta),
                                        _lib.ptr(out), _lib.ptr(info), where, C.c_void_p(stream) if stream else None))
         return out, info
@@ -250,12 +253,12 @@ class ColumnsSolver:
         if where == _lib.HOST:
             X0, Y0 = (np.ascontiguousarray(a, dtype=np.float64) for a in (X0, Y0))
             X, Y = np.empty((self.n, self.p)), np.empty((self.n, self.p))
-            summary = np.empty((self.p, _lib.SUMMARY_FIELDS))
-            trace = np.full((self.p, cap, _lib.TRACE_FIELDS), np.nan) if per_outer_trace else None
+            summary = np.empty((self.runs, _lib.SUMMARY_FIELDS))
+            trace = np.full((self.runs, cap, _lib.TRACE_FIELDS), np.nan) if per_outer_trace else None
         else:
             X, Y = X0.new_empty((self.n, self.p)), X0.new_empty((self.n, self.p))
-            summary = X0.new_empty((self.p, _lib.SUMMARY_FIELDS))
-            trace = X0.new_full((self.p, cap, _lib.TRACE_FIELDS), float("nan")) if per_outer_trace else None
+            summary = X0.new_empty((self.runs, _lib.SUMMARY_FIELDS))
+            trace = X0.new_full((self.runs, cap, _lib.TRACE_FIELDS), float("nan")) if per_outer_trace else None
         _lib.check(self.lib.riptrm_solve(self.handle.h, _lib.ptr(X0), _lib.ptr(Y0), _lib.ptr(X), _lib.ptr(Y),
                                          _lib.ptr(summary), _lib.ptr(trace), where,
                                          C.c_void_p(stream) if stream else None))
@@ -275,6 +278,13 @@ class ColumnsSolver:
 
     def close(self):
         self.handle.close()
+
+
+class StiefelSolver(ColumnsSolver):
+    """NonnegPCA on Stiefel(n, p) with offset constraints X_ij + eps >= 0 (family STIEFEL: the Stiefel reading of BASELINE
+    config 4, SURVEY.md App. A.4): ONE RIPTRM run whose iterates are n x p matrices.  Same calls as `ColumnsSolver`;
+    `tcg` returns info [1, 4], `solve` returns summary [1, 16] and trace [1, capacity, 25]."""
+    FAMILY = _lib.FAMILY_NONNEGPCA_STIEFEL
 
 
 def columns_bench(n, p, dev, peak, launches_out, tcg_iters=40, reps=3):
@@ -471,6 +481,37 @@ class RIPTRM:
                                log=trace_to_log(trace[c, :rows], save_inner_iteration=save_inner),
                                ineqLagmult=np.array(Y[:, c]), eqLagmult=[]))
         return outs
+
+    def run_stiefel(self, Z, X0, Y0, eps=0.01):
+        """NonnegPCA on Stiefel(n, p) with X_ij + eps >= 0 (family STIEFEL): one run, `Output.x` is the n x p matrix,
+        `ineqLagmult` the n*p multipliers in row-major constraint order.  The log's `distance` column is NaN (pymanopt's
+        Stiefel has no dist())."""
+        option = self.option
+        _options.check_supported(option)
+        n, p = X0.shape
+        save_inner = bool(option["save_inner_iteration"])
+        ss = StiefelSolver(Z, p, eps=eps, device=self.device)
+        try:
+            cap = None
+            while True:
+                X, Y, summary, trace = ss.solve(X0, Y0, option, per_outer_trace=not save_inner,
+                                                per_inner_trace=save_inner, trace_capacity=cap)
+                need = int(np.max((summary.cpu().numpy() if hasattr(summary, "cpu") else summary)[:, _lib.SM["trace_rows"]]))
+                if need <= trace.shape[1]:
+                    break
+                cap = need
+            run_time = ss.kernel_ms * 1e-3
+        finally:
+            ss.close()
+        to_np = lambda a: a.cpu().numpy() if hasattr(a, "cpu") else np.asarray(a)
+        X, Y, summary, trace = to_np(X), to_np(Y), to_np(summary), to_np(trace)
+        self.last_summary = summary
+        opt = copy.copy(option)
+        opt["stoppingcriterion"] = _stop_message(summary[0], option, run_time)
+        rows = int(summary[0, _lib.SM["trace_rows"]])
+        return Output(name=self.name, x=np.array(X), option=opt,
+                      log=trace_to_log(trace[0, :rows], save_inner_iteration=save_inner),
+                      ineqLagmult=np.array(Y).reshape(-1), eqLagmult=[])
 
     def run_batch(self, problems, structures=None):
         """Solves many (instance, initialpoint) pairs of one family in one launch; returns one

@@ -53,3 +53,16 @@ def max_rel_diff(log_a, log_b, column, rows=None, floor=0.0):
         return 0.0
     den = np.maximum(np.abs(b[mask]), floor if floor > 0 else 1e-300)
     return float(np.max(np.abs(a[mask] - b[mask]) / den))
+
+
+def stiefel_start(n, p, seed):
+    """Feasible starting point of the Stiefel reading of config 4: nonnegative orthonormal
+    columns with disjoint supports (blocks of n // p rows, |rand| + 0.1, column-normalised)."""
+    rs = np.random.RandomState(seed)
+    X = np.zeros((n, p))
+    b = n // p
+    for c in range(p):
+        lo, hi = c * b, (n if c == p - 1 else (c + 1) * b)
+        X[lo:hi, c] = np.abs(rs.rand(hi - lo)) + 0.1
+        X[:, c] /= np.linalg.norm(X[:, c])
+    return X

@@ -1,0 +1,166 @@
+"""GPU parity of the STIEFEL family (BASELINE config 4 as written -- NonnegPCA, n x p iterates on Stiefel(n, p),
+offset constraints X_ij + eps >= 0) at sizes the oracle finishes in seconds: Hessian-vector hook,
+tCG hook and the whole solve against the NumPy oracle's matrix-form operators (checked against the per-constraint
+restatement in tests/test_oracle_stiefel.py), plus size-independent properties at a larger n."""
+import numpy as np
+import pytest
+
+from helpers import stiefel_start
+
+pytestmark = pytest.mark.gpu
+EPS = 0.01
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import riptrm_b200
+    return riptrm_b200
+
+
+def _instance(n, p, seed):
+    from oracle.problems import nonnegpca_generate_Z
+    Z, rs = nonnegpca_generate_Z(n, seed=seed)
+    X = stiefel_start(n, p, seed)
+    Y = 0.5 + rs.rand(n, p)
+    return Z, X, Y, rs
+
+
+def _oracle(Z, X, Y):
+    from oracle.problems import NonnegPCAStiefelProblem
+    return NonnegPCAStiefelProblem(Z, X, Y.reshape(-1), eps=EPS, closed_form=True)
+
+
+def _hw(pb, X, Y, mu, V, emb=False):
+    from oracle import riptrm_oracle as O
+    y = Y.reshape(-1)
+    s = O.slack(pb, X)
+    return O.hess_lagrangian(pb, X, y, V) + O.G_apply(pb, X, (y * O.Gadj_apply(pb, X, V, emb)) / s)
+
+
+@pytest.mark.parametrize("n,p,emb", [(200, 4, False), (333, 10, False), (150, 13, False), (96, 2, True), (640, 16, False),
+                                     (1000, 10, True), (64, 1, False)])
+def test_hessvec_matches_oracle(rb, n, p, emb):
+    Z, X, Y, rs = _instance(n, p, seed=n + p)
+    pb = _oracle(Z, X, Y)
+    V = pb.manifold.projection(X, rs.randn(n, p))
+    opt = rb.options.default_option()
+    opt.update(TRS_solver="tCG", second_order_stationarity=False, is_euclidean_embedded=emb)
+    ss = rb.StiefelSolver(Z, p, eps=EPS, option=opt)
+    out = ss.hessvec(X, Y, 0.05, V)
+    assert ss.matvec_passes == 2
+    ref = _hw(pb, X, Y, 0.05, V, emb)
+    assert np.max(np.abs(out - ref)) < 1e-11 * max(1.0, np.max(np.abs(ref)))
+    # the product is a tangent vector: X'H + H'X = 0
+    assert np.max(np.abs(X.T @ out + out.T @ X)) < 1e-10 * max(1.0, np.max(np.abs(ref)))
+    ss.close()
+
+
+@pytest.mark.parametrize("n,p,Delta", [(120, 3, 0.2), (120, 3, 50.0), (400, 10, 0.5), (257, 4, 2.0), (300, 16, 0.7)])
+def test_tcg_matches_oracle_tcg(rb, n, p, Delta):
+    """Iteration count, stop reason and eta of the device tCG equal the oracle's Steihaug-Toint tCG (RIPTRM.py:41-216)
+    on the same operator."""
+    from oracle import riptrm_oracle as O
+    Z, X, Y, rs = _instance(n, p, seed=7 * n + p)
+    mu = 0.1
+    pb = _oracle(Z, X, Y)
+    man = pb.manifold
+    opt = rb.options.default_option()
+    opt.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=1)
+    ss = rb.StiefelSolver(Z, p, eps=EPS, option=opt)
+    eta, info = ss.tcg(X, Y, mu, Delta)
+    grad = pb.riemannian_gradient(X) - O.G_apply(pb, X, mu / O.slack(pb, X))
+    e_ref, _, j, stop = O.steihaug_tcg(man, lambda _x, v: _hw(pb, X, Y, mu, v), X, grad, Delta, 1, 0.1, 1, man.dim,
+                                       lambda _x, v: v)
+    assert int(info[0, 0]) == j + 1, (info[0], j + 1, stop)
+    assert O.TCG_STOPS[int(info[0, 1])] == stop
+    assert np.max(np.abs(eta - e_ref)) < 1e-8 * max(1e-3, np.max(np.abs(e_ref)))
+    assert abs(info[0, 2] - np.linalg.norm(e_ref)) < 1e-8 * max(1e-3, np.linalg.norm(e_ref))
+    assert np.max(np.abs(X.T @ eta + eta.T @ X)) < 1e-10
+    ss.close()
+
+
+def test_whole_solve_matches_the_oracle(rb):
+    """riptrm_solve on the STIEFEL family against the NumPy oracle (n = 40, p = 3): the per-trust-region-iteration log
+    agrees row by row (statuses, tCG stop reasons, radii, costs) through the first outer iterations, every outer
+    iteration is reached with all inner runs converged, and the objective / iterate / multipliers after 30 outer
+    iterations agree to 1e-8."""
+    from oracle import riptrm_oracle as O
+    from oracle.problems import NonnegPCAStiefelProblem
+    n, p = 40, 3
+    Z, X0, _, rs = _instance(n, p, seed=1)
+    Y0 = np.ones((n, p))
+    opt = rb.options.default_option()
+    opt.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=30, tolresid=0, maxtime=1e9, inner_maxiter=1000)
+    out = rb.RIPTRM(opt).run_stiefel(Z, X0, Y0, eps=EPS)
+    o = O.OracleRIPTRM({"maxiter": 30, "tolresid": 0, "inner_maxiter": 1000, "manviofun": NonnegPCAStiefelProblem.manviofun})
+    ref = o.run(_oracle(Z, X0, Y0))
+    L, G = out.log, ref.log
+    assert out.x.shape == (n, p) and out.ineqLagmult.shape == (n * p,)
+    first = next((i for i, (a, b, c, d) in enumerate(zip(L["inner_status"], G["inner_status"], L["dxtype"], G["dxtype"]))
+                  if (a, c) != (b, d)), len(G["iteration"]))
+    assert first > 30, f"discrete trace diverges at row {first}"
+    w = min(first, 30)
+    rel = lambda k: np.max(np.abs(np.array(L[k][1:w], float) - np.array(G[k][1:w], float)) / np.maximum(1e-300, np.abs(np.array(G[k][1:w], float))))
+    assert rel("TR_radius") < 1e-9 and rel("cost") < 1e-8 and rel("normdx") < 1e-7 and rel("residual") < 1e-6
+    assert L["tcg_iters"][1:w] == [int(v) for v in G["tcg_iters"][1:w]]
+    conv = lambda lg: np.array([c for c, st in zip(lg["cost"], lg["inner_status"]) if st == "converged"])
+    a, b = conv(L), conv(G)
+    assert len(a) == len(b) == 30
+    assert abs(a[-1] - b[-1]) < 1e-8 * abs(b[-1])
+    assert np.max(np.abs(out.x - ref.x)) < 1e-7
+    assert L["residual"][-1] < 1e-9 and G["residual"][-1] < 1e-9
+    assert np.max(np.abs(out.x.T @ out.x - np.eye(p))) < 1e-13 and out.x.min() > -EPS
+    assert L["manviolation"][-1] < 1e-13 and np.isnan(L["distance"][-1])
+
+
+def test_per_outer_trace_and_rollback_path(rb):
+    """save_inner_iteration=False gives one row per outer iteration; inner_maxiter=2 forces the rollback branch
+    (RIPTRM.py:835-842): the run stays finite and ends on maxiter."""
+    n, p = 64, 4
+    Z, X0, _, _ = _instance(n, p, seed=3)
+    Y0 = np.ones((n, p))
+    opt = rb.options.default_option()
+    opt.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=5, tolresid=0, maxtime=1e9, inner_maxiter=2,
+               save_inner_iteration=False)
+    solver = rb.RIPTRM(opt)
+    out = solver.run_stiefel(Z, X0, Y0, eps=EPS)
+    assert out.log["iteration"] == [0, 1, 2, 3, 4, 5]
+    assert all(st == "max-iter-exceeded" for st in out.log["inner_status"][1:])
+    assert np.array_equal(out.x, X0)          # every inner run was rolled back to its start
+    assert "Max iteration count reached" in out.option["stoppingcriterion"]
+
+
+def test_p1_stiefel_is_the_sphere(rb):
+    """Stiefel(n, 1) = Sphere(n): with eps = 0 the STIEFEL family's Hessian-vector product equals the COLUMNS family's."""
+    n = 500
+    from oracle.problems import nonnegpca_generate_Z
+    Z, rs = nonnegpca_generate_Z(n, seed=21)
+    x = np.abs(rs.rand(n, 1))
+    x /= np.linalg.norm(x)
+    y = 0.5 + rs.rand(n, 1)
+    v = rs.randn(n, 1)
+    v -= x * float(x.T @ v)
+    ss, cs = rb.StiefelSolver(Z, 1, eps=0.0), rb.ColumnsSolver(Z, 1, eps=0.0)
+    a, b = ss.hessvec(x, y, 0.03, v), cs.hessvec(x, y, 0.03, v)
+    assert np.max(np.abs(a - b)) < 1e-12 * np.max(np.abs(b))
+    ss.close()
+    cs.close()
+
+
+def test_fullsize_properties(rb):
+    """n = 8192, p = 10 (DMMA consumers, every SM streaming): Hw is linear, self-adjoint on the tangent space, maps into
+    the tangent space, and is bit-identical run to run."""
+    n, p = 8192, 10
+    Z, X, Y, rs = _instance(n, p, seed=13)
+    proj = lambda V: V - X @ (0.5 * (X.T @ V + V.T @ X))
+    U, V = proj(rs.randn(n, p)), proj(rs.randn(n, p))
+    ss = rb.StiefelSolver(Z, p, eps=EPS)
+    HU, HV = ss.hessvec(X, Y, 0.01, U), ss.hessvec(X, Y, 0.01, V)
+    HUV = ss.hessvec(X, Y, 0.01, U + 2.0 * V)
+    scale = np.max(np.abs(HUV))
+    assert np.max(np.abs(HUV - (HU + 2.0 * HV))) < 1e-11 * scale
+    uhv, vhu = np.sum(U * HV), np.sum(V * HU)
+    assert abs(uhv - vhu) < 1e-9 * abs(uhv)
+    assert np.max(np.abs(X.T @ HU + HU.T @ X)) < 1e-10 * scale
+    assert np.array_equal(ss.hessvec(X, Y, 0.01, U), HU)
+    ss.close()
