@@ -33,7 +33,8 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [
+    extra = os.environ.get("RIPTRM_NVCC_EXTRA", "").split()   # e.g. -DRIPTRM_COLUMNS_TIMING (diagnostic builds)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [
         os.path.join(CSRC, s) for s in SOURCES]
     subprocess.run(cmd, check=True)
     return LIB

@@ -55,19 +55,42 @@ __device__ __forceinline__ void breduce(const Params& prm, Smem<P>& sm, const do
     }
 }
 
-// after a grid barrier: tot[q * P + c] = sum (q < first_min) or minimum over the CTAs, in CTA order
+// after a grid barrier: tot[q * P + c] = sum (q < first_min) or minimum over the CTAs.  A warp takes 32 consecutive
+// values (coalesced loads of one CTA's partials) over a contiguous range of CTAs, sixteen loads in flight, added in CTA
+// order; the ranges' partial results go through shared memory and are added in range order.
 template <int P>
-__device__ __forceinline__ void gather_tot(const Params& prm, double* tot, int buf, int K, int first_min) {
-    const int G = gridDim.x;
-    for (int k = threadIdx.x; k < K * P; k += NT) {
-        const double* src = prm.dot_part + (size_t)buf * G * DOT_STRIDE + k;
-        double s = src[0];
-        if (k >= first_min * P) {
-#pragma unroll 4
-            for (int g = 1; g < G; ++g) s = fmin(s, src[(size_t)g * DOT_STRIDE]);
-        } else {
-#pragma unroll 4
-            for (int g = 1; g < G; ++g) s = s + src[(size_t)g * DOT_STRIDE];
+__device__ __forceinline__ void gather_tot(const Params& prm, Smem<P>& sm, double* tot, int buf, int K, int first_min) {
+    constexpr int NW = NT / 32;
+    const int G = gridDim.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nval = K * P, nkb = (nval + 31) >> 5;
+    const int gsplit = (nkb >= NW) ? 1 : NW / nkb;
+    double* scratch = &sm.redv[0][0];  // [gsplit][nkb * 32]
+    for (int item = warp; item < nkb * gsplit; item += NW) {
+        const int kb = item % nkb, gs = item / nkb;
+        const int k = kb * 32 + lane;
+        const int g_lo = (int)((long long)G * gs / gsplit), g_hi = (int)((long long)G * (gs + 1) / gsplit);
+        const bool is_min = k >= first_min * P;
+        const double neutral = is_min ? CUDART_INF : 0.0;
+        double s = neutral;
+        if (k < nval) {
+            const double* src = prm.dot_part + (size_t)buf * G * DOT_STRIDE + k;
+            for (int g0 = g_lo; g0 < g_hi; g0 += 16) {
+                double v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) v[u] = (g0 + u < g_hi) ? src[(size_t)(g0 + u) * DOT_STRIDE] : neutral;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) s = is_min ? fmin(s, v[u]) : (s + v[u]);
+            }
+        }
+        scratch[gs * (nkb * 32) + k] = s;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nval; k += NT) {
+        const bool is_min = k >= first_min * P;
+        double s = scratch[k];
+        for (int gs = 1; gs < gsplit; ++gs) {
+            const double t = scratch[gs * (nkb * 32) + k];
+            s = is_min ? fmin(s, t) : (s + t);
         }
         tot[k] = s;
     }
@@ -202,7 +225,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_kernel(Params prm) {
         breduce<P, 3 * P, 0>(prm, sm, part, buf);
     }
     grid.sync();
-    gather_tot<P>(prm, tot, buf, 3 * P, 3 * P);
+    gather_tot<P>(prm, sm, tot, buf, 3 * P, 3 * P);
     buf ^= 1;
     if (tid < P * P) {
         const int a = tid / P, c = tid - a * P;
@@ -254,10 +277,21 @@ __global__ void __launch_bounds__(NT, 1) stiefel_kernel(Params prm) {
     }
 
     for (int j = 0; j < maxinner; ++j) {
+#ifdef RIPTRM_COLUMNS_TIMING  // build with -DRIPTRM_COLUMNS_TIMING: CTA 0 prints the phase times of iteration 5
+        const bool dbg = g == 0 && tid == 0 && j == 5;
+        uint64_t tdbg[12];
+#define TDBG(i) if (dbg) tdbg[i] = global_timer_ns()
+#else
+#define TDBG(i)
+#endif
+        TDBG(0);
         stream_pass<P>(prm, sm, pipe);
+        TDBG(1);
         grid.sync();
+        TDBG(2);
         // X'delta of the direction just streamed (partials written before the barrier that preceded the pass)
-        gather_tot<P>(prm, tot, buf, P + 1, P + 1);
+        gather_tot<P>(prm, sm, tot, buf, P + 1, P + 1);
+        TDBG(3);
         buf ^= 1;
         if (tid < P * P) {
             const int a = tid / P, c = tid - a * P;
@@ -295,10 +329,14 @@ __global__ void __launch_bounds__(NT, 1) stiefel_kernel(Params prm) {
                 xt_acc<P>(part, xr, w);
                 part[P] = fma(v, w, part[P]);
             }
+            TDBG(4);
             breduce<P, P + 1, 0>(prm, sm, part, buf);
         }
+        TDBG(5);
         grid.sync();
-        gather_tot<P>(prm, tot, buf, P + 1, P + 1);
+        TDBG(6);
+        gather_tot<P>(prm, sm, tot, buf, P + 1, P + 1);
+        TDBG(7);
         buf ^= 1;
         if (tid < P * P) {
             const int a = tid / P, c = tid - a * P;
@@ -361,8 +399,10 @@ __global__ void __launch_bounds__(NT, 1) stiefel_kernel(Params prm) {
             }
             breduce<P, P + 3, 0>(prm, sm, part, buf);
         }
+        TDBG(8);
         grid.sync();
-        gather_tot<P>(prm, tot, buf, P + 3, P + 3);
+        gather_tot<P>(prm, sm, tot, buf, P + 3, P + 3);
+        TDBG(9);
         buf ^= 1;
         if (tid == 0) {
             TcgState& s = ts;
@@ -435,7 +475,22 @@ __global__ void __launch_bounds__(NT, 1) stiefel_kernel(Params prm) {
         __syncthreads();
         const bool finished = ts.done == 1;
         fence_proxy_async();
+        TDBG(10);
         grid.sync();
+#ifdef RIPTRM_COLUMNS_TIMING
+        if (dbg) {
+            tdbg[11] = global_timer_ns();
+            printf("stiefel tCG it 5 (CTA 0, ns): stream %llu | sync %llu | gather B %llu | M1 body %llu | M1 reduce %llu | sync %llu | "
+                   "gather %llu | M2 %llu | sync+gather %llu | M3 %llu | sync %llu | total %llu\n",
+                   (unsigned long long)(tdbg[1] - tdbg[0]), (unsigned long long)(tdbg[2] - tdbg[1]),
+                   (unsigned long long)(tdbg[3] - tdbg[2]), (unsigned long long)(tdbg[4] - tdbg[3]),
+                   (unsigned long long)(tdbg[5] - tdbg[4]), (unsigned long long)(tdbg[6] - tdbg[5]),
+                   (unsigned long long)(tdbg[7] - tdbg[6]), (unsigned long long)(tdbg[8] - tdbg[7]),
+                   (unsigned long long)(tdbg[9] - tdbg[8]), (unsigned long long)(tdbg[10] - tdbg[9]),
+                   (unsigned long long)(tdbg[11] - tdbg[10]), (unsigned long long)(tdbg[11] - tdbg[0]));
+        }
+#endif
+#undef TDBG
         if (finished) break;
     }
 
@@ -448,7 +503,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_kernel(Params prm) {
         }
         breduce<P, 1, 0>(prm, sm, part, buf);
         grid.sync();
-        gather_tot<P>(prm, tot, buf, 1, 1);
+        gather_tot<P>(prm, sm, tot, buf, 1, 1);
         if (g == 0 && tid == 0) {
             if (prm.solve) {
                 prm.colstate[CS_TCG_ITERS] = (double)ts.iters;
@@ -548,7 +603,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
             breduce<P, 1, 0>(prm, sm, part, buf);
         }
         grid.sync();
-        gather_tot<P>(prm, tot, buf, 1, 1);
+        gather_tot<P>(prm, sm, tot, buf, 1, 1);
         buf ^= 1;
         if (tid == 0) {
             PostState& s = ps;
@@ -586,7 +641,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
             breduce<P, 2 * P + 1, 0>(prm, sm, part, buf);
         }
         grid.sync();
-        gather_tot<P>(prm, tot, buf, 2 * P + 1, 2 * P + 1);
+        gather_tot<P>(prm, sm, tot, buf, 2 * P + 1, 2 * P + 1);
         buf ^= 1;
         if (tid < P * P) {
             const int a = tid / P, c = tid - a * P;
@@ -673,7 +728,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
             breduce<P, 2 * P + 3, 2>(prm, sm, part, buf);
         }
         grid.sync();
-        gather_tot<P>(prm, tot, buf, 2 * P + 3, 2 * P + 1);
+        gather_tot<P>(prm, sm, tot, buf, 2 * P + 3, 2 * P + 1);
         buf ^= 1;
         if (tid < P * P) {
             const int a = tid / P, c = tid - a * P;
@@ -706,7 +761,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
             breduce<P, 1, 0>(prm, sm, part, buf);
         }
         grid.sync();
-        gather_tot<P>(prm, tot, buf, 1, 1);
+        gather_tot<P>(prm, sm, tot, buf, 1, 1);
         buf ^= 1;
         if (tid == 0) {
             PostState& s = ps;
@@ -730,7 +785,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
             }
             fence_proxy_async();
             grid.sync();
-            gather_tot<P>(prm, tot, buf, 2, 2);
+            gather_tot<P>(prm, sm, tot, buf, 2, 2);
             buf ^= 1;
             if (tid == 0) {
                 ps.pl_cur = colsum<P>(tot, 0);
@@ -761,7 +816,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
                 breduce<P, P + 2, 0>(prm, sm, part, buf);
             }
             grid.sync();
-            gather_tot<P>(prm, tot, buf, P + 2, P + 2);
+            gather_tot<P>(prm, sm, tot, buf, P + 2, P + 2);
             buf ^= 1;
             if (tid < P * P) {
                 const int a = tid / P, c = tid - a * P;
@@ -846,7 +901,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
             breduce<P, 1, 0>(prm, sm, part, buf);
         }
         grid.sync();
-        gather_tot<P>(prm, tot, buf, 1, 1);
+        gather_tot<P>(prm, sm, tot, buf, 1, 1);
         buf ^= 1;
         if (tid == 0) {
             PostState& s = ps;
@@ -904,7 +959,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
             breduce<P, P + 6, 2>(prm, sm, part, buf, 2 * P);
         }
         grid.sync();
-        gather_tot<P>(prm, tot, buf, 3 * P + 6, 3 * P + 4);
+        gather_tot<P>(prm, sm, tot, buf, 3 * P + 6, 3 * P + 4);
         buf ^= 1;
         if (tid < P * P) {
             const int a = tid / P, c = tid - a * P;
@@ -942,7 +997,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
             breduce<P, 1, 0>(prm, sm, part, buf);
         }
         grid.sync();
-        gather_tot<P>(prm, tot, buf, 1, 1);
+        gather_tot<P>(prm, sm, tot, buf, 1, 1);
         buf ^= 1;
         if (tid == 0) {
             PostState& s = ps;

@@ -309,6 +309,7 @@ def columns_bench(n, p, dev, peak, launches_out, tcg_iters=40, reps=3):
     option = _options.default_option()
     option.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=1)
     solver = ColumnsSolver(Z, p, device=dev.index or 0, option=option)
+    stiefel = _stiefel_bench(Z, n, p, dev, gen, option, tcg_iters, reps, launches_out) if p >= 2 else None
     del Z
     o, keep = _options.to_c_options(option, 0, 0)
     o.tcg_maxinner = tcg_iters   # rate protocol: a fixed number of Hessian-vector
@@ -359,7 +360,59 @@ def columns_bench(n, p, dev, peak, launches_out, tcg_iters=40, reps=3):
                               "inner_iters": float(sm[:, _lib.SM["inner_iters"]].sum()),
                               "tcg_iters": float(sm[:, _lib.SM["tcg_iters"]].sum()),
                               "finite": bool(np.isfinite(sm).all())}}
+    if stiefel is not None:
+        extra["stiefel"] = stiefel
     return roofline, extra
+
+
+def _stiefel_bench(Z, n, p, dev, gen, option, tcg_iters, reps, launches_out, eps=0.01):
+    """The same rate protocol on the STIEFEL family (config 4 as written: one run with n x p iterates on Stiefel(n, p),
+    X_ij + eps >= 0): tCG capped at `tcg_iters` Hessian-vector products from the disjoint-support feasible start."""
+    import torch
+    X = torch.zeros((n, p), dtype=torch.float64, device=dev)
+    b = n // p
+    for c in range(p):
+        lo, hi = c * b, (n if c == p - 1 else (c + 1) * b)
+        X[lo:hi, c] = torch.rand(hi - lo, generator=gen, dtype=torch.float64, device=dev) + 0.1
+    X = (X / X.norm(dim=0, keepdim=True)).contiguous()
+    Y = torch.ones((n, p), dtype=torch.float64, device=dev)
+    solver = StiefelSolver(Z, p, eps=eps, device=dev.index or 0, option=option)
+    o, keep = _options.to_c_options(option, 0, 0)
+    o.tcg_maxinner = tcg_iters
+    o.tcg_kappa = 0.0
+    _lib.check(solver.lib.riptrm_set_options(solver.handle.h, C.byref(o)))
+    stream = torch.cuda.current_stream().cuda_stream
+    eta, info = solver.tcg(X, Y, 0.1, 1e6, stream=stream)
+    torch.cuda.synchronize()
+    l0 = solver.launches
+    times, passes = [], []
+    for _ in range(reps):
+        p0 = solver.matvec_passes
+        solver.tcg(X, Y, 0.1, 1e6, out=eta, info=info, stream=stream)
+        torch.cuda.synchronize()
+        times.append(solver.kernel_ms)
+        passes.append(solver.matvec_passes - p0)
+    launches_out.append(solver.launches - l0)
+    sopt = _options.default_option()
+    sopt.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=2, inner_maxiter=5, tolresid=0, maxtime=1e9)
+    l1, p0 = solver.launches, solver.matvec_passes
+    Xs, Ys, sm, _ = solver.solve(X, Y, sopt, stream=stream)
+    torch.cuda.synchronize()
+    solve_ms, solve_passes = solver.kernel_ms, solver.matvec_passes - p0
+    launches_out.append(solver.launches - l1)
+    sm = sm.cpu().numpy()
+    orth = float((Xs.T @ Xs - torch.eye(p, dtype=torch.float64, device=dev)).abs().max())
+    solver.close()
+    alg = 8.0 * n * n + 40.0 * n * p
+    ms = float(np.mean(times))
+    return {"kernel": f"stiefel_kernel<{solver.p if solver.p in (4, 10, 16) else (4 if solver.p <= 4 else (10 if solver.p <= 10 else 16))},2>",
+            "eps": eps, "tcg_launch_ms": ms, "matvec_passes_per_launch": float(np.mean(passes)),
+            "ms_per_hessvec": ms / float(np.mean(passes)), "hessvec_hbm_gbs": alg * float(np.mean(passes)) / (ms * 1e-3) / 1e9,
+            "tcg_iters_per_sec": float(info[0, 0]) / (ms * 1e-3), "tcg_stop": int(info[0, 1]),
+            "capped_solve": {"protocol": "maxiter=2, inner_maxiter=5", "ms": solve_ms, "matvec_passes": int(solve_passes),
+                             "hbm_gbs": alg * solve_passes / (solve_ms * 1e-3) / 1e9,
+                             "inner_iters": float(sm[0, _lib.SM["inner_iters"]]), "tcg_iters": float(sm[0, _lib.SM["tcg_iters"]]),
+                             "orthonormality": orth, "finite": bool(np.isfinite(sm).all())}}
 
 
 # ---------------------------------------------------------------------------------------------
