@@ -208,13 +208,14 @@ int riptrm_solve(riptrm_handle* h, const double* x0, const double* y0, double* x
 int riptrm_hessvec(riptrm_handle* h, const double* x, const double* y, double mu, const double* v,
                    double* out, int where, void* stream);
 /* One tCG solve at (x, y, mu, Delta) (RIPTRM.py:41-216 via :445-452):
- * eta [batch][n*p], info [batch][4] = {j+1, stop reason, ||eta||, <eta,Hw eta> model value} */
+ * eta [batch][n*p], info [batch][4] = {j+1, stop reason, ||eta||, <eta,Hw eta> model value}
+ * (COLUMNS: info [p][4], one tCG per column; STIEFEL: info [1][4]) */
 int riptrm_tcg(riptrm_handle* h, const double* x, const double* y, double mu, double Delta, double* eta,
                double* info, int where, void* stream);
 
 /* number of kernel launches the handle has issued (for bench.py's gpu_launches) */
 int64_t riptrm_launch_count(const riptrm_handle* h);
-/* COLUMNS family: number of full S.V streaming passes (one per Hessian-vector product, plus the S.X of the
+/* COLUMNS and STIEFEL families: number of full S.V streaming passes (one per Hessian-vector product, plus the S.X of the
  * point cache) the handle has executed since riptrm_set_nonnegpca -- the unit of the HBM roofline */
 int64_t riptrm_matvec_passes(riptrm_handle* h);
 /* milliseconds the last riptrm_solve / hessvec / tcg kernel took on its stream (CUDA events
