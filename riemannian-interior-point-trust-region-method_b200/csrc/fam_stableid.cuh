@@ -135,32 +135,38 @@ struct StableIdFam {
         slot(c, s)[lane_id()] = a;
         __syncwarp();
     }
-    // op(A) op(B) for d x d lane matrices
-    static __device__ __forceinline__ LM mul(const Ctx& c, LM a, LM b, bool tA = false, bool tB = false) {
-        put(c, 0, a);
-        put(c, 1, b);
-        const int l = lane_id(), d = c.d;
+    // op(A) op(B) for d x d lane matrices.  Out of line (see smallmat.cuh): called from ~150 sites of the solve.
+    static __device__ __noinline__ LM mul_impl(double* sc, int d, LM a, LM b, bool tA, bool tB) {
+        const int l = lane_id();
+        sc[l] = a;
+        sc[32 + l] = b;
+        __syncwarp();
         double s = 0.0;
-        if (l < c.dd) {
+        if (l < d * d) {
             const int i = l / d, j = l - i * d;
-            const double* A = slot(c, 0);
-            const double* B = slot(c, 1);
+            const double* A = sc;
+            const double* B = sc + 32;
             for (int k = 0; k < d; ++k) s = fma(tA ? A[k * d + i] : A[i * d + k], tB ? B[j * d + k] : B[k * d + j], s);
         }
         __syncwarp();
         return s;
     }
-    static __device__ __forceinline__ LM transpose(const Ctx& c, LM a) {
-        put(c, 0, a);
-        const int l = lane_id(), d = c.d;
+    static __device__ __forceinline__ LM mul(const Ctx& c, LM a, LM b, bool tA = false, bool tB = false) {
+        return mul_impl(c.sc, c.d, a, b, tA, tB);
+    }
+    static __device__ __noinline__ LM transpose_impl(double* sc, int d, LM a) {
+        const int l = lane_id();
+        sc[l] = a;
+        __syncwarp();
         double r = 0.0;
-        if (l < c.dd) {
+        if (l < d * d) {
             const int i = l / d, j = l - i * d;
-            r = slot(c, 0)[j * d + i];
+            r = sc[j * d + i];
         }
         __syncwarp();
         return r;
     }
+    static __device__ __forceinline__ LM transpose(const Ctx& c, LM a) { return transpose_impl(c.sc, c.d, a); }
     static __device__ __forceinline__ LM symm(const Ctx& c, LM a) { return 0.5 * (a + transpose(c, a)); }
     static __device__ __forceinline__ LM skew(const Ctx& c, LM a) { return 0.5 * (a - transpose(c, a)); }
     static __device__ __forceinline__ LM inverse(const Ctx& c, LM a, bool& ok) {
@@ -170,29 +176,35 @@ struct StableIdFam {
         __syncwarp();
         return r;
     }
-    // sum_i w_i coef_i E_{r_i c_i} (+ base) as a lane matrix; contributions added in constraint order
-    static __device__ __forceinline__ LM scatter(const Ctx& c, const CVec& w, const CVec& coef, LM base) {
-        double* P = slot(c, 4);
-        double* wc = slot(c, 5);
-        int* rc = reinterpret_cast<int*>(slot(c, 6));
-        P[lane_id()] = base;
-        wc[lane_id()] = (lane_id() < c.m) ? w.v[0] * coef.v[0] : 0.0;
-        rc[lane_id()] = c.rc;
+    // sum_i wc_i E_{r_i c_i} (+ base) as a lane matrix; contributions added in constraint order
+    static __device__ __noinline__ LM scatter_impl(double* sc, int m, int dd, int my_rc, double my_wc, LM base) {
+        double* P = sc + 32 * 4;
+        double* wc = sc + 32 * 5;
+        int* rc = reinterpret_cast<int*>(sc + 32 * 6);
+        const int l = lane_id();
+        P[l] = base;
+        wc[l] = (l < m) ? my_wc : 0.0;
+        rc[l] = my_rc;
         __syncwarp();
-        if (lane_id() == 0)
-            for (int i = 0; i < c.m; ++i) P[rc[i]] = P[rc[i]] + wc[i];
+        if (l == 0)
+            for (int i = 0; i < m; ++i) P[rc[i]] = P[rc[i]] + wc[i];
         __syncwarp();
-        const double r = on(c) ? P[lane_id()] : 0.0;
+        const double r = (l < dd) ? P[l] : 0.0;
         __syncwarp();
         return r;
+    }
+    static __device__ __forceinline__ LM scatter(const Ctx& c, const CVec& w, const CVec& coef, LM base) {
+        return scatter_impl(c.sc, c.m, c.dd, c.rc, w.v[0] * coef.v[0], base);
     }
     // value of a lane matrix at this lane's constraint entry (r_i, c_i)
-    static __device__ __forceinline__ double at_constraint(const Ctx& c, LM a) {
-        put(c, 0, a);
-        const double r = (lane_id() < c.m) ? slot(c, 0)[c.rc] : 0.0;
+    static __device__ __noinline__ double at_constraint_impl(double* sc, int m, int my_rc, LM a) {
+        sc[lane_id()] = a;
+        __syncwarp();
+        const double r = (lane_id() < m) ? sc[my_rc] : 0.0;
         __syncwarp();
         return r;
     }
+    static __device__ __forceinline__ double at_constraint(const Ctx& c, LM a) { return at_constraint_impl(c.sc, c.m, c.rc, a); }
 
     // Euclidean -> Riemannian gradient, componentwise
     static __device__ __forceinline__ Vec egrad2rgrad(const Ctx& c, const Pt& pt, LM egJ, LM egR, LM egQ) {
@@ -267,6 +279,8 @@ struct StableIdFam {
     }
 
     // <a, b>_x = <aJ, bJ> + tr(R^-1 aR R^-1 bR) + tr(Q^-1 aQ Q^-1 bQ): per-lane partial
+    // (taking this and the gradient conversions out of line as well costs registers -- 12 instead of 16 warps per SM --
+    // and was slower: 442 vs 367 ms for the 2048-pair sweep)
     static __device__ __forceinline__ double inner_partial(const Ctx& c, const Pt& pt, const Vec& a, const Vec& b) {
         const LM tR = mul(c, mul(c, pt.Rinv, a.v[1]), pt.Rinv);
         const LM tQ = mul(c, mul(c, pt.Qinv, a.v[2]), pt.Qinv);

@@ -938,7 +938,7 @@ struct SmallParams {
 };
 
 template <class F, int MODE>
-__global__ void __launch_bounds__(32) small_kernel(SmallParams P, DevOpts o, int* counter) {
+__global__ void __launch_bounds__(32, 16) small_kernel(SmallParams P, DevOpts o, int* counter) {  // <= 128 registers: 16 warps per SM
     extern __shared__ __align__(16) double smem[];
     typename F::Ctx ctx = F::make_ctx(P, o, smem);
     const int lane = lane_id();
@@ -988,7 +988,12 @@ static int launch_small(riptrm_handle* h, const SmallParams& P, const DevOpts& o
     auto kern = small_kernel<F, MODE>;
     const size_t smem = (size_t)F::smem_doubles(P.n, P.N) * sizeof(double);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = h->num_sms * 8;
+    // one warp per CTA, as many CTAs per SM as registers / shared memory allow (the warps are latency-bound)
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+    if (per_sm < 1) return fail(RIPTRM_E_UNSUPPORTED, "small-family kernel does not fit on an SM");
+    if (const char* e = getenv("RIPTRM_SMALL_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));  // diagnostic
+    int grid = h->num_sms * per_sm;
     if (grid > h->batch) grid = h->batch;
     CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
     CUDA_TRY(cudaEventRecord(h->ev0, st));

@@ -2,6 +2,9 @@
 // matrices live row-major in a warp's shared-memory scratch, the 32 lanes split the output entries, every
 // entry is a serial (fixed-order) sum, and every routine ends with __syncwarp().  Sizes are <= 5 x 5 here:
 // latency, not throughput, is what matters and determinism is free.
+// The routines are NOT inlined: the whole-solve kernels call them from hundreds of sites, and with everything inlined
+// the StableIdentification kernel was 1 MB of SASS whose warps, each at a different place, waited on instruction
+// fetch 83 % of the time (profiles/r01k_stableid_*).
 #pragma once
 #include "common.cuh"
 
@@ -9,7 +12,7 @@ namespace riptrm {
 namespace sm {
 
 // C[m x n] = op(A) * op(B); op(A) is m x k (A stored k x m when tA), op(B) is k x n (B stored n x k when tB)
-__device__ __forceinline__ void mm(double* C, const double* A, const double* B, int m, int k, int n, bool tA = false,
+static __device__ __noinline__ void mm(double* C, const double* A, const double* B, int m, int k, int n, bool tA = false,
                                    bool tB = false) {
     for (int e = lane_id(); e < m * n; e += 32) {
         const int i = e / n, j = e - i * n;
@@ -42,7 +45,7 @@ __device__ __forceinline__ void sym(double* C, const double* A, int n, double si
 // Cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (n <= 5), executed redundantly by every lane on
 // private copies: A = V diag(w) V'.  Returns false if a non-finite entry appears.
 template <int NMAX>
-__device__ __forceinline__ bool jacobi_eig(const double* Ain, int n, double (&w)[NMAX], double (&V)[NMAX][NMAX]) {
+__device__ __noinline__ bool jacobi_eig(const double* Ain, int n, double (&w)[NMAX], double (&V)[NMAX][NMAX]) {
     double A[NMAX][NMAX];
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) {
@@ -88,7 +91,7 @@ __device__ __forceinline__ bool jacobi_eig(const double* Ain, int n, double (&w)
 // In-place inverse of an n x n matrix (n <= 5) by Gauss-Jordan with partial pivoting, redundantly per lane on a
 // private copy, result written back by lane 0.  Returns false when singular / non-finite.
 template <int NMAX>
-__device__ __forceinline__ bool inverse(double* Ainv, const double* Ain, int n) {
+__device__ __noinline__ bool inverse(double* Ainv, const double* Ain, int n) {
     double M[NMAX][2 * NMAX];
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) {
@@ -133,7 +136,7 @@ __device__ __forceinline__ bool inverse(double* Ainv, const double* Ain, int n) 
 
 // true iff the symmetric n x n matrix is positive definite (Cholesky succeeds), redundantly per lane
 template <int NMAX>
-__device__ __forceinline__ bool is_spd(const double* Ain, int n) {
+__device__ __noinline__ bool is_spd(const double* Ain, int n) {
     double L[NMAX][NMAX];
     for (int i = 0; i < n; ++i)
         for (int j = 0; j <= i; ++j) {

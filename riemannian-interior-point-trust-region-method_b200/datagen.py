@@ -66,3 +66,44 @@ def nonnegpca_sweep(first_instance, instances, points_per_instance, dim=50, out=
             x0[i * points_per_instance + k] = more_initial_points(x0[0], 2000000000 + 16 * inst + k, 1)[0]
     y0[:] = 1.0
     return Z, x0, y0
+
+
+def stableid_constraint_values(A, conspec):
+    """g_i(A) for the constraint rows [kind, row, col, a, b] (src/StableIdentification/coordinator.py:108-130)."""
+    g = np.empty(len(conspec))
+    for i, (kind, r, c, a, b) in enumerate(conspec):
+        v = A[int(r), int(c)]
+        g[i] = (-v + a) if kind == 0 else ((v - a) if kind == 1 else (-(v - a) ** 2 + b))
+    return g
+
+
+def stableid_more_initial_points(base_points, conspec, count, seed=0, scale=0.02, margin=1e-3):
+    """`count` strictly feasible starting points (J, R, Q) for a StableIdentification instance: the reference ships 20 per
+    instance (found with RALM, src/StableIdentification/generator.py); a sweep over more takes base point k % len(base)
+    plus a small random skew / symmetric / symmetric perturbation, halved until R, Q stay positive definite and every
+    constraint keeps g_i(A) <= -margin * |g_i(A_base)|.  Point k < len(base) is the base point itself."""
+    rs = np.random.RandomState(seed)
+    out = []
+    nb = len(base_points)
+    for k in range(count):
+        J0, R0, Q0 = (np.asarray(a, dtype=np.float64) for a in base_points[k % nb])
+        if k < nb:
+            out.append([J0.copy(), R0.copy(), Q0.copy()])
+            continue
+        g0 = stableid_constraint_values((J0 - R0) @ Q0, conspec)
+        d = J0.shape[0]
+        EJ, ER, EQ = rs.randn(d, d), rs.randn(d, d), rs.randn(d, d)
+        t = scale
+        while True:
+            J = J0 + t * 0.5 * (EJ - EJ.T)
+            R = R0 + t * 0.5 * (ER + ER.T) * np.linalg.norm(R0) / d
+            Q = Q0 + t * 0.5 * (EQ + EQ.T) * np.linalg.norm(Q0) / d
+            ok = np.linalg.eigvalsh(R).min() > 0 and np.linalg.eigvalsh(Q).min() > 0
+            if ok:
+                g = stableid_constraint_values((J - R) @ Q, conspec)
+                ok = bool(np.all(g <= -margin * np.abs(g0)))
+            if ok:
+                break
+            t *= 0.5
+        out.append([J, R, Q])
+    return out

@@ -104,3 +104,29 @@ def test_batch_of_twenty_initial_points(rb, datasets):
     assert (best < 2e-9).all(), best
     costs = np.array([o.log["cost"][-1] for o in outs])
     assert np.all(np.isfinite(costs)) and costs.min() > 0.5 and costs.max() < 1.0
+
+
+def test_sweep_of_1024_initial_points(rb, datasets):
+    """north_star's batch size for this workload: 1024 strictly feasible starting points of instance 1 (the reference's 20
+    plus perturbations of them) in one launch.  The first 20 pairs are the reference's own points and must reproduce the
+    20-pair launch bit for bit (pairs are independent of their batch); every pair stays on the manifold and feasible,
+    and at least 95 % reach the KKT residual level the reference's notebook reports."""
+    base = [stableid_problem(datasets, pt) for pt in "abcdefghijklmnopqrst"]
+    conspec = np.array([[k, r, c, a, b] for (k, r, c, a, b) in base[0].spec], dtype=float)
+    pts = rb.datagen.stableid_more_initial_points([P.initialpoint for P in base], conspec, 1024, seed=5)
+    assert all(np.array_equal(pts[i][1], base[i].initialpoint[1]) for i in range(20))
+    sts = [_structure(rb, base[0], x0=x0) for x0 in pts]
+    opt = {"TRS_solver": "tCG", "second_order_stationarity": False, "maxiter": 25, "tolresid": 0, "maxtime": 1e9,
+           "save_inner_iteration": False}
+    solver = rb.RIPTRM(opt)
+    outs = solver.run_batch([None] * len(sts), structures=sts)
+    ref = rb.RIPTRM(opt).run_batch([None] * 20, structures=sts[:20])
+    for a, b in zip(outs[:20], ref):
+        assert all(np.array_equal(u, v) for u, v in zip(a.x, b.x)) and a.log["cost"] == b.log["cost"]
+    best = np.array([np.nanmin(o.log["residual"]) for o in outs])
+    assert np.isfinite(best).all() and (best < 2e-9).mean() >= 0.95, (np.isfinite(best).all(), (best < 2e-9).mean())
+    from riptrm_b200.datagen import stableid_constraint_values
+    for o in outs[::37]:
+        J, R, Q = o.x
+        assert np.max(np.abs(J + J.T)) < 1e-13 and np.linalg.eigvalsh(R).min() > 0 and np.linalg.eigvalsh(Q).min() > 0
+        assert stableid_constraint_values((J - R) @ Q, conspec).max() < 1e-9

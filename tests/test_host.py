@@ -212,3 +212,20 @@ def test_save_output_product_point_is_block_file(tmp_path):
     assert got.shape == (3, 5, 5) and np.max(np.abs(got - np.stack(x))) < 1e-7
     assert np.loadtxt(os.path.join(path, "RIPTRM_tCG_ineqLagmult.csv")).shape == (16,)
     assert os.path.getsize(os.path.join(path, "RIPTRM_tCG_eqLagmult.csv")) == 0
+
+
+def test_stableid_sweep_points_are_strictly_feasible(datasets):
+    """More starting points for the StableIdentification sweep: the reference's own 20 come first unchanged, the rest
+    are perturbations that stay skew / symmetric positive definite and strictly inside every constraint."""
+    d = datasets["StableIdentification/1"]
+    conspec = rb.StableIdStructure.conspec_from_constset(d["constset"])
+    base = [[d[f"init{c}_{pt}"] for c in "JRQ"] for pt in "abcdefghijklmnopqrst"]
+    pts = rb.datagen.stableid_more_initial_points(base, conspec, 200, seed=5)
+    assert len(pts) == 200 and all(np.array_equal(pts[i][k], base[i][k]) for i in range(20) for k in range(3))
+    for J, R, Q in pts:
+        assert np.array_equal(J, -J.T) and np.array_equal(R, R.T) and np.array_equal(Q, Q.T)
+        assert np.linalg.eigvalsh(R).min() > 0 and np.linalg.eigvalsh(Q).min() > 0
+        assert rb.datagen.stableid_constraint_values((J - R) @ Q, conspec).max() < 0
+    assert not np.array_equal(pts[20][1], base[0][1])
+    again = rb.datagen.stableid_more_initial_points(base, conspec, 200, seed=5)
+    assert all(np.array_equal(a[k], b[k]) for a, b in zip(pts, again) for k in range(3))
