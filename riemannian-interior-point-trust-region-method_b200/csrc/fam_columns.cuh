@@ -391,23 +391,53 @@ __device__ __forceinline__ void block_reduce_store(const Params& prm, Smem<P>& s
     }
 }
 
-// after a grid barrier: scal[q*P+c] = sum over CTAs.  Four lanes per value (lane-strided partial sums over the CTAs,
-// then a two-level butterfly), eight values per warp: all Q*P <= 72 totals in one round.
-template <int P, int Q>
-__device__ __forceinline__ void gather_scalars(const Params& prm, Smem<P>& sm, int buf) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int G = gridDim.x;
+// after a grid barrier: dst[k] = sum (k < first_min) or minimum over the CTAs of value k of their partial records
+// (`stride` doubles per CTA and buffer).  A warp takes 32 consecutive values (coalesced loads of one CTA's record) over a
+// contiguous range of CTAs, sixteen loads in flight, added in CTA order; the ranges' results go through shared memory
+// (`scratch`, at least NT doubles) and are added in range order.  Same order in every CTA: the totals are bit-identical
+// across the grid.
+__device__ __forceinline__ void gather_values(const double* __restrict__ part, int stride, double* scratch, double* dst,
+                                              int nval, int first_min) {
+    constexpr int NW = NT / 32;
+    const int G = gridDim.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = (nval + 31) >> 5;
+    const int gsplit = (nkb >= NW) ? 1 : NW / nkb;
+    for (int item = warp; item < nkb * gsplit; item += NW) {
+        const int kb = item % nkb, gs = item / nkb;
+        const int k = kb * 32 + lane;
+        const int g_lo = (int)((long long)G * gs / gsplit), g_hi = (int)((long long)G * (gs + 1) / gsplit);
+        const bool is_min = k >= first_min;
+        const double neutral = is_min ? CUDART_INF : 0.0;
+        double s = neutral;
+        if (k < nval) {
+            const double* src = part + k;
+            for (int g0 = g_lo; g0 < g_hi; g0 += 16) {
+                double v[16];
 #pragma unroll
-    for (int base = 0; base < Q * P; base += 8 * (NCW + 1)) {
-        const int k = base + warp * 8 + (lane >> 2), sub = lane & 3;
-        double s = 0.0;
-        if (k < Q * P)
-            for (int g = sub; g < G; g += 4) s = s + prm.dot_part[((size_t)buf * G + g) * (MAXQ * MAXP) + k];
-        s = s + __shfl_xor_sync(kFull, s, 1);
-        s = s + __shfl_xor_sync(kFull, s, 2);
-        if (k < Q * P && sub == 0) sm.scal[k] = s;
+                for (int u = 0; u < 16; ++u) v[u] = (g0 + u < g_hi) ? src[(size_t)(g0 + u) * stride] : neutral;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) s = is_min ? fmin(s, v[u]) : (s + v[u]);
+            }
+        }
+        scratch[gs * (nkb * 32) + k] = s;
     }
     __syncthreads();
+    for (int k = threadIdx.x; k < nval; k += NT) {
+        const bool is_min = k >= first_min;
+        double s = scratch[k];
+        for (int gs = 1; gs < gsplit; ++gs) {
+            const double t = scratch[gs * (nkb * 32) + k];
+            s = is_min ? fmin(s, t) : (s + t);
+        }
+        dst[k] = s;
+    }
+    __syncthreads();
+}
+
+// scal[q*P+c] = sum over CTAs of the Q per-column partial sums
+template <int P, int Q>
+__device__ __forceinline__ void gather_scalars(const Params& prm, Smem<P>& sm, int buf) {
+    gather_values(prm.dot_part + (size_t)buf * gridDim.x * (MAXQ * MAXP), MAXQ * MAXP, &sm.redv[0][0], sm.scal, Q * P, Q * P);
 }
 
 // per-column tCG state, identical in every CTA
@@ -973,24 +1003,8 @@ __device__ __forceinline__ void reduce_store_mixed(const Params& prm, Smem<P>& s
 }
 template <int P, int QS, int QM>
 __device__ __forceinline__ void gather_mixed(const Params& prm, Smem<P>& sm, int buf) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int G = gridDim.x;
-    for (int base = 0; base < (QS + QM) * P; base += 8 * (NCW + 1)) {
-        const int k = base + warp * 8 + (lane >> 2), sub = lane & 3;
-        const bool is_sum = k < QS * P;
-        double s = is_sum ? 0.0 : CUDART_INF;
-        if (k < (QS + QM) * P)
-            for (int g = sub; g < G; g += 4) {
-                const double v = prm.dot_part[((size_t)buf * G + g) * (MAXQ * MAXP) + k];
-                s = is_sum ? (s + v) : fmin(s, v);
-            }
-        const double t1 = __shfl_xor_sync(kFull, s, 1);
-        s = is_sum ? (s + t1) : fmin(s, t1);
-        const double t2 = __shfl_xor_sync(kFull, s, 2);
-        s = is_sum ? (s + t2) : fmin(s, t2);
-        if (k < (QS + QM) * P && sub == 0) sm.scal[k] = s;
-    }
-    __syncthreads();
+    gather_values(prm.dot_part + (size_t)buf * gridDim.x * (MAXQ * MAXP), MAXQ * MAXP, &sm.redv[0][0], sm.scal,
+                  (QS + QM) * P, QS * P);
 }
 
 struct PostState {  // per column, identical in every CTA

@@ -55,46 +55,10 @@ __device__ __forceinline__ void breduce(const Params& prm, Smem<P>& sm, const do
     }
 }
 
-// after a grid barrier: tot[q * P + c] = sum (q < first_min) or minimum over the CTAs.  A warp takes 32 consecutive
-// values (coalesced loads of one CTA's partials) over a contiguous range of CTAs, sixteen loads in flight, added in CTA
-// order; the ranges' partial results go through shared memory and are added in range order.
+// after a grid barrier: tot[q * P + c] = sum (q < first_min) or minimum over the CTAs (col::gather_values)
 template <int P>
 __device__ __forceinline__ void gather_tot(const Params& prm, Smem<P>& sm, double* tot, int buf, int K, int first_min) {
-    constexpr int NW = NT / 32;
-    const int G = gridDim.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nval = K * P, nkb = (nval + 31) >> 5;
-    const int gsplit = (nkb >= NW) ? 1 : NW / nkb;
-    double* scratch = &sm.redv[0][0];  // [gsplit][nkb * 32]
-    for (int item = warp; item < nkb * gsplit; item += NW) {
-        const int kb = item % nkb, gs = item / nkb;
-        const int k = kb * 32 + lane;
-        const int g_lo = (int)((long long)G * gs / gsplit), g_hi = (int)((long long)G * (gs + 1) / gsplit);
-        const bool is_min = k >= first_min * P;
-        const double neutral = is_min ? CUDART_INF : 0.0;
-        double s = neutral;
-        if (k < nval) {
-            const double* src = prm.dot_part + (size_t)buf * G * DOT_STRIDE + k;
-            for (int g0 = g_lo; g0 < g_hi; g0 += 16) {
-                double v[16];
-#pragma unroll
-                for (int u = 0; u < 16; ++u) v[u] = (g0 + u < g_hi) ? src[(size_t)(g0 + u) * DOT_STRIDE] : neutral;
-#pragma unroll
-                for (int u = 0; u < 16; ++u) s = is_min ? fmin(s, v[u]) : (s + v[u]);
-            }
-        }
-        scratch[gs * (nkb * 32) + k] = s;
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < nval; k += NT) {
-        const bool is_min = k >= first_min * P;
-        double s = scratch[k];
-        for (int gs = 1; gs < gsplit; ++gs) {
-            const double t = scratch[gs * (nkb * 32) + k];
-            s = is_min ? fmin(s, t) : (s + t);
-        }
-        tot[k] = s;
-    }
-    __syncthreads();
+    gather_values(prm.dot_part + (size_t)buf * gridDim.x * DOT_STRIDE, DOT_STRIDE, &sm.redv[0][0], tot, K * P, first_min * P);
 }
 
 // sum over the columns of one reduced quantity (column order)

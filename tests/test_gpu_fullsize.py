@@ -84,3 +84,52 @@ def test_config4_full_size_hessvec_properties(rb):
     assert torch.allclose(eta.norm(dim=0), info[:, 2], rtol=1e-12, atol=0)
     assert int(info[:, 0].min()) >= 1
     cs.close()
+
+
+def test_config4_full_size_on_stiefel(rb):
+    """n = 20000, p = 10 as ONE problem on Stiefel(n, p) (family STIEFEL): Hw against an independent fp64 evaluation on the
+    device (torch matmuls), tangency of the product, the tCG's trust-region / tangency invariants, and a
+    capped whole solve (maxiter = 2, inner_maxiter = 5) that must stay on the manifold and strictly feasible."""
+    import torch
+    n, p, eps = 20000, 10, 0.01
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    Z = torch.randn((n, n), generator=g, dtype=torch.float64, device=dev) / np.sqrt(n)
+    X = torch.zeros((n, p), dtype=torch.float64, device=dev)
+    b = n // p
+    for c in range(p):
+        X[c * b:(c + 1) * b, c] = torch.rand(b, generator=g, dtype=torch.float64, device=dev) + 0.1
+    X = (X / X.norm(dim=0, keepdim=True)).contiguous()
+    Y = (0.5 + torch.rand((n, p), generator=g, dtype=torch.float64, device=dev)).contiguous()
+    sym = lambda M: 0.5 * (M + M.T)
+    proj = lambda V: V - X @ sym(X.T @ V)
+    V = proj(torch.randn((n, p), generator=g, dtype=torch.float64, device=dev)).contiguous()
+    ss = rb.StiefelSolver(Z, p, eps=eps)
+    mu = 0.05
+    HV = ss.hessvec(X, Y, mu, V)
+    SV, SX = Z @ V + Z.T @ V, Z @ X + Z.T @ X
+    C1 = sym(X.T @ SX) + sym(X.T @ Y)
+    ref = proj(-SV + V @ C1 + (Y / (X + eps)) * proj(V))
+    assert float((HV - ref).abs().max()) < 1e-9 * float(ref.abs().max())
+    assert float((X.T @ HV + HV.T @ X).abs().max()) < 1e-9 * float(ref.abs().max())
+    assert torch.equal(ss.hessvec(X, Y, mu, V), HV)
+    opt = rb.options.default_option()
+    opt.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=1)
+    ss.set_options(opt)
+    Delta = 0.05
+    eta, info = ss.tcg(X, Y, mu, Delta)
+    assert float(eta.norm()) <= Delta * (1 + 1e-12) and abs(float(eta.norm()) - float(info[0, 2])) < 1e-12 * Delta
+    assert float((X.T @ eta + eta.T @ X).abs().max()) < 1e-12 and int(info[0, 0]) >= 1
+    sopt = rb.options.default_option()
+    sopt.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=2, inner_maxiter=5, tolresid=0, maxtime=1e9)
+    Y1 = torch.ones((n, p), dtype=torch.float64, device=dev)
+    Xs, Ys, sm, _ = ss.solve(X, Y1, sopt)
+    sm = sm.cpu().numpy()
+    SM = rb._lib.SM
+    assert np.isfinite(sm).all() and sm[0, SM["outer_iters"]] == 2 and sm[0, SM["inner_iters"]] >= 2
+    assert float((Xs.T @ Xs - torch.eye(p, dtype=torch.float64, device=dev)).abs().max()) < 1e-13
+    assert float(Xs.min()) > -eps and float(Ys.min()) > 0.0
+    cost = lambda M: -float((M * (Z @ M)).sum())
+    assert abs(sm[0, SM["cost"]] - cost(Xs)) < 1e-10 * abs(cost(Xs))
+    ss.close()
