@@ -84,12 +84,15 @@ struct Params {
     double* trace;                 // [p][trace_capacity][RIPTRM_TRACE_FIELDS] or nullptr
     double* summary;               // [p][RIPTRM_SUMMARY_FIELDS]
     int* all_done;                 // device flag read by the host loop
+    // time limits (RIPTRM.py:822-834, base_solver.py:85-106): the host loop measures the time since the start of the solve
+    // when it polls `all_done` and passes it in, so every CTA takes the same branch
+    double now_s, maxtime, inner_maxtime;   // inner_maxtime < 0: None (the outer limit applies to the inner loop)
 };
 
 // per-column solver state kept in global memory between launches
 enum {
     CS_IT = 0, CS_K, CS_DELTA, CS_XSX, CS_COST, CS_CNT_INNER, CS_CNT_TCG, CS_CNT_AUX, CS_ROWS, CS_FINISHED, CS_STOP,
-    CS_DELTA_INIT, CS_XSX_INIT, CS_COST_INIT, CS_TCG_ITERS, CS_TCG_STOP, CS_KAPPA, CS_FIELDS = 24
+    CS_DELTA_INIT, CS_XSX_INIT, CS_COST_INIT, CS_TCG_ITERS, CS_TCG_STOP, CS_KAPPA, CS_T_INNER, CS_FIELDS = 24
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -1012,6 +1015,7 @@ struct PostState {  // per column, identical in every CTA
     double mu, tolL, tolC, kappa, normdx, nrm, bdot, xSxN, costN, minx, miny, compl_v, xy, ngl, pl_cur, pl_new, a, b, d;
     double ared_pred, radius_update, inner_status, dual_clipping, tcg_iters, tcg_stop, DeltaNext;
     double radius0;  // trust-region radius before the step (the log's TR_radius)
+    double t_inner;  // start of the current inner loop, seconds since the start of the solve
     int path;      // 0 idle (finished), 1 converged, 2 primal infeasible, 3 normal (rho test)
     int accept, boundary, rollback;
     int evalc;     // evaluate (utils.py:342-368) this column in this call: boundary, or every step with trace_mode 1
@@ -1045,6 +1049,7 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
         s.finished = (tid >= prm.p) ? 1.0 : st[CS_FINISHED]; s.stop = st[CS_STOP];
         s.Delta_init = st[CS_DELTA_INIT]; s.xSx_init = st[CS_XSX_INIT]; s.cost_init = st[CS_COST_INIT];
         s.tcg_iters = st[CS_TCG_ITERS]; s.tcg_stop = st[CS_TCG_STOP]; s.kappa = st[CS_KAPPA];
+        s.t_inner = st[CS_T_INNER];
         const int it = (int)s.it;
         s.mu = prm.mu_sched[it > 0 ? it - 1 : 0];
         s.tolL = prm.tolL_sched[it > 0 ? it - 1 : 0];
@@ -1335,7 +1340,16 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
                     s.inner_status = (double)RIPTRM_INNER_UNSUCCESSFUL;
                 }
             }
-            if (prm.inner_maxiter >= 0 && (int)s.k >= prm.inner_maxiter) {  // :835-842 (after the step, as the reference)
+            {   // :822-834 (after the step, as the reference)
+                const double rt = (prm.inner_maxtime < 0.0) ? prm.now_s : (prm.now_s - s.t_inner);
+                const double lim = (prm.inner_maxtime < 0.0) ? prm.maxtime : prm.inner_maxtime;
+                if (rt >= lim) {
+                    s.inner_status = (double)RIPTRM_INNER_MAX_TIME;
+                    s.rollback = 1;
+                    s.boundary = 1;
+                }
+            }
+            if (prm.inner_maxiter >= 0 && (int)s.k >= prm.inner_maxiter) {  // :835-842
                 s.inner_status = (double)RIPTRM_INNER_MAX_ITER;
                 s.rollback = 1;
                 s.boundary = 1;
@@ -1485,13 +1499,14 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
                 row[RIPTRM_TR_MANVIOLATION] = man_v;
                 row[RIPTRM_TR_MAXVIOLATION] = max_v;
                 row[RIPTRM_TR_MEANVIOLATION] = mean_v;
-                row[RIPTRM_TR_TIME] = 0.0;
+                row[RIPTRM_TR_TIME] = prm.now_s;
             }
             s.rows += 1.0;
         }
         if (s.boundary) {
             int stop = RIPTRM_STOP_RUNNING;
-            if (it >= prm.maxiter) stop = RIPTRM_STOP_MAXITER;
+            if (prm.now_s >= prm.maxtime) stop = RIPTRM_STOP_MAXTIME;
+            else if (it >= prm.maxiter) stop = RIPTRM_STOP_MAXITER;
             if (residual <= prm.tolresid) stop = RIPTRM_STOP_TOLRESID;
             if (g == 0 && prm.summary != nullptr) {
                 double* sm_ = prm.summary + (size_t)tid * RIPTRM_SUMMARY_FIELDS;
@@ -1522,6 +1537,7 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
                 s.Delta_init = s.Delta;
                 s.xSx_init = s.xSx;
                 s.cost_init = s.cost;
+                s.t_inner = prm.now_s;
             }
         }
     }
@@ -1545,6 +1561,7 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
         st[CS_CNT_INNER] = s.cnt_inner; st[CS_CNT_TCG] = s.cnt_tcg; st[CS_CNT_AUX] = s.cnt_aux; st[CS_ROWS] = s.rows;
         st[CS_FINISHED] = s.finished; st[CS_STOP] = s.stop;
         st[CS_DELTA_INIT] = s.Delta_init; st[CS_XSX_INIT] = s.xSx_init; st[CS_COST_INIT] = s.cost_init;
+        st[CS_T_INNER] = s.t_inner;
     }
     if (g == 0 && tid == 0) {
         bool all = true;

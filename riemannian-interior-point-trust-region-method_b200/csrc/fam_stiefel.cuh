@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_kernel(Params prm) {
 struct PostState {
     double it, k, Delta, cost, cnt_inner, cnt_tcg, cnt_aux, rows, finished, stop, Delta_init, cost_init;
     double mu, tolL, tolC, normdx, costN, minx, miny, compl_v, ngl, pl_cur, pl_new, hdx, cdx;
-    double ared_pred, radius_update, inner_status, dual_clipping, tcg_iters, tcg_stop, DeltaNext, radius0;
+    double ared_pred, radius_update, inner_status, dual_clipping, tcg_iters, tcg_stop, DeltaNext, radius0, t_inner;
     int path;      // 0 idle (finished), 1 converged, 2 primal infeasible, 3 normal (rho test)
     int accept, boundary, rollback, evalc;
 };
@@ -534,6 +534,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
         s.finished = st[CS_FINISHED]; s.stop = st[CS_STOP];
         s.Delta_init = st[CS_DELTA_INIT]; s.cost_init = st[CS_COST_INIT];
         s.tcg_iters = st[CS_TCG_ITERS]; s.tcg_stop = st[CS_TCG_STOP];
+        s.t_inner = st[CS_T_INNER];
         const int it = (int)s.it;
         s.mu = prm.mu_sched[it > 0 ? it - 1 : 0];
         s.tolL = prm.tolL_sched[it > 0 ? it - 1 : 0];
@@ -831,6 +832,15 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
                     s.inner_status = (double)RIPTRM_INNER_UNSUCCESSFUL;
                 }
             }
+            {   // :822-834
+                const double rt = (prm.inner_maxtime < 0.0) ? prm.now_s : (prm.now_s - s.t_inner);
+                const double lim = (prm.inner_maxtime < 0.0) ? prm.maxtime : prm.inner_maxtime;
+                if (rt >= lim) {
+                    s.inner_status = (double)RIPTRM_INNER_MAX_TIME;
+                    s.rollback = 1;
+                    s.boundary = 1;
+                }
+            }
             if (prm.inner_maxiter >= 0 && (int)s.k >= prm.inner_maxiter) {  // :835-842
                 s.inner_status = (double)RIPTRM_INNER_MAX_ITER;
                 s.rollback = 1;
@@ -1006,13 +1016,14 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
                     row[RIPTRM_TR_MANVIOLATION] = man_v;
                     row[RIPTRM_TR_MAXVIOLATION] = max_v;
                     row[RIPTRM_TR_MEANVIOLATION] = mean_v;
-                    row[RIPTRM_TR_TIME] = 0.0;
+                    row[RIPTRM_TR_TIME] = prm.now_s;
                 }
                 s.rows += 1.0;
             }
             if (s.boundary) {
                 int stop = RIPTRM_STOP_RUNNING;
-                if (it >= prm.maxiter) stop = RIPTRM_STOP_MAXITER;
+                if (prm.now_s >= prm.maxtime) stop = RIPTRM_STOP_MAXTIME;
+                else if (it >= prm.maxiter) stop = RIPTRM_STOP_MAXITER;
                 if (residual <= prm.tolresid) stop = RIPTRM_STOP_TOLRESID;
                 if (g == 0 && prm.summary != nullptr) {
                     double* sm_ = prm.summary;
@@ -1042,6 +1053,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
                     s.k = 0.0;
                     s.Delta_init = s.Delta;
                     s.cost_init = s.cost;
+                    s.t_inner = prm.now_s;
                 }
             }
         }
@@ -1062,6 +1074,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
         st[CS_CNT_INNER] = s.cnt_inner; st[CS_CNT_TCG] = s.cnt_tcg; st[CS_CNT_AUX] = s.cnt_aux; st[CS_ROWS] = s.rows;
         st[CS_FINISHED] = s.finished; st[CS_STOP] = s.stop;
         st[CS_DELTA_INIT] = s.Delta_init; st[CS_COST_INIT] = s.cost_init;
+        st[CS_T_INNER] = s.t_inner;
         *prm.all_done = (s.finished != 0.0) ? 1 : 0;
     }
 #undef FOR_ROWS

@@ -8,6 +8,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -597,6 +598,10 @@ static int columns_solve(riptrm_handle* h, const double* x0, const double* y0, d
     prm.gamma = o.gamma;
     prm.const_left = o.const_left;
     prm.const_right = o.const_right;
+    prm.maxtime = o.maxtime;
+    prm.inner_maxtime = o.inner_maxtime;
+    const auto wall0 = std::chrono::steady_clock::now();
+    auto seconds_since_start = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count(); };
     const int nruns = is_stiefel(h) ? 1 : h->p;  // STIEFEL: one run; COLUMNS: one per column
     const size_t tb = (o.trace_mode != 0 && trace != nullptr)
                           ? (size_t)nruns * o.trace_capacity * RIPTRM_TRACE_FIELDS * sizeof(double) : 0;
@@ -615,6 +620,7 @@ static int columns_solve(riptrm_handle* h, const double* x0, const double* y0, d
     if ((rc = columns_import(h, prm.X, x0, where, st)) || (rc = columns_import(h, prm.Y, y0, where, st))) return rc;
     CUDA_TRY(cudaMemsetAsync(q.colstate, 0, (size_t)col::MAXP * col::CS_FIELDS * sizeof(double), st));
     CUDA_TRY(cudaEventRecord(h->ev0, st));
+    prm.now_s = seconds_since_start();
     if ((rc = columns_dispatch_post<true>(h, prm, st))) return rc;
     const long long max_rounds = (long long)(o.maxiter + 1) * (o.inner_maxiter > 0 ? o.inner_maxiter : 100000);
     for (long long round = 0; round < max_rounds; ++round) {
@@ -634,6 +640,7 @@ static int columns_solve(riptrm_handle* h, const double* x0, const double* y0, d
         cudaEventDestroy(t0);
         cudaEventDestroy(t1);
         if (rc) return rc;
+        prm.now_s = seconds_since_start();   // as of the last poll: the limits are tested one trust-region iteration late at most
         if ((rc = columns_dispatch_post<false>(h, prm, st))) return rc;
     }
     CUDA_TRY(cudaEventRecord(h->ev1, st));

@@ -405,7 +405,7 @@ def _stiefel_bench(Z, n, p, dev, gen, option, tcg_iters, reps, launches_out, eps
     solver.close()
     alg = 8.0 * n * n + 40.0 * n * p
     ms = float(np.mean(times))
-    return {"kernel": f"stiefel_kernel<{solver.p if solver.p in (4, 10, 16) else (4 if solver.p <= 4 else (10 if solver.p <= 10 else 16))},2>",
+    return {"kernel": f"stiefel_kernel<{4 if p <= 4 else (10 if p <= 10 else 16)},2>",
             "eps": eps, "tcg_launch_ms": ms, "matvec_passes_per_launch": float(np.mean(passes)),
             "ms_per_hessvec": ms / float(np.mean(passes)), "hessvec_hbm_gbs": alg * float(np.mean(passes)) / (ms * 1e-3) / 1e9,
             "tcg_iters_per_sec": float(info[0, 0]) / (ms * 1e-3), "tcg_stop": int(info[0, 1]),

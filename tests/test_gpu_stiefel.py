@@ -142,7 +142,7 @@ def test_p1_stiefel_is_the_sphere(rb):
     x /= np.linalg.norm(x)
     y = 0.5 + rs.rand(n, 1)
     v = rs.randn(n, 1)
-    v -= x * float(x.T @ v)
+    v -= x * float((x.T @ v)[0, 0])
     ss, cs = rb.StiefelSolver(Z, 1, eps=0.0), rb.ColumnsSolver(Z, 1, eps=0.0)
     a, b = ss.hessvec(x, y, 0.03, v), cs.hessvec(x, y, 0.03, v)
     assert np.max(np.abs(a - b)) < 1e-12 * np.max(np.abs(b))
@@ -167,3 +167,31 @@ def test_fullsize_properties(rb):
     assert np.max(np.abs(X.T @ HU + HU.T @ X)) < 1e-10 * scale
     assert np.array_equal(ss.hessvec(X, Y, 0.01, U), HU)
     ss.close()
+
+
+@pytest.mark.parametrize("family", ["stiefel", "columns"])
+def test_time_limits_of_the_large_n_solves(rb, family):
+    """`maxtime` (base_solver.py:85-106) and `inner_maxtime` (RIPTRM.py:822-834) on the host-sequenced whole solves: a run
+    whose budget is already spent stops at outer iteration 0 with the starting point; an inner budget of zero rolls every
+    inner loop back after its first trust-region iteration ('max-time-exceeded') and the run ends on maxiter."""
+    n, p = 96, 4
+    Z, X0, _, rs = _instance(n, p, seed=17)
+    if family == "columns":
+        X0 = np.abs(rs.rand(n, p))
+        X0 /= np.linalg.norm(X0, axis=0, keepdims=True)
+    Y0 = np.ones((n, p))
+    run = (lambda s: s.run_stiefel(Z, X0, Y0, eps=EPS)) if family == "stiefel" else (lambda s: s.run_columns(Z, X0, Y0)[0])
+    base = dict(TRS_solver="tCG", second_order_stationarity=False, maxiter=4, tolresid=0)
+    opt = rb.options.default_option()
+    opt.update(base, maxtime=1e-12)
+    out = run(rb.RIPTRM(opt))
+    x0 = X0 if family == "stiefel" else X0[:, 0]
+    assert out.log["iteration"] == [0] and np.array_equal(out.x, x0)
+    assert out.option["stoppingcriterion"].startswith("Max time exceeded")
+    opt = rb.options.default_option()
+    opt.update(base, maxtime=1e9, inner_maxtime=0.0)
+    out = run(rb.RIPTRM(opt))
+    assert out.log["iteration"][-1] == 4 and "Max iteration count reached" in out.option["stoppingcriterion"]
+    assert [s for s in out.log["inner_status"][1:]] == ["max-time-exceeded"] * 4
+    assert np.array_equal(out.x, x0)
+    assert all(t >= 0 for t in out.log["time"]) and out.log["time"][-1] > 0
