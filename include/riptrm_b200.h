@@ -111,9 +111,10 @@ typedef struct {
                                            2 one row per outer iteration (False) */
     int32_t trace_capacity;             /* rows per instance, incl. row 0 */
     int32_t schedule_split;             /* not a reference key.  Batches larger than the GPU's resident capacity are solved
-                                           in two launches: `schedule_split` outer iterations of every pair, then the
-                                           remainder with the pairs sorted by work so far (longest first).  Results are
-                                           bit-identical either way.  0 = automatic, < 0 = single launch */
+                                           in several launches: every pair is advanced to an outer iteration, the pairs are
+                                           sorted by work so far, and the remainder runs longest first.  Results are
+                                           bit-identical either way.  0 = automatic (two splits, at 4/15 and 7/15 of
+                                           maxiter), k > 0 = one split at outer iteration k, < 0 = single launch */
     double tolresid;                    /* 'tolresid' */
     double maxtime;                     /* 'maxtime' seconds, measured on the device clock */
     double inner_maxtime;               /* 'inner_maxtime'; < 0 == None */

@@ -1045,13 +1045,25 @@ static SmallParams small_params(const riptrm_handle* h) {
     return P;
 }
 
-// One launch, or two with the pairs re-ordered in between (see solve_instance): `schedule_split` outer
-// iterations for every pair first, then the rest, longest first.  Bit-identical results either way.
+// One launch, or several with the pairs re-ordered in between (see solve_instance): every pair is advanced to outer
+// iteration s1, then -- longest first, by the work spent so far -- to s2, then to the end.  Bit-identical results either
+// way.  Work per pair varies 3-5x and is only partly predictable from its first iterations: on six 16384-pair batches of
+// the bench workload the makespan over the ideal (total work / resident warps) was 1.34 / 1.22 / ... for one launch in
+// index order, 1.06-1.23 for one split at 6, 1.04-1.08 at 8, 1.03-1.04 for splits at 8 and 14, 1.005 with perfect
+// knowledge (scripts/schedule_probe.py + offline list scheduling of the measured per-pair work).
 static int solve_scheduled(riptrm_handle* h, SphereParams P, const DevOpts& o, cudaStream_t st) {
-    int split = h->opts.schedule_split;  //: 0 auto, < 0 off, > 0 outer iteration
+    const int user = h->opts.schedule_split;  //: 0 auto, < 0 off, > 0 one split at that outer iteration
+    const int maxiter = h->opts.maxiter;
     const int resident = h->num_sms * 10;
-    if (split == 0) split = (h->batch > resident && h->opts.maxiter > 12) ? 6 : -1;
-    if (split <= 0 || split >= h->opts.maxiter) {
+    int splits[2] = {-1, -1};
+    int nsplit = 0;
+    if (user > 0 && user < maxiter) {
+        splits[nsplit++] = user;
+    } else if (user == 0 && h->batch > resident && maxiter > 12) {
+        splits[nsplit++] = (4 * maxiter + 7) / 15;   // 8 of 30
+        splits[nsplit++] = (7 * maxiter + 7) / 15;   // 14 of 30
+    }
+    if (nsplit == 0) {
         P.order = nullptr;
         P.pause = nullptr;
         P.resume = 0;
@@ -1081,22 +1093,25 @@ static int solve_scheduled(riptrm_handle* h, SphereParams P, const DevOpts& o, c
     }
     cudaEvent_t first_start = nullptr;
     CUDA_TRY(cudaEventCreateWithFlags(&first_start, cudaEventDefault));
-    P.order = nullptr;
     P.pause = h->d_pause;
-    P.resume = 0;
-    P.pause_at = split;
-    if ((rc = dispatch_sphere<0>(h, P, o, st))) return rc;
-    std::swap(first_start, h->ev0);  // keep the start of the first launch: the reported time spans both
-    schedule_keys_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(h->d_pause, h->d_keys, h->d_idx, (int)B);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(h->d_sort_tmp, h->sort_tmp_bytes, h->d_keys, h->d_keys_sorted,
-                                                       h->d_idx, h->d_order, (int)B, 0, 32, st));
-    h->launches += 2;
-    P.order = h->d_order;
-    P.resume = 1;
-    P.pause_at = -1;
-    rc = dispatch_sphere<0>(h, P, o, st);
-    std::swap(first_start, h->ev0);
+    for (int phase = 0; phase <= nsplit; ++phase) {
+        P.order = (phase == 0) ? nullptr : h->d_order;
+        P.resume = (phase == 0) ? 0 : 1;
+        P.pause_at = (phase < nsplit) ? splits[phase] : -1;
+        if ((rc = dispatch_sphere<0>(h, P, o, st))) break;
+        if (phase == 0) std::swap(first_start, h->ev0);  // keep the start of the first launch: the reported time spans all
+        if (phase < nsplit) {
+            schedule_keys_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(h->d_pause, h->d_keys, h->d_idx, (int)B);
+            if (cudaGetLastError() != cudaSuccess) { rc = fail(RIPTRM_E_CUDA, "schedule_keys_kernel launch failed"); break; }
+            if (cub::DeviceRadixSort::SortPairsDescending(h->d_sort_tmp, h->sort_tmp_bytes, h->d_keys, h->d_keys_sorted,
+                                                          h->d_idx, h->d_order, (int)B, 0, 32, st) != cudaSuccess) {
+                rc = fail(RIPTRM_E_CUDA, "radix sort of the schedule keys failed");
+                break;
+            }
+            h->launches += 2;
+        }
+    }
+    std::swap(first_start, h->ev0);   // ev0 = start of the first launch again; ev1 was recorded by the last one
     cudaEventDestroy(first_start);
     return rc;
 }
