@@ -5,8 +5,8 @@ The directory name carries the reference's name; import it as `riptrm_b200` (rep
 from . import _lib, datagen, io, options, sharding, structure
 from ._lib import RiptrmError, load_library
 from .solver import RIPTRM, BatchSolver, ColumnsSolver, StiefelSolver, Output, columns_bench, trace_to_log
-from .structure import (NonnegPCAStructure, RosenbrockStructure, StableIdStructure,
+from .structure import (NonnegPCAStructure, NonnegPCAStiefelStructure, RosenbrockStructure, StableIdStructure,
                         structure_from_problem)
 
 __all__ = ["RIPTRM", "BatchSolver", "ColumnsSolver", "StiefelSolver", "columns_bench", "Output", "trace_to_log", "RiptrmError", "load_library",
-           "NonnegPCAStructure", "RosenbrockStructure", "StableIdStructure", "structure_from_problem"]
+           "NonnegPCAStructure", "NonnegPCAStiefelStructure", "RosenbrockStructure", "StableIdStructure", "structure_from_problem"]

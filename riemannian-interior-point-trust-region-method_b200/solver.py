@@ -496,7 +496,12 @@ class RIPTRM:
         if getattr(problem, "has_eqconstraints", False):  # RIPTRM.py:911-912
             warnings.warn("Equality constraints detecred. Currently, RIPTRM does not support equality "
                           "constraints and will completely ignore them.", Warning)
-        out = self.run_batch([problem])[0]
+        st = structure_from_problem(problem)
+        if st.family == _lib.FAMILY_NONNEGPCA_STIEFEL:    # one large instance with matrix iterates: its own kernel family
+            out = self.run_stiefel(st.Z, np.asarray(st.x0, dtype=np.float64),
+                                   np.asarray(st.y0, dtype=np.float64).reshape(st.x0.shape), eps=st.eps)
+        else:
+            out = self.run_batch([problem], structures=[st])[0]
         self.log = out.log
         return out
 

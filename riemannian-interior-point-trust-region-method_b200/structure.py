@@ -42,6 +42,27 @@ class NonnegPCAStructure:
 
 
 @dataclass
+class NonnegPCAStiefelStructure:
+    """min -tr(X'ZX) on Stiefel(n, p), X_ij + eps >= 0 -- BASELINE config 4 as written (no reference coordinator: the
+    reference's NonnegPCA lives on the sphere).  One run with an n x p matrix iterate; `y0` holds the
+    n*p multipliers in row-major constraint order (flat or n x p)."""
+    Z: np.ndarray
+    x0: np.ndarray
+    y0: np.ndarray
+    eps: float = 0.01
+    family: int = field(default=_lib.FAMILY_NONNEGPCA_STIEFEL, init=False)
+
+    @property
+    def shape(self):
+        n, p = self.x0.shape
+        return (n, p, n * p)
+
+    @property
+    def typical_dist(self):
+        return np.sqrt(self.x0.shape[1])
+
+
+@dataclass
 class RosenbrockStructure:
     """Quadratic chain on Grassmann(n,k) (src/Rosenbrock/coordinator.py:33-91)."""
     n: int
@@ -177,7 +198,7 @@ def _original_constraints(problem):
 
 def structure_from_problem(problem):
     """Returns the structure of a reference-style NonlinearProblem or raises NotImplementedError."""
-    if isinstance(problem, (NonnegPCAStructure, RosenbrockStructure, StableIdStructure)):
+    if isinstance(problem, (NonnegPCAStructure, NonnegPCAStiefelStructure, RosenbrockStructure, StableIdStructure)):
         return problem
     st = getattr(problem, "riptrm_structure", None)
     if st is not None:

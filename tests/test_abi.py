@@ -56,6 +56,12 @@ def test_errors_are_codes_not_exceptions(built):
     assert lib.riptrm_create(1, 0, 1, 0, 1, 0, ctypes.byref(h)) == -1
     assert b"positive" in lib.riptrm_last_error()
     assert lib.riptrm_create(99, 5, 1, 5, 1, 0, ctypes.byref(h)) in (-1, -3)
+    # shape rules of the large-n families (4 = COLUMNS, 5 = STIEFEL): batch 1, m = n p, p <= 16, Stiefel also p <= n
+    assert lib.riptrm_create(5, 100, 4, 400, 2, 0, ctypes.byref(h)) == -1 and b"batch must be 1" in lib.riptrm_last_error()
+    assert lib.riptrm_create(5, 100, 4, 100, 1, 0, ctypes.byref(h)) == -1 and b"m == n * p" in lib.riptrm_last_error()
+    assert lib.riptrm_create(5, 100, 17, 1700, 1, 0, ctypes.byref(h)) == -3
+    assert lib.riptrm_create(5, 3, 4, 12, 1, 0, ctypes.byref(h)) == -3
+    assert lib.riptrm_create(4, 100, 17, 1700, 1, 0, ctypes.byref(h)) == -3
     assert lib.riptrm_destroy(None) == 0
     assert lib.riptrm_launch_count(None) == 0
     with pytest.raises(built.RiptrmError):

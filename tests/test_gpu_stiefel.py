@@ -195,3 +195,15 @@ def test_time_limits_of_the_large_n_solves(rb, family):
     assert [s for s in out.log["inner_status"][1:]] == ["max-time-exceeded"] * 4
     assert np.array_equal(out.x, x0)
     assert all(t >= 0 for t in out.log["time"]) and out.log["time"][-1] > 0
+
+
+def test_run_accepts_a_stiefel_structure(rb):
+    """`RIPTRM(option).run(...)` -- the reference's entry point -- with a structured Stiefel problem (flat multipliers)."""
+    n, p = 48, 3
+    Z, X0, _, _ = _instance(n, p, seed=2)
+    st = rb.NonnegPCAStiefelStructure(Z=Z, x0=X0, y0=np.ones(n * p), eps=EPS)
+    opt = dict(TRS_solver="tCG", second_order_stationarity=False, maxiter=3, tolresid=0, maxtime=1e9)
+    solver = rb.RIPTRM(opt)
+    a = solver.run(st)
+    b = rb.RIPTRM(opt).run_stiefel(Z, X0, np.ones((n, p)), eps=EPS)
+    assert np.array_equal(a.x, b.x) and a.log["cost"] == b.log["cost"] and solver.log is a.log
