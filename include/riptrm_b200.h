@@ -214,6 +214,14 @@ int riptrm_hessvec(riptrm_handle* h, const double* x, const double* y, double mu
 int riptrm_tcg(riptrm_handle* h, const double* x, const double* y, double mu, double Delta, double* eta,
                double* info, int where, void* stream);
 
+/* ---- synthetic sweeps drawn on the device (src/NonnegPCA/generator.py:9-65) ----------------
+ * `instances` NonnegPCA instances first_instance .. by the reference generator's law (snr, delta as in
+ * config_dataset.yaml:7-8), each with `points_per_instance` feasible starting points: Z [instances][n][n],
+ * x0 / y0 [instances * points_per_instance][n] (instance-major), all DEVICE pointers on `device`.  Every number is a
+ * function of (instance id, stream, index) through Philox4x32-10, so ranks draw their own shares independently. */
+int riptrm_generate_nonnegpca(int device, int n, long long first_instance, int instances, int points_per_instance,
+                              double snr, double delta, double* Z, double* x0, double* y0, void* stream);
+
 /* number of kernel launches the handle has issued (for bench.py's gpu_launches) */
 int64_t riptrm_launch_count(const riptrm_handle* h);
 /* COLUMNS and STIEFEL families: number of full S.V streaming passes (one per Hessian-vector product, plus the S.X of the

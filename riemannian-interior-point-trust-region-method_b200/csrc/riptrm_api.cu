@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/riptrm_b200.h"
+#include "datagen.cuh"
 #include "fam_columns.cuh"
 #include "fam_stiefel.cuh"
 #include "fam_grassmann.cuh"
@@ -1114,6 +1115,20 @@ static int solve_scheduled(riptrm_handle* h, SphereParams P, const DevOpts& o, c
     std::swap(first_start, h->ev0);   // ev0 = start of the first launch again; ev1 was recorded by the last one
     cudaEventDestroy(first_start);
     return rc;
+}
+
+extern "C" int riptrm_generate_nonnegpca(int device, int n, long long first_instance, int instances, int points_per_instance,
+                                         double snr, double delta, double* Z, double* x0, double* y0, void* stream) {
+    if (Z == nullptr || x0 == nullptr || y0 == nullptr) return fail(RIPTRM_E_INVALID, "NULL argument");
+    if (n < 2 || n > 2048 || instances < 1 || points_per_instance < 1 || first_instance < 0)
+        return fail(RIPTRM_E_INVALID, "generate_nonnegpca: 2 <= n <= 2048, instances >= 1, points_per_instance >= 1");
+    if (!(snr >= 0.0) || !(delta > 0.0 && delta <= 1.0) || (int)floor(delta * n) < 1)
+        return fail(RIPTRM_E_INVALID, "generate_nonnegpca: snr >= 0, 0 < delta <= 1, floor(delta n) >= 1");
+    CUDA_TRY(cudaSetDevice(device));
+    const size_t smem = (size_t)n * (2 * sizeof(double) + sizeof(int));
+    gen::nonnegpca_kernel<<<instances, 128, smem, (cudaStream_t)stream>>>(n, first_instance, points_per_instance, snr, delta, Z, x0, y0);
+    CUDA_TRY(cudaGetLastError());
+    return RIPTRM_OK;
 }
 
 extern "C" int riptrm_solve(riptrm_handle* h, const double* x0, const double* y0, double* x, double* y,

@@ -107,3 +107,21 @@ def stableid_more_initial_points(base_points, conspec, count, seed=0, scale=0.02
             t *= 0.5
         out.append([J, R, Q])
     return out
+
+
+def nonnegpca_sweep_device(first_instance, instances, points_per_instance, dim=50, snr=0.5, delta=0.7, device=0, stream=None):
+    """The same sweep drawn ON the device (csrc/datagen.cuh: Philox4x32-10 keyed by the instance id, the reference
+    generator's law): returns torch CUDA tensors Z [instances, dim, dim], x0 / y0 [instances * points, dim].  A different
+    random stream than `nonnegpca_sweep` (NumPy's MT19937 is sequential); tests/helpers.py restates it bit for bit."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    lib = _lib.load_library()
+    dev = torch.device("cuda", device)
+    Z = torch.empty((instances, dim, dim), dtype=torch.float64, device=dev)
+    x0 = torch.empty((instances * points_per_instance, dim), dtype=torch.float64, device=dev)
+    y0 = torch.empty_like(x0)
+    _lib.check(lib.riptrm_generate_nonnegpca(device, dim, int(first_instance), instances, points_per_instance, float(snr),
+                                             float(delta), Z.data_ptr(), x0.data_ptr(), y0.data_ptr(),
+                                             C.c_void_p(stream) if stream else None))
+    return Z, x0, y0

@@ -66,3 +66,104 @@ def stiefel_start(n, p, seed):
         X[lo:hi, c] = np.abs(rs.rand(hi - lo)) + 0.1
         X[:, c] /= np.linalg.norm(X[:, c])
     return X
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# NumPy restatement of the device-side generator (csrc/datagen.cuh): Philox4x32-10, polar normals, det_log
+# ----------------------------------------------------------------------------------------------------------------
+def _philox(key, index, stream, sub):
+    """Vectorised over `index` (uint64 array); key, stream, sub scalars or arrays.  Returns four uint32 arrays."""
+    index = np.asarray(index, dtype=np.uint64)
+    M = np.uint64(0xFFFFFFFF)
+    c0 = index & M
+    c1 = index >> np.uint64(32)
+    c2 = np.broadcast_to(np.uint64(stream), index.shape).copy()
+    c3 = np.broadcast_to(np.asarray(sub, dtype=np.uint64), index.shape).copy()
+    k0 = np.uint64(int(key) & 0xFFFFFFFF)
+    k1 = np.uint64((int(key) >> 32) & 0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c0
+        p1 = np.uint64(0xCD9E8D57) * c2
+        n0 = (p1 >> np.uint64(32)) ^ c1 ^ k0
+        n1 = p1 & M
+        n2 = (p0 >> np.uint64(32)) ^ c3 ^ k1
+        n3 = p0 & M
+        c0, c1, c2, c3 = n0, n1, n2, n3
+        k0 = (k0 + np.uint64(0x9E3779B9)) & M
+        k1 = (k1 + np.uint64(0xBB67AE85)) & M
+    return c0, c1, c2, c3
+
+
+def _u53(hi, lo):
+    return ((hi >> np.uint64(5)).astype(np.float64) * 67108864.0 + (lo >> np.uint64(6)).astype(np.float64)) * (1.0 / 9007199254740992.0)
+
+
+def det_log_np(x):
+    """csrc/common.cuh det_log (fdlibm-style, no contraction) for positive normal doubles."""
+    x = np.asarray(x, dtype=np.float64)
+    u = x.view(np.uint64).copy()
+    hx = u >> np.uint64(32)
+    k = (hx >> np.uint64(20)).astype(np.int64) - 1023
+    hx = hx & np.uint64(0x000FFFFF)
+    i = (hx + np.uint64(0x95F64)) & np.uint64(0x100000)
+    u = ((hx | (i ^ np.uint64(0x3FF00000))) << np.uint64(32)) | (u & np.uint64(0xFFFFFFFF))
+    k = k + (i >> np.uint64(20)).astype(np.int64)
+    f = u.view(np.float64) - 1.0
+    dk = k.astype(np.float64)
+    Lg = (6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
+          1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01)
+    ln2_hi, ln2_lo = 6.93147180369123816490e-01, 1.90821492927058770002e-10
+    s = f / (2.0 + f)
+    z = s * s
+    w = z * z
+    t1 = w * (Lg[1] + w * (Lg[3] + w * Lg[5]))
+    t2 = z * (Lg[0] + w * (Lg[2] + w * (Lg[4] + w * Lg[6])))
+    R = t2 + t1
+    hfsq = 0.5 * f * f
+    return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f)
+
+
+def _normal_twin(key, index, stream):
+    index = np.asarray(index, dtype=np.uint64)
+    out = np.zeros(index.shape)
+    todo = np.ones(index.shape, dtype=bool)
+    for t in range(64):
+        if not todo.any():
+            break
+        a, b, c, d = _philox(key, index[todo], stream, t)
+        v1, v2 = 2.0 * _u53(a, b) - 1.0, 2.0 * _u53(c, d) - 1.0
+        s = v1 * v1 + v2 * v2
+        ok = (s < 1.0) & (s > 0.0)
+        val = np.zeros(s.shape)
+        val[ok] = v1[ok] * np.sqrt((-2.0 * det_log_np(s[ok])) / s[ok])
+        idx = np.flatnonzero(todo)
+        out[idx[ok]] = val[ok]
+        todo[idx[ok]] = False
+    return out
+
+
+def device_generator_twin(inst, n, points, snr=0.5, delta=0.7):
+    """(Z [n, n], x0 [points, n]) of instance `inst` exactly as csrc/datagen.cuh draws them."""
+    k = int(np.floor(delta * n))
+    perm = np.arange(n)
+    a, b, _, _ = _philox(inst, np.arange(k, dtype=np.uint64), 0, 0)
+    us = _u53(a, b)
+    for i in range(k):
+        j = min(i + int(us[i] * float(n - i)), n - 1)
+        perm[i], perm[j] = perm[j], perm[i]
+    v = np.zeros(n)
+    v[perm[:k]] = 1.0 / np.sqrt(float(k))
+    rn = np.sqrt(float(n))
+    noise = _normal_twin(inst, np.arange(n * n, dtype=np.uint64), 1).reshape(n, n) / rn
+    diag = (_normal_twin(inst, np.arange(n, dtype=np.uint64), 2) * 2.0) / rn
+    noise[np.arange(n), np.arange(n)] = diag
+    Z = np.sqrt(snr) * np.outer(v, v) + noise
+    x0 = np.empty((points, n))
+    for pt in range(points):
+        a, b, _, _ = _philox(inst, np.arange(n, dtype=np.uint64), 3 + pt, 0)
+        u = _u53(a, b)
+        s = 0.0
+        for val in u:
+            s = s + val * val
+        x0[pt] = np.abs(u / np.sqrt(s))
+    return Z, x0
