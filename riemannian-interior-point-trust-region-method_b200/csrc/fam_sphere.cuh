@@ -24,7 +24,7 @@ namespace riptrm {
 // consecutive 32-bit TMEM columns of the warp's own TMEM lane l, fetched with tcgen05.ld.32x32b (SASS LDTM).  With
 // every SM full, S.v from shared memory costs ~1890 cycles (the shared-memory pipe is the bottleneck: 83 % busy),
 // from TMEM ~630 (scripts/tmem_test.cu); the values and their order are the same, so results stay bit-identical.
-template <int K_, int NFIX = 0, bool TM = false>
+template <int K_, int NFIX = 0, bool TM = false, int TCH = 64>
 struct SphereFam {
     static_assert(!TM || (NFIX == 50 && K_ == 2), "the TMEM layout is built for n = 50");
     static constexpr int K = K_;
@@ -85,6 +85,23 @@ struct SphereFam {
         reinterpret_cast<double2*>(c.vbuf)[lane] = make_double2(v.v[0], v.v[1]);
         __syncwarp();
         double a0x = 0.0, a0y = 0.0, a1x = 0.0, a1y = 0.0;
+        if (TCH == 32) {
+            // 32-column chunks for the 128-register kernel (same order of additions)
+#pragma unroll
+            for (int ch = 0; ch < 6; ++ch) {
+                uint32_t r[32];
+                tmem::tmem_ld_x32(c.taddr + 32 * ch, r);
+                tmem::wait_ld();
+#pragma unroll
+                for (int jj = 0; jj < 8; jj += 2) {
+                    const double2 vj = *reinterpret_cast<const double2*>(c.vbuf + 8 * ch + jj);
+                    a0x = fma(__hiloint2double((int)r[4 * jj + 1], (int)r[4 * jj + 0]), vj.x, a0x);
+                    a0y = fma(__hiloint2double((int)r[4 * jj + 3], (int)r[4 * jj + 2]), vj.x, a0y);
+                    a1x = fma(__hiloint2double((int)r[4 * jj + 5], (int)r[4 * jj + 4]), vj.y, a1x);
+                    a1y = fma(__hiloint2double((int)r[4 * jj + 7], (int)r[4 * jj + 6]), vj.y, a1y);
+                }
+            }
+        } else {
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
             uint32_t r[64];
@@ -98,6 +115,7 @@ struct SphereFam {
                 a1x = fma(__hiloint2double((int)r[4 * jj + 5], (int)r[4 * jj + 4]), vj.y, a1x);
                 a1y = fma(__hiloint2double((int)r[4 * jj + 7], (int)r[4 * jj + 6]), vj.y, a1y);
             }
+        }
         }
         {
             uint32_t r[8];

@@ -70,7 +70,10 @@ struct riptrm_handle {
     double* d_v = nullptr;      // hook operand
     double* d_info = nullptr;   // hook info
     size_t trace_bytes = 0;
-    int* d_counter = nullptr;
+    int* d_counter = nullptr;   // [2]: work queue of the main kernel, work queue of the fast lane
+    int* d_fast_order = nullptr;  // fast lane: the pairs of the longest units
+    cudaStream_t lane_stream = nullptr;
+    cudaEvent_t lane_ev0 = nullptr, lane_ev1 = nullptr;
     // two-launch schedule of the batched families (longest pairs first in the second launch)
     double* d_pause = nullptr;   // [batch][kPauseFields]
     float *d_keys = nullptr, *d_keys_sorted = nullptr;
@@ -105,6 +108,8 @@ struct SphereParams {
     double* pause;     // [batch][kPauseFields] or nullptr
     int resume;        // second launch: continue the paused pairs from (x, y, pause)
     int pause_at;      // first launch: outer iteration to pause at (< 0: run to the end)
+    int sibling_units; // 1: the queue (and `order`) counts units of two consecutive pairs that share a Z (sphere_tmem2_kernel)
+    int queue_len;     // entries of the work queue (0: batch, or batch / 2 units)
     // hooks
     const double* v;
     double mu;
@@ -267,7 +272,7 @@ extern "C" int riptrm_create(int family, int n, int p, int m, int batch, int dev
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
-    CUDA_TRY(cudaMalloc(&h->d_counter, sizeof(int)));
+    CUDA_TRY(cudaMalloc(&h->d_counter, 2 * sizeof(int)));
     CUDA_TRY(cudaEventCreate(&h->ev0));
     CUDA_TRY(cudaEventCreate(&h->ev1));
     *out = h;
@@ -303,6 +308,10 @@ extern "C" int riptrm_destroy(riptrm_handle* h) {
     if (h->d_sort_tmp) cudaFree(h->d_sort_tmp);
     if (h->d_passes) cudaFree(h->d_passes);
     if (h->d_counter) cudaFree(h->d_counter);
+    if (h->d_fast_order) cudaFree(h->d_fast_order);
+    if (h->lane_stream) cudaStreamDestroy(h->lane_stream);
+    if (h->lane_ev0) cudaEventDestroy(h->lane_ev0);
+    if (h->lane_ev1) cudaEventDestroy(h->lane_ev1);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
@@ -803,7 +812,7 @@ __global__ void __launch_bounds__(128, 2) sphere_tmem_kernel(SphereParams P, Dev
         int inst = 0;
         if (lane == 0) inst = atomicAdd(counter, 1);
         inst = __shfl_sync(kFull, inst, 0);
-        if (inst >= P.batch) break;
+        if (inst >= (P.queue_len > 0 ? P.queue_len : P.batch)) break;
         if (P.order != nullptr) inst = P.order[inst];
         double* pause = (P.pause != nullptr) ? P.pause + (size_t)inst * kPauseFields : nullptr;
         if (MODE == 0 && P.resume && pause[7] == 0.0) continue;
@@ -850,6 +859,96 @@ __global__ void __launch_bounds__(128, 2) sphere_tmem_kernel(SphereParams P, Dev
     tmem::fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem::dealloc(tmem_base, 256);
+}
+
+// The same with two warps per copy of S.  Consecutive pairs of one instance (its initial points) share Z, and a warp of the
+// same TMEM sub-partition in the same CTA can read what its neighbour staged: 8 warps per CTA, warps w and w + 4 work on
+// the two pairs of a unit from one copy of S in sub-partition w % 4.  16 resident warps per SM instead of 8 (the
+// register file then allows 128 registers per thread), TMEM and staging traffic per pair halved.  The pairs of an
+// instance do nearly the same work (correlation 0.99), so the warps of a unit finish together.
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) sphere_tmem2_kernel(SphereParams P, DevOpts o, int* counter) {
+    using F = SphereFam<2, 50, true, 32>;
+    constexpr int K = 2;
+    extern __shared__ __align__(16) double smem[];
+    __shared__ uint32_t tmem_base;
+    __shared__ int unit_slot[4];
+    const int n = 50, ns = 50, pad = 64;
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int q = warp & 3, role = warp >> 2;
+    double* stage = smem + (size_t)q * (n * ns + pad);
+    if (warp == 0) tmem::alloc(&tmem_base, 256);
+    tmem::fence_before_sync();
+    __syncthreads();
+    tmem::fence_after_sync();
+    typename F::Ctx ctx;
+    ctx.S = stage;                    // staging copy of the sub-partition; S.v reads the TMEM copy
+    ctx.vbuf = smem + (size_t)4 * (n * ns + pad) + (size_t)warp * 64;
+    ctx.n = n;
+    ctx.ns = ns;
+    ctx.eps = P.eps;
+    ctx.embedded = o.is_euclidean_embedded != 0;
+    ctx.taddr = tmem_base + ((uint32_t)(32 * q) << 16);
+    const int units = P.batch / 2, ipp = P.batch / P.batch_z;
+    auto pair_bar = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
+    int loaded_z = -1;
+    while (true) {
+        if (role == 0 && lane == 0) unit_slot[q] = atomicAdd(counter, 1);
+        pair_bar();
+        int unit = unit_slot[q];
+        pair_bar();                   // both warps have read the slot (and are done with the previous unit's S)
+        if (unit >= units) break;
+        if (P.order != nullptr) unit = P.order[unit];
+        const int inst = 2 * unit + role;
+        const bool resume = P.resume != 0;
+        // paused[7]: 1 paused, 0 finished in an earlier launch, 2 handed to the fast lane of this launch
+        const bool skip0 = resume && P.pause[(size_t)(2 * unit) * kPauseFields + 7] != 1.0;
+        const bool skip1 = resume && P.pause[(size_t)(2 * unit + 1) * kPauseFields + 7] != 1.0;
+        if (skip0 && skip1) continue;  // both finished in an earlier launch (uniform over the two warps)
+        const int zi = (2 * unit) / ipp;
+        if (zi != loaded_z) {
+            if (role == 0) {
+                load_S(P.Z + (size_t)zi * n * n, stage, n, ns, pad);
+                F::stage_to_tmem(ctx);
+            }
+            tmem::fence_before_sync();
+            pair_bar();
+            tmem::fence_after_sync();
+            loaded_z = zi;
+        }
+        if (role == 0 ? skip0 : skip1) continue;
+        double* pause = (P.pause != nullptr) ? P.pause + (size_t)inst * kPauseFields : nullptr;
+        const typename F::Vec x0 = load_vec<K>((resume ? P.x : P.x0) + (size_t)inst * n, n);
+        const typename F::CVec y0 = load_vec<K>((resume ? P.y : P.y0) + (size_t)inst * n, n);
+        typename F::Pt pt;
+        typename F::CVec y;
+        double* tr = (P.trace != nullptr && o.trace_mode != 0) ? P.trace + (size_t)inst * o.trace_capacity * RIPTRM_TRACE_FIELDS
+                                                               : nullptr;
+        solve_instance<F>(ctx, o, x0, y0, pt, y, P.summary ? P.summary + (size_t)inst * RIPTRM_SUMMARY_FIELDS : nullptr, tr,
+                          pause, resume, P.pause_at);
+        if (P.x) store_vec<K>(P.x + (size_t)inst * n, pt.x, n);
+        if (P.y) store_vec<K>(P.y + (size_t)inst * n, y, n);
+    }
+    tmem::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem::dealloc(tmem_base, 256);
+}
+
+static int launch_sphere_tmem2(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
+    const size_t smem = ((size_t)4 * (50 * 50 + 64) + 8 * 64) * sizeof(double);
+    auto kern = sphere_tmem2_kernel<0>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int grid = h->num_sms * 2;
+    const int need = (h->batch / 2 + 3) / 4;
+    if (grid > need) grid = need;
+    CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
+    CUDA_TRY(cudaEventRecord(h->ev0, st));
+    kern<<<grid, 256, smem, st>>>(P, o, h->d_counter);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->ev1, st));
+    h->launches += 1;
+    return RIPTRM_OK;
 }
 
 template <int MODE>
@@ -902,10 +1001,50 @@ __global__ void schedule_keys_kernel(const double* __restrict__ pause, float* ke
     idx[i] = i;
 }
 
+// the same per unit of two consecutive pairs (sphere_tmem2_kernel): the sum of the two pairs' work
+__global__ void schedule_unit_keys_kernel(const double* __restrict__ pause, float* keys, int* idx, int units) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= units) return;
+    const double* p0 = pause + (size_t)(2 * u) * kPauseFields;
+    const double* p1 = p0 + kPauseFields;
+    const double w0 = (p0[7] != 0.0) ? p0[3] + 2.0 * p0[2] : 0.0, w1 = (p1[7] != 0.0) ? p1[3] + 2.0 * p1[2] : 0.0;
+    keys[u] = (p0[7] != 0.0 || p1[7] != 0.0) ? (float)(w0 + w1) : -1.0f;
+    idx[u] = u;
+}
+
+// Fast lane of the last launch.  With 16 warps per SM a tCG iteration of one pair takes 2.4 us instead of 1.4 (1.0 with
+// one warp per scheduler), and the longest pairs of a batch (30-75 k iterations where the mean is 6 k) become its
+// critical path.  By outer iteration 20 they are at the head of the sorted list (the truly longest pair ranked 2-14 in six
+// batches; at 14 it can still rank 900th), with 80-90 % of their work ahead.  Their units are taken out of the main queue
+// and run by the one-warp-per-copy kernel on a few SMs of their own, one warp per scheduler, next to the main kernel.
+__global__ void hold_kernel(unsigned ns) {
+    const uint64_t t0 = global_timer_ns();
+    while (global_timer_ns() - t0 < ns) __nanosleep(1000);
+}
+
+__global__ void mark_fast_lane_kernel(const int* __restrict__ unit_order, int units, double* pause, int* fast_order) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= units) return;
+    for (int r = 0; r < 2; ++r) {
+        const int i = 2 * unit_order[j] + r;
+        if (pause[(size_t)i * kPauseFields + 7] == 1.0) pause[(size_t)i * kPauseFields + 7] = 2.0;
+        fast_order[2 * j + r] = i;   // finished pairs stay in the list and are skipped by the kernel
+    }
+}
+
+// two warps per copy of S when the initial points of an instance come in pairs (see sphere_tmem2_kernel)
+static bool sibling_units(const riptrm_handle* h) {
+    if (h->n != 50 || h->batch_z < 1 || getenv("RIPTRM_SPHERE_NO_TMEM") != nullptr || getenv("RIPTRM_SPHERE_NO_SIBLINGS") != nullptr)
+        return false;
+    const int ipp = h->batch / h->batch_z;
+    return ipp >= 2 && ipp % 2 == 0 && h->batch >= 2 * h->num_sms * 8;
+}
+
 template <int MODE>
 static int dispatch_sphere(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
     const int n = h->n;
     const bool no_tmem = getenv("RIPTRM_SPHERE_NO_TMEM") != nullptr;  // A/B switch (measurements, tests)
+    if (MODE == 0 && P.sibling_units) return launch_sphere_tmem2(h, P, o, st);
     if (n == 50 && !no_tmem) return launch_sphere_tmem<MODE>(h, P, o, st);      // the reference's dim, S in TMEM
     if (n == 50) return launch_sphere<2, MODE, 50>(h, P, o, st);  // the reference's dim (config_dataset.yaml:6)
     if (n <= 64) return launch_sphere<2, MODE, 0>(h, P, o, st);
@@ -1046,6 +1185,39 @@ static SmallParams small_params(const riptrm_handle* h) {
     return P;
 }
 
+static int launch_fast_lane(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
+    const int fast_units = 16;   // 32 pairs: 8 CTAs of the 4-warp kernel on 8 SMs of their own
+    if (h->lane_stream == nullptr) {
+        int lo = 0, hi = 0;   // highest priority: its CTAs are placed before the main kernel's when both are pending
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&h->lane_stream, cudaStreamNonBlocking, hi));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->lane_ev0, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->lane_ev1, cudaEventDisableTiming));
+        CUDA_TRY(cudaMalloc(&h->d_fast_order, 2 * fast_units * sizeof(int)));
+    }
+    mark_fast_lane_kernel<<<1, 32, 0, st>>>(h->d_order, fast_units, h->d_pause, h->d_fast_order);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemsetAsync(h->d_counter + 1, 0, sizeof(int), st));
+    CUDA_TRY(cudaEventRecord(h->lane_ev0, st));
+    CUDA_TRY(cudaStreamWaitEvent(h->lane_stream, h->lane_ev0, 0));
+    SphereParams F = P;
+    F.sibling_units = 0;
+    F.order = h->d_fast_order;
+    F.queue_len = 2 * fast_units;
+    // 150 KB of shared memory per CTA: no CTA of the main kernel (86 KB) fits next to it
+    const size_t smem = 150 * 1024;
+    auto kern = sphere_tmem_kernel<0>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    kern<<<(2 * fast_units + 3) / 4, 128, smem, h->lane_stream>>>(F, o, h->d_counter + 1);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->lane_ev1, h->lane_stream));
+    hold_kernel<<<1, 32, 0, st>>>(30000);   // the main kernel follows on `st` once the lane's CTAs have their SMs
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 3;
+    return RIPTRM_OK;
+}
+
 // One launch, or several with the pairs re-ordered in between (see solve_instance): every pair is advanced to outer
 // iteration s1, then -- longest first, by the work spent so far -- to s2, then to the end.  Bit-identical results either
 // way.  Work per pair varies 3-5x and is only partly predictable from its first iterations: on six 16384-pair batches of
@@ -1056,13 +1228,15 @@ static int solve_scheduled(riptrm_handle* h, SphereParams P, const DevOpts& o, c
     const int user = h->opts.schedule_split;  //: 0 auto, < 0 off, > 0 one split at that outer iteration
     const int maxiter = h->opts.maxiter;
     const int resident = h->num_sms * 10;
-    int splits[2] = {-1, -1};
+    P.sibling_units = sibling_units(h) ? 1 : 0;
+    int splits[3] = {-1, -1, -1};
     int nsplit = 0;
     if (user > 0 && user < maxiter) {
         splits[nsplit++] = user;
     } else if (user == 0 && h->batch > resident && maxiter > 12) {
         splits[nsplit++] = (4 * maxiter + 7) / 15;   // 8 of 30
         splits[nsplit++] = (7 * maxiter + 7) / 15;   // 14 of 30
+        if (P.sibling_units) splits[nsplit++] = (2 * maxiter) / 3;   // 20 of 30: the fast lane needs the late ranking
     }
     if (nsplit == 0) {
         P.order = nullptr;
@@ -1099,13 +1273,21 @@ static int solve_scheduled(riptrm_handle* h, SphereParams P, const DevOpts& o, c
         P.order = (phase == 0) ? nullptr : h->d_order;
         P.resume = (phase == 0) ? 0 : 1;
         P.pause_at = (phase < nsplit) ? splits[phase] : -1;
+        const bool lane = P.sibling_units && user == 0 && phase == nsplit && nsplit == 3 && getenv("RIPTRM_SPHERE_NO_FAST_LANE") == nullptr;
+        if (lane && (rc = launch_fast_lane(h, P, o, st))) break;
         if ((rc = dispatch_sphere<0>(h, P, o, st))) break;
+        if (lane && cudaStreamWaitEvent(st, h->lane_ev1, 0) != cudaSuccess) { rc = fail(RIPTRM_E_CUDA, "fast lane join failed"); break; }
+        if (lane) cudaEventRecord(h->ev1, st);   // the reported time ends when both kernels have
         if (phase == 0) std::swap(first_start, h->ev0);  // keep the start of the first launch: the reported time spans all
         if (phase < nsplit) {
-            schedule_keys_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(h->d_pause, h->d_keys, h->d_idx, (int)B);
+            const int items = P.sibling_units ? (int)(B / 2) : (int)B;
+            if (P.sibling_units)
+                schedule_unit_keys_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(h->d_pause, h->d_keys, h->d_idx, items);
+            else
+                schedule_keys_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(h->d_pause, h->d_keys, h->d_idx, items);
             if (cudaGetLastError() != cudaSuccess) { rc = fail(RIPTRM_E_CUDA, "schedule_keys_kernel launch failed"); break; }
             if (cub::DeviceRadixSort::SortPairsDescending(h->d_sort_tmp, h->sort_tmp_bytes, h->d_keys, h->d_keys_sorted,
-                                                          h->d_idx, h->d_order, (int)B, 0, 32, st) != cudaSuccess) {
+                                                          h->d_idx, h->d_order, items, 0, 32, st) != cudaSuccess) {
                 rc = fail(RIPTRM_E_CUDA, "radix sort of the schedule keys failed");
                 break;
             }

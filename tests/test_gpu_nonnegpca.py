@@ -298,3 +298,29 @@ def test_dataset_files_in_output_files_out(rb, datasets, tmp_path):
     assert int((log["inner_status"] == "converged").sum()) == 40
     assert abs(log["cost"].iloc[-1] - g["log"]["cost"][-1]) < REL_TOL * abs(g["log"]["cost"][-1])
     assert np.array_equal(np.loadtxt(path + "/RIPTRM_tCG_x.csv"), out.x)
+
+
+def test_two_warps_per_copy_of_S_is_bit_identical(rb, monkeypatch):
+    """Large batches whose instances come with an even number of initial points run two warps per TMEM copy of S
+    (sphere_tmem2_kernel, 16 warps per SM); RIPTRM_SPHERE_NO_SIBLINGS=1 selects the one-warp-per-copy kernel.  Same
+    arithmetic per pair: every output must be the same bits, with and without the re-sorting launches."""
+    inst, ipp = 1536, 2
+    Z, x0, y0 = rb.datagen.nonnegpca_sweep(500, inst, ipp)
+    res = {}
+    for split in (0, -1):
+        for sib in ("1", None):
+            if sib is None:
+                monkeypatch.delenv("RIPTRM_SPHERE_NO_SIBLINGS", raising=False)
+            else:
+                monkeypatch.setenv("RIPTRM_SPHERE_NO_SIBLINGS", sib)
+            opt = rb.options.default_option()
+            opt.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=30, inner_maxiter=1000, tolresid=0, maxtime=1e9,
+                       schedule_split=split)
+            bs = rb.BatchSolver.nonnegpca_from_arrays(Z, x0, y0)
+            bs.set_options(opt, 0, 0)
+            res[(split, sib)] = bs.solve()
+            bs.close()
+    ref = res[(-1, "1")]
+    for key, (x, y, sm, _) in res.items():
+        assert np.array_equal(x, ref[0]) and np.array_equal(y, ref[1]) and np.array_equal(sm[:, :15], ref[2][:, :15]), key
+    assert (ref[2][:, rb._lib.SM["residual"]] < 1e-8).all()
