@@ -113,8 +113,9 @@ typedef struct {
     int32_t schedule_split;             /* not a reference key.  Batches larger than the GPU's resident capacity are solved
                                            in several launches: every pair is advanced to an outer iteration, the pairs are
                                            sorted by work so far, and the remainder runs longest first.  Results are
-                                           bit-identical either way.  0 = automatic (two splits, at 4/15 and 7/15 of
-                                           maxiter), k > 0 = one split at outer iteration k, < 0 = single launch */
+                                           bit-identical either way.  0 = automatic (splits at 4/15 and 7/15 of maxiter, and
+                                           at 2/3 where two warps share a copy of S), k > 0 = one split at outer
+                                           iteration k, < 0 = single launch */
     double tolresid;                    /* 'tolresid' */
     double maxtime;                     /* 'maxtime' seconds, measured on the device clock */
     double inner_maxtime;               /* 'inner_maxtime'; < 0 == None */

@@ -1186,14 +1186,15 @@ static SmallParams small_params(const riptrm_handle* h) {
 }
 
 static int launch_fast_lane(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
-    const int fast_units = 16;   // 32 pairs: 8 CTAs of the 4-warp kernel on 8 SMs of their own
+    int fast_units = 16;   // 32 pairs: 8 CTAs of the 4-warp kernel on 8 SMs of their own
+    if (const char* e = getenv("RIPTRM_FAST_UNITS")) fast_units = std::max(1, std::min(64, atoi(e)));   // tuning knob
     if (h->lane_stream == nullptr) {
         int lo = 0, hi = 0;   // highest priority: its CTAs are placed before the main kernel's when both are pending
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CUDA_TRY(cudaStreamCreateWithPriority(&h->lane_stream, cudaStreamNonBlocking, hi));
         CUDA_TRY(cudaEventCreateWithFlags(&h->lane_ev0, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&h->lane_ev1, cudaEventDisableTiming));
-        CUDA_TRY(cudaMalloc(&h->d_fast_order, 2 * fast_units * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&h->d_fast_order, 2 * 64 * sizeof(int)));
     }
     mark_fast_lane_kernel<<<1, 32, 0, st>>>(h->d_order, fast_units, h->d_pause, h->d_fast_order);
     CUDA_TRY(cudaGetLastError());
@@ -1237,6 +1238,15 @@ static int solve_scheduled(riptrm_handle* h, SphereParams P, const DevOpts& o, c
         splits[nsplit++] = (4 * maxiter + 7) / 15;   // 8 of 30
         splits[nsplit++] = (7 * maxiter + 7) / 15;   // 14 of 30
         if (P.sibling_units) splits[nsplit++] = (2 * maxiter) / 3;   // 20 of 30: the fast lane needs the late ranking
+        if (const char* e = getenv("RIPTRM_SPLITS")) {   // tuning knob: up to three comma-separated outer iterations
+            nsplit = 0;
+            for (const char* c = e; *c != 0 && nsplit < 3;) {
+                const int v = atoi(c);
+                if (v > 0 && v < maxiter) splits[nsplit++] = v;
+                while (*c != 0 && *c != ',') ++c;
+                if (*c == ',') ++c;
+            }
+        }
     }
     if (nsplit == 0) {
         P.order = nullptr;
@@ -1273,7 +1283,8 @@ static int solve_scheduled(riptrm_handle* h, SphereParams P, const DevOpts& o, c
         P.order = (phase == 0) ? nullptr : h->d_order;
         P.resume = (phase == 0) ? 0 : 1;
         P.pause_at = (phase < nsplit) ? splits[phase] : -1;
-        const bool lane = P.sibling_units && user == 0 && phase == nsplit && nsplit == 3 && getenv("RIPTRM_SPHERE_NO_FAST_LANE") == nullptr;
+        const bool lane = P.sibling_units && user == 0 && phase == nsplit && nsplit >= 1 && splits[nsplit - 1] * 3 >= maxiter * 2 - 2 &&
+                          getenv("RIPTRM_SPHERE_NO_FAST_LANE") == nullptr;   // needs the ranking of outer iteration ~ 2/3 maxiter
         if (lane && (rc = launch_fast_lane(h, P, o, st))) break;
         if ((rc = dispatch_sphere<0>(h, P, o, st))) break;
         if (lane && cudaStreamWaitEvent(st, h->lane_ev1, 0) != cudaSuccess) { rc = fail(RIPTRM_E_CUDA, "fast lane join failed"); break; }
