@@ -307,7 +307,7 @@ def test_two_warps_per_copy_of_S_is_bit_identical(rb, monkeypatch):
     inst, ipp = 1536, 2
     Z, x0, y0 = rb.datagen.nonnegpca_sweep(500, inst, ipp)
     res = {}
-    for split in (0, -1):
+    for split in (0, -1, 5):    # automatic (three re-sorts + fast lane), single launch, one re-sort at outer iteration 5
         for sib in ("1", None):
             if sib is None:
                 monkeypatch.delenv("RIPTRM_SPHERE_NO_SIBLINGS", raising=False)
