@@ -136,16 +136,30 @@ struct StableIdFam {
         __syncwarp();
     }
     // op(A) op(B) for d x d lane matrices.  Out of line (see smallmat.cuh): called from ~150 sites of the solve.
+    template <bool TA, bool TB>
+    static __device__ __forceinline__ double dot5(const double* A, const double* B, int i, int j) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) s = fma(TA ? A[k * 5 + i] : A[i * 5 + k], TB ? B[j * 5 + k] : B[k * 5 + j], s);
+        return s;
+    }
     static __device__ __noinline__ LM mul_impl(double* sc, int d, LM a, LM b, bool tA, bool tB) {
         const int l = lane_id();
         sc[l] = a;
         sc[32 + l] = b;
         __syncwarp();
         double s = 0.0;
-        if (l < d * d) {
+        const double* A = sc;
+        const double* B = sc + 32;
+        if (d == 5) {
+            // the reference's dimension: unrolled, same order of additions as the loop below
+            if (l < 25) {
+                const int i = l / 5, j = l - i * 5;
+                s = tA ? (tB ? dot5<true, true>(A, B, i, j) : dot5<true, false>(A, B, i, j))
+                       : (tB ? dot5<false, true>(A, B, i, j) : dot5<false, false>(A, B, i, j));
+            }
+        } else if (l < d * d) {
             const int i = l / d, j = l - i * d;
-            const double* A = sc;
-            const double* B = sc + 32;
             for (int k = 0; k < d; ++k) s = fma(tA ? A[k * d + i] : A[i * d + k], tB ? B[j * d + k] : B[k * d + j], s);
         }
         __syncwarp();
