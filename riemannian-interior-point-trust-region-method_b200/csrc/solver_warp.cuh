@@ -140,11 +140,13 @@ struct EvalRow {
 
 template <class F>
 __device__ __forceinline__ EvalRow evaluate(const typename F::Ctx& ctx, const typename F::Pt& pt,
-                                            const typename F::CVec& y, const typename F::Vec& xPrev) {
+                                            const typename F::CVec& y, const typename F::Vec& xPrev, bool want_distance = true) {
     constexpr int MK = F::MK;
     EvalRow ev;
     ev.cost = pt.cost;
-    ev.distance = F::dist(ctx, xPrev, pt);
+    // `distance` only goes to the log; without a trace the SPD / Grassmann geodesic distance (two Jacobi eigen-solves per
+    // component: a fifth of the StableIdentification kernel's instructions) is not computed
+    ev.distance = want_distance ? F::dist(ctx, xPrev, pt) : 0.0;
     ev.gradnorm = F::gradL_norm(ctx, pt, y);
     double p_compl = 0.0, p_nonneg = 0.0, p_ineq = 0.0, p_sum = 0.0, p_max = 0.0;
 #pragma unroll
@@ -417,7 +419,7 @@ __device__ __forceinline__ void solve_instance(const typename F::Ctx& ctx, const
     bool skip_top = resume;
     while (true) {                                                  // :931
         if (!skip_top) {
-            ev = evaluate<F>(ctx, pt, y, xPrev);                    // :933
+            ev = evaluate<F>(ctx, pt, y, xPrev, trace != nullptr && o.trace_mode != 0);   // :933
             if (o.trace_mode != 0 && (it == 0 || o.trace_mode == 2)) {  // :936-941
                 if (trace != nullptr && rows < o.trace_capacity)
                     write_trace_row(trace + (size_t)rows * RIPTRM_TRACE_FIELDS, it, mu, info, max_abs_mult<F>(ctx, y),
