@@ -69,13 +69,6 @@ __device__ __forceinline__ double colsum(const double* tot, int q) {
     for (int c = 1; c < P; ++c) s = s + tot[q * P + c];
     return s;
 }
-template <int P>
-__device__ __forceinline__ double colmin(const double* tot, int q) {
-    double s = tot[q * P];
-#pragma unroll
-    for (int c = 1; c < P; ++c) s = fmin(s, tot[q * P + c]);
-    return s;
-}
 
 // acc[a] += xrow[a] * val: column c of X'U accumulated by the thread that owns U[row, c]
 template <int P>
