@@ -283,6 +283,11 @@ static void free_dev(double*& p) {
     if (p) cudaFree(p);
     p = nullptr;
 }
+template <class T>
+static void free_any(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
 
 extern "C" int riptrm_destroy(riptrm_handle* h) {
     if (h == nullptr) return RIPTRM_OK;
@@ -301,14 +306,14 @@ extern "C" int riptrm_destroy(riptrm_handle* h) {
     free_dev(h->d_colbuf);
     free_dev(h->d_pause);
     free_dev(h->d_sid);
-    if (h->d_keys) cudaFree(h->d_keys);
-    if (h->d_keys_sorted) cudaFree(h->d_keys_sorted);
-    if (h->d_idx) cudaFree(h->d_idx);
-    if (h->d_order) cudaFree(h->d_order);
-    if (h->d_sort_tmp) cudaFree(h->d_sort_tmp);
-    if (h->d_passes) cudaFree(h->d_passes);
-    if (h->d_counter) cudaFree(h->d_counter);
-    if (h->d_fast_order) cudaFree(h->d_fast_order);
+    free_any(h->d_keys);
+    free_any(h->d_keys_sorted);
+    free_any(h->d_idx);
+    free_any(h->d_order);
+    free_any(h->d_sort_tmp);
+    free_any(h->d_passes);
+    free_any(h->d_counter);
+    free_any(h->d_fast_order);
     if (h->lane_stream) cudaStreamDestroy(h->lane_stream);
     if (h->lane_ev0) cudaEventDestroy(h->lane_ev0);
     if (h->lane_ev1) cudaEventDestroy(h->lane_ev1);
@@ -352,26 +357,31 @@ static int columns_setup(riptrm_handle* h, const double* Z, double eps, int wher
     free_dev(h->dS);
     free_dev(h->d_colbuf);
     free_dev(h->d_pause);
-    if (h->d_keys) cudaFree(h->d_keys);
-    if (h->d_keys_sorted) cudaFree(h->d_keys_sorted);
-    if (h->d_idx) cudaFree(h->d_idx);
-    if (h->d_order) cudaFree(h->d_order);
-    if (h->d_sort_tmp) cudaFree(h->d_sort_tmp);
+    free_any(h->d_keys);
+    free_any(h->d_keys_sorted);
+    free_any(h->d_idx);
+    free_any(h->d_order);
+    free_any(h->d_sort_tmp);
     CUDA_TRY(cudaMalloc(&h->dS, sbytes));
     CUDA_TRY(cudaMemset(h->dS, 0, sbytes));
     const double* dZ = Z;
     double* tmpZ = nullptr;
     if (where != RIPTRM_DEVICE) {
         CUDA_TRY(cudaMalloc(&tmpZ, (size_t)n * n * sizeof(double)));
-        CUDA_TRY(cudaMemcpy(tmpZ, Z, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice));
+        const cudaError_t ce = cudaMemcpy(tmpZ, Z, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice);
+        if (ce != cudaSuccess) {
+            cudaFree(tmpZ);
+            return fail(RIPTRM_E_CUDA, std::string("cudaMemcpy(Z): ") + cudaGetErrorString(ce));
+        }
         dZ = tmpZ;
     }
     dim3 grid((n + 31) / 32, (n + 31) / 32), block(32, 8);
     col::build_S_kernel<<<grid, block>>>(dZ, h->dS, n, h->n_pad / col::TJ, h->colP >= 8 ? 1 : 0);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaDeviceSynchronize());
-    h->launches += 1;
+    cudaError_t be = cudaGetLastError();
+    if (be == cudaSuccess) be = cudaDeviceSynchronize();
     if (tmpZ) cudaFree(tmpZ);
+    if (be != cudaSuccess) return fail(RIPTRM_E_CUDA, std::string("build_S_kernel: ") + cudaGetErrorString(be));
+    h->launches += 1;
     const size_t arr = (size_t)h->n_pad * h->colP;
     const size_t mv = (size_t)h->col_grid * h->col_slots * col::TW * h->colP;
     const size_t dots = (size_t)2 * h->col_grid * stf::DOT_STRIDE;
@@ -1188,6 +1198,7 @@ static SmallParams small_params(const riptrm_handle* h) {
 static int launch_fast_lane(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
     int fast_units = 16;   // 32 pairs: 8 CTAs of the 4-warp kernel on 8 SMs of their own
     if (const char* e = getenv("RIPTRM_FAST_UNITS")) fast_units = std::max(1, std::min(64, atoi(e)));   // tuning knob
+    fast_units = std::min(fast_units, h->batch / 2);
     if (h->lane_stream == nullptr) {
         int lo = 0, hi = 0;   // highest priority: its CTAs are placed before the main kernel's when both are pending
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -1196,7 +1207,7 @@ static int launch_fast_lane(riptrm_handle* h, const SphereParams& P, const DevOp
         CUDA_TRY(cudaEventCreateWithFlags(&h->lane_ev1, cudaEventDisableTiming));
         CUDA_TRY(cudaMalloc(&h->d_fast_order, 2 * 64 * sizeof(int)));
     }
-    mark_fast_lane_kernel<<<1, 32, 0, st>>>(h->d_order, fast_units, h->d_pause, h->d_fast_order);
+    mark_fast_lane_kernel<<<(fast_units + 31) / 32, 32, 0, st>>>(h->d_order, fast_units, h->d_pause, h->d_fast_order);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemsetAsync(h->d_counter + 1, 0, sizeof(int), st));
     CUDA_TRY(cudaEventRecord(h->lane_ev0, st));
@@ -1277,6 +1288,7 @@ static int solve_scheduled(riptrm_handle* h, SphereParams P, const DevOpts& o, c
         P.y = h->d_y;
     }
     cudaEvent_t first_start = nullptr;
+    bool swapped = false;
     CUDA_TRY(cudaEventCreateWithFlags(&first_start, cudaEventDefault));
     P.pause = h->d_pause;
     for (int phase = 0; phase <= nsplit; ++phase) {
@@ -1289,7 +1301,10 @@ static int solve_scheduled(riptrm_handle* h, SphereParams P, const DevOpts& o, c
         if ((rc = dispatch_sphere<0>(h, P, o, st))) break;
         if (lane && cudaStreamWaitEvent(st, h->lane_ev1, 0) != cudaSuccess) { rc = fail(RIPTRM_E_CUDA, "fast lane join failed"); break; }
         if (lane) cudaEventRecord(h->ev1, st);   // the reported time ends when both kernels have
-        if (phase == 0) std::swap(first_start, h->ev0);  // keep the start of the first launch: the reported time spans all
+        if (phase == 0) {   // keep the start of the first launch: the reported time spans all
+            std::swap(first_start, h->ev0);
+            swapped = true;
+        }
         if (phase < nsplit) {
             const int items = P.sibling_units ? (int)(B / 2) : (int)B;
             if (P.sibling_units)
@@ -1305,7 +1320,7 @@ static int solve_scheduled(riptrm_handle* h, SphereParams P, const DevOpts& o, c
             h->launches += 2;
         }
     }
-    std::swap(first_start, h->ev0);   // ev0 = start of the first launch again; ev1 was recorded by the last one
+    if (swapped) std::swap(first_start, h->ev0);   // ev0 = start of the first launch again; ev1 was recorded by the last one
     cudaEventDestroy(first_start);
     return rc;
 }

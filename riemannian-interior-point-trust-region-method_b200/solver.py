@@ -52,6 +52,31 @@ class _Handle:
             pass
 
 
+def validate_batch(structures):
+    """A batch is (instance, initialpoint) pairs of ONE family and shape.  NonnegPCA carries a data matrix per pair
+    (`riptrm_set_nonnegpca(batch_z)`); the Rosenbrock and StableIdentification handles bind ONE instance's data
+    (`riptrm_set_rosenbrock` / `riptrm_set_stableid`), so a batch of those is many initial points of one instance --
+    anything else raises instead of being solved against the first instance's data."""
+    st0 = structures[0]
+    for s in structures:
+        if s.family != st0.family or s.shape != st0.shape:
+            raise ValueError("a batch must hold problems of one family and one shape")
+    if st0.family == _lib.FAMILY_NONNEGPCA_SPHERE:
+        if any(s.eps != st0.eps for s in structures):
+            raise ValueError("one eps per batch")
+    elif st0.family == _lib.FAMILY_ROSENBROCK_GRASSMANN:
+        if any(s.alpha != st0.alpha or s.offset != st0.offset for s in structures):
+            raise ValueError("Rosenbrock batch: one instance (alpha, offset) per batch -- solve other instances in "
+                             "their own batch")
+    elif st0.family == _lib.FAMILY_STABLEID_PRODUCT:
+        for s in structures[1:]:
+            same = s.h == st0.h and all(a is b or np.array_equal(a, b) for a, b in
+                                        ((s.X, st0.X), (s.XP, st0.XP), (s.conspec, st0.conspec)))
+            if not same:
+                raise ValueError("StableIdentification batch: one instance (X, XP, h, conspec) per batch -- solve "
+                                 "other instances in their own batch")
+
+
 class BatchSolver:
     """A device-resident batch of same-shaped problems of one family (the C-ABI handle plus the
     marshalling of problem data).  This is the object bench.py and the parity tests drive."""
@@ -63,9 +88,7 @@ class BatchSolver:
         self.n, self.p, self.m = st0.shape
         self.batch = len(structures)
         self.device = device
-        for s in structures:
-            if s.family != self.family or s.shape != st0.shape:
-                raise ValueError("a batch must hold problems of one family and one shape")
+        validate_batch(structures)
         self.handle = _Handle(self.family, self.n, self.p, self.m, self.batch, device)
         self.lib = self.handle.lib
         self._keep = []
@@ -82,8 +105,6 @@ class BatchSolver:
             Zs = [s.Z for s in self.structures]
             shared = all(z is Zs[0] for z in Zs)
             Z = np.ascontiguousarray(Zs[0][None] if shared else np.stack(Zs), dtype=np.float64)
-            if any(s.eps != st0.eps for s in self.structures):
-                raise ValueError("one eps per batch")
             _lib.check(self.lib.riptrm_set_nonnegpca(h, _lib.ptr(Z), Z.shape[0], float(st0.eps), _lib.HOST))
         elif self.family == _lib.FAMILY_ROSENBROCK_GRASSMANN:
             _lib.check(self.lib.riptrm_set_rosenbrock(h, float(st0.alpha), float(st0.offset)))
@@ -471,6 +492,79 @@ def _stop_message(summary, option, run_time):
     return f"stopped ({reason}) after {run_time:.2f} seconds"
 
 
+def builtin_manvio(st, x):
+    """The manifold-violation measures the kernels evaluate (`F::manvio`), restated on the host: they are the
+    `manviofun`s the reference's three simulators install (src/NonnegPCA/simulator.py:12-14,
+    src/Rosenbrock/simulator.py:107-114, src/StableIdentification/simulator.py:11-33)."""
+    if st.family == _lib.FAMILY_NONNEGPCA_SPHERE:
+        return float(np.linalg.norm(x) - 1)
+    if st.family == _lib.FAMILY_ROSENBROCK_GRASSMANN:
+        return 0.0 if np.linalg.matrix_rank(x) == st.k else float("inf")
+    if st.family == _lib.FAMILY_STABLEID_PRODUCT:
+        J, R, Q = x
+        v = np.linalg.norm(J + J.T) + np.linalg.norm(R - R.T) + np.linalg.norm(Q - Q.T)
+        if not (np.all(np.linalg.eigvalsh(R) > 0) and np.all(np.linalg.eigvalsh(Q) > 0)):
+            v = float("inf")
+        return float(v)
+    return 0.0
+
+
+def _off_manifold_probe(st, x0):
+    if st.family == _lib.FAMILY_NONNEGPCA_SPHERE:
+        return 1.25 * np.asarray(x0)
+    if st.family == _lib.FAMILY_ROSENBROCK_GRASSMANN:
+        x = np.array(x0, dtype=float)
+        x[:, -1] = x[:, 0]          # rank deficient
+        return x
+    if st.family == _lib.FAMILY_STABLEID_PRODUCT:
+        J, R, Q = (np.array(a, dtype=float) for a in x0)
+        J[0, 1] += 0.5
+        R[0, 1] += 0.25
+        return [J, R, Q]
+    return x0
+
+
+def check_user_functions(option, problem, st, log):
+    """`manviofun` / `callbackfun` are Python callables evaluated per logged row by the reference (utils.py:342-368).
+    The device evaluates a fixed `manviofun` per family and no callback, so a caller's functions are checked against that,
+    loudly: a `manviofun` that is neither the class default (identically 0; differs from the built-in by rounding noise on
+    the manifold) nor equal to the family's built-in raises; a `callbackfun` that adds or changes log columns is reported
+    with a warning naming the columns.  Returns the list of log columns the callback would have added."""
+    manviofun, callbackfun = option.get("manviofun"), option.get("callbackfun")
+    x0 = problem.initialpoint
+    if manviofun is not None:
+        for x in (x0, _off_manifold_probe(st, x0)):
+            try:
+                user = float(manviofun(problem, x))
+            except Exception as e:     # a function that needs state the probe point lacks: cannot be validated
+                raise NotImplementedError(f"option['manviofun'] failed on a probe point ({type(e).__name__}: {e}); the GPU "
+                                          "path evaluates the family's built-in manifold violation") from e
+            ours = builtin_manvio(st, x)
+            same = (user == ours) or (math.isfinite(user) and math.isfinite(ours) and abs(user - ours) <= 1e-12 * max(1.0, abs(ours)))
+            if not same and user != 0.0:
+                raise NotImplementedError(
+                    f"option['manviofun'] returns {user!r} where the kernel family's built-in manifold violation is {ours!r}: "
+                    "the GPU path cannot evaluate a Python manviofun per logged row (see INTEGRATION.md); there is no CPU fallback")
+    dropped = []
+    if callbackfun is not None and log is not None and len(log.get("iteration", [])) > 0:
+        ev = {c: log[c][0] for c in _EVAL_COLS}
+        try:
+            got = callbackfun(problem, x0, np.asarray(problem.initialineqLagmult, dtype=float), [], dict(ev))
+        except Exception as e:
+            got = None
+            warnings.warn(f"option['callbackfun'] failed on the initial point ({type(e).__name__}: {e}); the GPU path does not "
+                          "evaluate callbacks", RuntimeWarning)
+        if isinstance(got, dict):
+            dropped = [k for k in got if k not in ev]
+            changed = [k for k in ev if k in got and not (got[k] == ev[k] or (got[k] != got[k] and ev[k] != ev[k]))]
+            if dropped or changed:
+                warnings.warn("option['callbackfun'] adds / rewrites log columns "
+                              f"{dropped + changed}; the GPU path logs the reference's evaluation columns only (the callback "
+                              "is logging-only in the reference, iterates are unaffected); see INTEGRATION.md", RuntimeWarning)
+            dropped = dropped + changed
+    return dropped
+
+
 class RIPTRM:
     """Drop-in for the reference's `RIPTRM` class on the tCG path (src/solver/RIPTRM.py:302-976)."""
 
@@ -502,6 +596,10 @@ class RIPTRM:
                                    np.asarray(st.y0, dtype=np.float64).reshape(st.x0.shape), eps=st.eps)
         else:
             out = self.run_batch([problem], structures=[st])[0]
+        if st is not problem and hasattr(problem, "initialpoint") and st.family != _lib.FAMILY_NONNEGPCA_STIEFEL:
+            dropped = check_user_functions(self.option, problem, st, out.log)
+            if dropped:
+                out.option["riptrm_b200_missing_log_columns"] = dropped
         self.log = out.log
         return out
 
