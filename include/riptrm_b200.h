@@ -232,6 +232,13 @@ int64_t riptrm_matvec_passes(riptrm_handle* h);
  * recorded around the launch); blocks until that kernel has finished */
 double riptrm_last_kernel_ms(riptrm_handle* h);
 
+/* ---- measurement utility (no reference counterpart) -------------------------------------------------------------------
+ * FP64 arithmetic peaks of `device`, measured by saturating micro-kernels (csrc/peaks.cuh): out[0] = DFMA TFLOP/s (the FP64
+ * vector pipe the whole-solve kernels run on), out[1] = DMMA TFLOP/s (mma.sync.m8n8k4.f64, the tensor path of the COLUMNS /
+ * STIEFEL consumers).  Best of `repeats` launches of about `ms_target` ms each, CUDA events on `stream`.  bench.py uses them
+ * as the denominators of `step_roofline` (MEASURED_PEAKS.json has no fp64 figure; the data sheet's 40 TFLOP/s is nominal). */
+int riptrm_measure_fp64_peaks(int device, double ms_target, int repeats, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,7 @@ SYMBOLS = {
     "riptrm_launch_count": (C.c_int64, [C.c_void_p]),
     "riptrm_matvec_passes": (C.c_int64, [C.c_void_p]),
     "riptrm_last_kernel_ms": (C.c_double, [C.c_void_p]),
+    "riptrm_measure_fp64_peaks": (C.c_int, [C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 
@@ -99,6 +100,14 @@ def load_library():
         raise RiptrmError("libriptrm_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib
+
+
+def measure_fp64_peaks(device=0, ms_target=20.0, repeats=3, stream=None):
+    """(DFMA TFLOP/s, DMMA TFLOP/s) measured on `device` by the library's saturating micro-kernels."""
+    out = (C.c_double * 2)()
+    check(load_library().riptrm_measure_fp64_peaks(int(device), float(ms_target), int(repeats), out,
+                                                   C.c_void_p(stream) if stream else None))
+    return float(out[0]), float(out[1])
 
 
 def check(rc):

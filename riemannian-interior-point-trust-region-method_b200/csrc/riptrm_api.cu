@@ -23,6 +23,7 @@
 #include "fam_grassmann.cuh"
 #include "fam_sphere.cuh"
 #include "fam_stableid.cuh"
+#include "peaks.cuh"
 
 using namespace riptrm;
 
@@ -1481,4 +1482,52 @@ extern "C" double riptrm_last_kernel_ms(riptrm_handle* h) {
     if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0;
     h->last_ms = ms;
     return h->last_ms;
+}
+
+
+// Measured FP64 peaks (peaks.cuh): out[0] = DFMA TFLOP/s (vector pipe), out[1] = DMMA TFLOP/s (mma.sync m8n8k4 f64), each the
+// best of `repeats` launches of ~`ms_target` ms timed with CUDA events on `stream`.
+extern "C" int riptrm_measure_fp64_peaks(int device, double ms_target, int repeats, double* out, void* stream) {
+    if (out == nullptr || repeats < 1 || !(ms_target > 0.0)) return fail(RIPTRM_E_INVALID, "measure_fp64_peaks: bad argument");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    cudaStream_t st = (cudaStream_t)stream;
+    double* sink = nullptr;
+    CUDA_TRY(cudaMalloc(&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int grid = prop.multiProcessorCount * 4, block = 256;
+    int rc = RIPTRM_OK;
+    for (int which = 0; which < 2 && rc == RIPTRM_OK; ++which) {
+        // flops per repetition of the kernel's outer loop, whole grid
+        const double flops_rep = (which == 0)
+            ? 2.0 * peaks::kChains * peaks::kUnroll * (double)grid * block
+            : 2.0 * 8 * 8 * 4 * 4 * peaks::kUnroll * (double)grid * (block / 32);
+        int reps = 64;
+        double best = 0.0;
+        for (int it = 0; it < repeats + 2; ++it) {   // two calibration rounds size `reps` for ms_target
+            cudaEventRecord(e0, st);
+            if (which == 0) peaks::dfma_kernel<<<grid, block, 0, st>>>(sink, reps, 0.999999, 1e-9);
+            else peaks::dmma_kernel<<<grid, block, 0, st>>>(sink, reps, 0.999999, 1e-9);
+            cudaEventRecord(e1, st);
+            if (cudaEventSynchronize(e1) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+                rc = fail(RIPTRM_E_CUDA, "measure_fp64_peaks: kernel failed");
+                break;
+            }
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (it < 2) {
+                reps = (int)fmin(1e6, fmax(16.0, reps * ms_target / fmax(ms, 1e-3)));
+            } else {
+                best = fmax(best, flops_rep * reps / (ms * 1e-3) / 1e12);
+            }
+        }
+        out[which] = best;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return rc;
 }

@@ -26,7 +26,18 @@ CASES = {
     "stableid_1_a_K25": ("StableIdentification", {"solver_option.common.maxiter": 25, "problem_initialpoint": "a"}),
     "stableid_1_b_K25": ("StableIdentification", {"solver_option.common.maxiter": 25, "problem_initialpoint": "b"}),
     "stableid_1_t_K25": ("StableIdentification", {"solver_option.common.maxiter": 25, "problem_initialpoint": "t"}),
+    # round 2: a converged Rosenbrock run (the reference reaches cost 4.0000009514e7 by outer iteration 14) ...
+    "rosenbrock_K14": ("Rosenbrock", {"solver_option.common.maxiter": 14}),
+    "rosenbrock_K20": ("Rosenbrock", {"solver_option.common.maxiter": 20, "solver_option.RIPTRM.inner_maxiter": 2000}),
 }
+# ... and all 20 initial points of StableIdentification instance 1 (dataset/StableIdentification/1/
+# init{J,R,Q}_{a..t}.csv) at 30 outer iterations (mu = 3.9e-12: the identified quantity A = (J-R)Q is converged to
+# ~1e-10 there; at 25 it still moves by 1e-7), stored reduced: row 0 and the rows that end an outer iteration
+for _pt in "abcdefghijklmnopqrst":
+    CASES[f"stableid_1_{_pt}_K30"] = ("StableIdentification", {"solver_option.common.maxiter": 30,
+                                                                 "solver_option.RIPTRM.inner_maxiter": 1000,
+                                                                 "problem_initialpoint": _pt})
+REDUCED = {"rosenbrock_K14", "rosenbrock_K20"} | {f"stableid_1_{_pt}_K30" for _pt in "abcdefghijklmnopqrst"}
 # columns whose values depend on the reference's unseeded RNG (Rosenbrock callback,
 # src/Rosenbrock/simulator.py:52-57) or on wall-clock
 SKIP_COLUMNS = ("time", "second_order_residual", "condition_number")
@@ -57,6 +68,19 @@ def run_case(name):
     overrides.update(ov)
     out, tcg, _ = run_reference(problem, overrides)
     log = {k: _jsonable(v) for k, v in out.log.items() if k not in SKIP_COLUMNS}
+    rows_total = len(log["iteration"])
+    inner_per_outer = None
+    if name in REDUCED:
+        # per-outer-iteration records only: row 0 + the last row of every outer iteration (`converged`, or the row at
+        # which an inner run hit its cap); the number of trust-region iterations and tCG iterations per outer iteration
+        # are kept as counts
+        it = log["iteration"]
+        keep = [0] + [i for i in range(1, rows_total) if i + 1 == rows_total or it[i + 1] != it[i]]
+        K = max(it)
+        inner_per_outer = [sum(1 for i in range(1, rows_total) if it[i] == k) for k in range(1, K + 1)]
+        tcg_per_outer = [sum(tcg[i - 1] for i in range(1, rows_total) if it[i] == k) for k in range(1, K + 1)]
+        log = {k: [v[i] for i in keep] for k, v in log.items()}
+        tcg = tcg_per_outer
     doc = {
         "case": name,
         "problem": problem,
@@ -67,6 +91,9 @@ def run_case(name):
         "x": _jsonable(out.x),
         "ineqLagmult": _jsonable(out.ineqLagmult),
         "tcg_iters": tcg,
+        "rows_total": rows_total,
+        "inner_per_outer": inner_per_outer,
+        "reduced": name in REDUCED,
         "log": log,
     }
     with open(os.path.join(HERE, f"{name}.json"), "w") as f:

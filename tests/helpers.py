@@ -167,3 +167,45 @@ def device_generator_twin(inst, n, points, snr=0.5, delta=0.7):
             s = s + val * val
         x0[pt] = np.abs(u / np.sqrt(s))
     return Z, x0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# per-outer-iteration view of a log (profiles/parity_r02.md, tests/test_parity_report.py)
+# ----------------------------------------------------------------------------------------------------------------
+def per_outer(log, tcg=None):
+    """Aggregates a per-inner-iteration log (SURVEY.md App. E layout: row 0 + one row per trust-region iteration,
+    `iteration` = outer index) into per-outer-iteration arrays: trust-region iterations, tCG iterations, and the
+    last row's radius / cost / residual / status.  `tcg`: per-row tCG counts (`log['tcg_iters']` when absent)."""
+    it = np.array(log["iteration"], dtype=int)
+    if tcg is None:
+        tcg = log["tcg_iters"]
+    tcg = np.array([0 if v is None else v for v in tcg], dtype=float)
+    if len(tcg) == len(it) - 1:          # golden files keep one count per tCG call (no entry for row 0)
+        tcg = np.concatenate([[0.0], tcg])
+    K = int(it.max())
+    out = {k: [] for k in ("outer", "inner", "tcg", "radius", "cost", "residual", "mu", "status", "last_row")}
+    for k in range(1, K + 1):
+        rows = np.nonzero(it == k)[0]
+        rows = rows[rows > 0]
+        if len(rows) == 0:
+            continue
+        last = int(rows[-1])
+        out["outer"].append(k)
+        out["inner"].append(len(rows))
+        out["tcg"].append(float(tcg[rows].sum()))
+        out["radius"].append(float(log["TR_radius"][last]))
+        out["cost"].append(float(log["cost"][last]))
+        out["residual"].append(float(log["residual"][last]))
+        out["mu"].append(float(log["mu"][last]))
+        out["status"].append(log["inner_status"][last])
+        out["last_row"].append(last)
+    return {k: (np.array(v) if k not in ("status",) else v) for k, v in out.items()}
+
+
+def outer_window(a, b, key):
+    """Number of leading outer iterations for which per-outer arrays a[key] and b[key] are identical."""
+    n = min(len(a[key]), len(b[key]))
+    for i in range(n):
+        if a[key][i] != b[key][i]:
+            return i
+    return n

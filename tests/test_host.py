@@ -291,3 +291,17 @@ def test_package_import_does_not_need_torch():
             "import riptrm_b200 as rb; rb.RIPTRM({'TRS_solver': 'tCG'}); print('ok')")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-1000:]
+
+
+def test_standin_coordinator_problems_are_recognised(datasets):
+    """tests/dropin_standins.py (the caller side of the drop-in as the reference's coordinators write it, used by the GPU
+    drop-in test) yields problems whose structure is recovered from the closures alone."""
+    import dropin_standins as D
+    st = rb.structure_from_problem(D.build_problem("NonnegPCA", datasets))
+    assert isinstance(st, rb.NonnegPCAStructure) and np.array_equal(st.Z, datasets["NonnegPCA/1"]["Z"])
+    st = rb.structure_from_problem(D.build_problem("Rosenbrock", datasets))
+    assert isinstance(st, rb.RosenbrockStructure) and (st.alpha, st.offset, st.shape) == (1e7, 0.01, (5, 3, 15))
+    st = rb.structure_from_problem(D.build_problem("StableIdentification", datasets, "t"))
+    cs = rb.StableIdStructure.conspec_from_constset(datasets["StableIdentification/1"]["constset"])
+    assert isinstance(st, rb.StableIdStructure) and np.array_equal(st.conspec, cs) and st.X.shape == (5, 95)
+    assert np.array_equal(st.x0[2], datasets["StableIdentification/1"]["initQ_t"])
