@@ -599,7 +599,8 @@ class RIPTRM:
         if st is not problem and hasattr(problem, "initialpoint") and st.family != _lib.FAMILY_NONNEGPCA_STIEFEL:
             dropped = check_user_functions(self.option, problem, st, out.log)
             if dropped:
-                out.option["riptrm_b200_missing_log_columns"] = dropped
+                # a string, not a list: Simulator.save_output builds a one-row DataFrame from the option dict
+                out.option["riptrm_b200_missing_log_columns"] = ",".join(dropped)
         self.log = out.log
         return out
 

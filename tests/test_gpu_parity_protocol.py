@@ -41,8 +41,9 @@ def test_rosenbrock_end_of_protocol():
     assert s["final_cost_abs_diff"] < 1e-3                                              # 4e7 * 2.5e-11
     assert s["X_maxabs_diff"] < 2e-4                                                    # attainable: 4.7e-5 (see above)
     assert s["final_residual_here"] < 5e-7 and s["final_residual_ref"] < 5e-7
-    assert abs(s["inner_per_outer_here"][0] - s["inner_per_outer_ref"][0]) <= 40        # 333..350 trust-region iterations
-    assert abs(s["tcg_total_here"] - s["tcg_total_ref"]) < 0.25 * s["tcg_total_ref"]
+    assert abs(s["inner_per_outer_here"][0] - s["inner_per_outer_ref"][0]) <= 40        # 327 / 333 / 350 (GPU / NumPy / ref)
+    # later counts are not comparable: at mu < 1e-6 an inner run takes 4..1000 trust-region iterations depending on
+    # rounding in ALL three implementations (GPU 1033 at outer 20, reference 204 at 17, NumPy oracle 302 at 20)
 
 
 def test_stableid_all_twenty_initial_points_end_of_protocol():
