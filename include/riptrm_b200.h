@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RIPTRM_ABI_VERSION 1
+#define RIPTRM_ABI_VERSION 2
 
 /* memory space of a pointer argument */
 #define RIPTRM_HOST 0
@@ -70,6 +70,21 @@ typedef enum {
     RIPTRM_TCG_REACHED_TARGET_SUPERLINEAR = 5
 } riptrm_tcg_stop;
 
+/* dxtype of the exact trust-region solver -- the `type` string TRSgep returns (RIPTRM.py:262, :271, :280, :298), stored in
+ * the same trace field as the tCG stop reasons */
+typedef enum {
+    RIPTRM_TRS_BOUNDARY = 6,
+    RIPTRM_TRS_INTERIOR = 7,
+    RIPTRM_TRS_HARDCASE_1 = 8,
+    RIPTRM_TRS_HARDCASE_3 = 9,
+    RIPTRM_TRS_HARDCASE_6 = 10,
+    RIPTRM_TRS_HARDCASE_9 = 11
+} riptrm_trs_type;
+
+/* 'TRS_solver' (RIPTRM.py:323, :431, :445) */
+#define RIPTRM_TRS_SOLVER_TCG 0
+#define RIPTRM_TRS_SOLVER_EXACT_REPMAT 1
+
 /* inner_status -- RIPTRM.py:763,770,678,698,829,837 */
 typedef enum {
     RIPTRM_INNER_NONE = 0,
@@ -98,7 +113,7 @@ typedef enum {
     RIPTRM_STOP_NUMERICAL = 4 /* non-finite state; the reference would raise inside outer_step (:961-966) */
 } riptrm_stop_reason;
 
-/* Solver options: the numeric keys of RIPTRM.py:305-358 (tCG path).  The callable keys
+/* Solver options: the numeric keys of RIPTRM.py:305-358.  The callable keys
  * (forcing_function_*, barrier update rule :890-893) are evaluated by the host into the
  * per-outer-iteration schedules below, so any Python callable remains usable. */
 typedef struct {
@@ -135,11 +150,19 @@ typedef struct {
     const double* mu_sched;
     const double* tol_lagrangian_sched;
     const double* tol_complementarity_sched;
+    /* ---- ABI 2: the exact trust-region solver on the representation matrix (Sphere n <= 64, Grassmann, Product) ---- */
+    int32_t trs_solver;                 /* 'TRS_solver': RIPTRM_TRS_SOLVER_TCG | RIPTRM_TRS_SOLVER_EXACT_REPMAT (:431-444).  The
+                                           tangent basis ('basisfun', random in the reference) is fixed per manifold
+                                           (riptrm_b200/basis.py); step and eigenvalues do not depend on the basis */
+    int32_t second_order_stationarity;  /* 'second_order_stationarity' (:599-617); needs EXACT_REPMAT as in the reference */
+    double trs_tolhardcase;             /* 'TRS_tolhardcase' (:432, :263) */
+    const double* tol_second_order_sched; /* forcing_function_second_order(mu) per outer iteration (:886-887); may be NULL
+                                           when second_order_stationarity == 0 */
 } riptrm_options;
 
 /* One trace row = RIPTRM_TRACE_FIELDS doubles; field indices below.  Mirrors the reference
  * log row (base_solver.py:58-76; utils.py:356-364; RIPTRM.py:980-1024) + tcg_iters. */
-#define RIPTRM_TRACE_FIELDS 25
+#define RIPTRM_TRACE_FIELDS 26
 enum {
     RIPTRM_TR_ITERATION = 0, RIPTRM_TR_NUM_INNER = 1, RIPTRM_TR_MU = 2, RIPTRM_TR_RADIUS = 3,
     RIPTRM_TR_DXTYPE = 4, RIPTRM_TR_TCG_ITERS = 5, RIPTRM_TR_NORMDX = 6, RIPTRM_TR_MINXFEASI = 7,
@@ -148,7 +171,8 @@ enum {
     RIPTRM_TR_COST = 15, RIPTRM_TR_DISTANCE = 16, RIPTRM_TR_RESIDUAL = 17, RIPTRM_TR_GRADNORM = 18,
     RIPTRM_TR_COMPLVIOLATION = 19, RIPTRM_TR_DUALVIOLATION = 20, RIPTRM_TR_MANVIOLATION = 21,
     RIPTRM_TR_MAXVIOLATION = 22, RIPTRM_TR_MEANVIOLATION = 23,
-    RIPTRM_TR_TIME = 24 /* seconds since the solve started, device clock (base_solver.py:71) */
+    RIPTRM_TR_TIME = 24, /* seconds since the solve started, device clock (base_solver.py:71) */
+    RIPTRM_TR_MINEIGVALHW = 25 /* 'mineigvalHw' (RIPTRM.py:609-610, :1003); NaN on the tCG path */
 };
 /* absent values (Python None) are stored as NaN; dual_clipping: 0 False, 1 True, NaN None */
 
@@ -214,6 +238,18 @@ int riptrm_hessvec(riptrm_handle* h, const double* x, const double* y, double mu
  * (COLUMNS: info [p][4], one tCG per column; STIEFEL: info [1][4]) */
 int riptrm_tcg(riptrm_handle* h, const double* x, const double* y, double mu, double Delta, double* eta,
                double* info, int where, void* stream);
+
+/* One exact trust-region solve at (x, y, mu, Delta) (RIPTRM.py:431-444: representation matrix of Hw in the fixed tangent
+ * basis, `TRSgep` :218-299): dx [batch][n*p], info [batch][4] = {type (riptrm_trs_type), lam1, ||dx||_x, smallest eigenvalue of
+ * the representation matrix of Hw at (x, y)}.  Sphere (n <= 64), Grassmann and Product families. */
+int riptrm_trs(riptrm_handle* h, const double* x, const double* y, double mu, double Delta, double* dx,
+               double* info, int where, void* stream);
+
+/* The dense core of the above on caller-supplied data -- `TRSgep(A, a, I, Delta, tolhardcase)` (RIPTRM.py:218-299) for `count`
+ * independent problems, one warp each: A [count][d][d] symmetric, a [count][d] -> x [count][d], info [count][4] = {type, lam1,
+ * ||x||, smallest eigenvalue of A}.  d <= 64. */
+int riptrm_trs_dense(int device, int d, int count, const double* A, const double* a, double Delta, double tolhardcase,
+                     double* x, double* info, int where, void* stream);
 
 /* ---- synthetic sweeps drawn on the device (src/NonnegPCA/generator.py:9-65) ----------------
  * `instances` NonnegPCA instances first_instance .. by the reference generator's law (snr, delta as in

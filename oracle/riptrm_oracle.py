@@ -71,6 +71,10 @@ def default_option():
         "second_order_stationarity": False,
         "do_euclidean_lincomb": False,
         "is_euclidean_embedded": False,
+        "forcing_function_second_order": lambda mu: mu,
+        "TRS_tolresid": 1e-12,
+        "TRS_tolhardcase": 1e-8,
+        "basisfun": None,                 # RIPTRM.py:341 default is the RANDOM tangentorthobasis; tests pass a fixed one
         "tCG_theta": 1,
         "tCG_kappa": 0.1,
         "tCG_mininner": 1,
@@ -298,14 +302,93 @@ def evaluate(problem, xPrev, x, y, manviofun, callbackfun):
 
 
 # --------------------------------------------------------------------------
+# Exact trust-region subproblem on the representation matrix (TRS_solver='Exact_RepMat')
+# --------------------------------------------------------------------------
+def operator_matrix(man, x, F, basis):
+    """selfadj_operator2matrix (utils.py:565-573): upper triangle from <F(b_j), b_i>, mirrored."""
+    n = len(basis)
+    A = np.zeros((n, n))
+    for j in range(n):
+        Fb = F(basis[j])
+        for i in range(j + 1):
+            A[i, j] = man.inner_product(x, Fb, basis[i])
+    return A + np.triu(A, 1).T
+
+
+def tangent_coords(man, x, basis, v):
+    """The loops of RIPTRM.py:436-438 / :605-607: coefficient i = <v, b_i>_x."""
+    out = np.empty(len(basis))
+    for i in range(len(basis)):
+        out[i] = man.inner_product(x, v, basis[i])
+    return out
+
+
+def trs_gep(A, a, B, Del, tolhardcase=1e-4):
+    """min x'Ax/2 + a'x s.t. x'Bx <= Del^2 through the rightmost eigenpair of a 2n x 2n pencil
+    (RIPTRM.py:218-299; Adachi, Iwata, Nakatsukasa, Takeda 2017).  Same library calls as the reference:
+    scipy.sparse.linalg.cg for the interior candidate (:244), scipy.linalg.eig for the pencil (:252),
+    scipy.linalg.solve / eigh in the hard case (:270-280)."""
+    import scipy.linalg
+    import scipy.sparse.linalg
+    n = A.shape[0]
+    aat = np.outer(a, a) / (Del ** 2)
+    M0 = np.block([[-B, A], [A, -aat]])                                  # :240
+    M1 = np.block([[np.zeros((n, n)), B], [B, np.zeros((n, n))]])        # :241
+    newton, _ = scipy.sparse.linalg.cg(A, -a)                            # :244 (rtol 1e-5, maxiter 10 n)
+    ok = np.linalg.norm(A @ newton + a) / np.linalg.norm(a) < 1e-5       # :245
+    if ok and newton @ B @ newton >= Del ** 2:                           # :246-247
+        ok = False
+    if not ok:
+        newton = np.full_like(newton, np.nan)                            # :247, :249
+    lams, vecs = scipy.linalg.eig(a=M0, b=-M1)                           # :252
+    k = np.argmax(np.real(lams))                                         # :253
+    lam1 = np.real(lams[k])
+    V = np.real(vecs[:, k])                                              # :255-256
+    x = V[:n]                                                            # :257
+    normx = np.sqrt(x @ (B @ x))                                         # :258
+    x = x / normx * Del                                                  # :259
+    if x @ a > 0:                                                        # :260-261
+        x = -x
+    kind = "boundary"
+    if normx < tolhardcase:                                              # :263
+        x1 = V[n:]
+        shifted = A + lam1 * B                                           # :267
+        Bp = B @ x1
+        H = shifted + lam1 * np.outer(Bp, Bp)                            # :268-269 (alpha1 = lam1)
+        x2 = scipy.linalg.solve(H, -a, assume_a="sym")                   # :270
+        kind = "hardcase_1"
+        if np.linalg.norm(shifted @ x2 + a) / np.linalg.norm(a) > tolhardcase:   # :274
+            _, v = scipy.linalg.eigh(A, B)                               # :275
+            for ii in (3, 6, 9):                                         # :276-283
+                Bp = B @ v[:, :ii]
+                H = shifted + lam1 * Bp @ Bp.T
+                x2 = scipy.linalg.solve(H, -a, assume_a="sym")
+                kind = f"hardcase_{ii}"
+                if np.linalg.norm(shifted @ x2 + a) / np.linalg.norm(a) < tolhardcase:
+                    break
+        Bx, Bx2 = B @ x1, B @ x2                                         # :284-285
+        aa, bb, cc = x1 @ Bx, 2 * x2 @ Bx, x2 @ Bx2 - Del ** 2           # :286-288
+        alp = (-bb + np.sqrt(bb ** 2 - 4 * aa * cc)) / (2 * aa)          # :289
+        x = x2 + alp * x1                                                # :290
+    if not np.isnan(newton).any():                                       # :293-299
+        if 0.5 * (newton @ A @ newton) + a @ newton <= 0.5 * (x @ A @ x) + a @ x:
+            return newton, 0, "interior"
+    return x, lam1, kind
+
+
+# --------------------------------------------------------------------------
 # The solver
 # --------------------------------------------------------------------------
 class OracleRIPTRM:
     def __init__(self, option=None):
         opt = default_option()
         opt.update(option or {})
-        if opt["TRS_solver"] != "tCG" or opt["second_order_stationarity"]:
-            raise ValueError("oracle covers the tCG path only (SURVEY.md section 8)")
+        if opt["TRS_solver"] not in ("tCG", "Exact_RepMat"):
+            raise ValueError(f"TRS_solver {opt['TRS_solver']} is not supported.")        # RIPTRM.py:453-454
+        if opt["TRS_solver"] == "Exact_RepMat" and opt["basisfun"] is None:
+            raise ValueError("Exact_RepMat: pass option['basisfun'] (the reference's default basis is random)")
+        self.rep = None      # (basis, Hw matrix, c vector) at the current (x, y): is_RepMat_available (RIPTRM.py:415-421)
+        self.rep_new = None
         self.option = opt
         self.log = {}
         self.name = f"RIPTRM_{opt['TRS_solver']}"
@@ -336,17 +419,35 @@ class OracleRIPTRM:
         st["maxabsLagmult"] = m
         return st
 
-    # RIPTRM.py:574-629 (tCG branch: no eigenvalue test)
-    def _inner_stop_tests(self, problem, xNew, yNew, mu, tolL, tolC):
+    # RIPTRM.py:574-629
+    def _inner_stop_tests(self, problem, xNew, yNew, mu, tolL, tolC, tolS=None):
+        o = self.option
         man = problem.manifold
+        lin, emb = o["do_euclidean_lincomb"], o["is_euclidean_embedded"]
         sNew = slack(problem, xNew)
-        ngl = man.norm(xNew, grad_lagrangian(problem, xNew, yNew, self.option["do_euclidean_lincomb"]))
+        ngl = man.norm(xNew, grad_lagrangian(problem, xNew, yNew, lin))
         compl = np.linalg.norm(yNew * sNew - mu)
+        mineig, eig_ok = None, True
+        if o["TRS_solver"] == "Exact_RepMat" and o["second_order_stationarity"]:     # :599-617
+            import scipy.linalg
+
+            def HwNew(dx):
+                return hess_lagrangian(problem, xNew, yNew, dx, lin) + G_apply(
+                    problem, xNew, (yNew * Gadj_apply(problem, xNew, dx, emb)) / sNew, lin)
+
+            basis = o["basisfun"](man, xNew)
+            Hmat = operator_matrix(man, xNew, HwNew, basis)
+            cNew = problem.riemannian_gradient(xNew) - G_apply(problem, xNew, mu / sNew, lin)
+            cvec = tangent_coords(man, xNew, basis, cNew)
+            mineig = scipy.linalg.eigh(Hmat, eigvals_only=True)[0]                   # :609-610
+            eig_ok = bool(mineig >= -tolS)                                           # :611
+            self.rep_new = (basis, Hmat, cvec)                                       # :613-615
         return {
             "xfeasi": bool(np.all(sNew > 0)),
             "yfeasi": bool(np.all(yNew > 0)),
             "gradL": bool(ngl <= tolL),
             "compl_ok": bool(compl <= tolC),
+            "eig_ok": eig_ok, "mineigvalHw": mineig,
             "minxfeasi": min(sNew), "minyfeasi": min(yNew), "compl": compl, "sNew": sNew,
         }
 
@@ -385,13 +486,18 @@ class OracleRIPTRM:
             I_right = np.full_like(y, max(o["const_right"], o["const_right"] / mu))
             clipped = np.minimum(np.maximum(yNew, I_left), I_right)                  # :683-684
             out["dual_clipping"] = not np.array_equal(yNew, clipped)                 # :685-695
+            # :687-695: the matrix built at (xNew, yNew) for the eigenvalue test is next iteration's matrix, unless
+            # clipping changed the multipliers
+            self.rep = None
+            if (not out["dual_clipping"] and o["TRS_solver"] == "Exact_RepMat" and o["second_order_stationarity"]):
+                self.rep = copy.deepcopy(self.rep_new)
             return copy.deepcopy(xNew), clipped, DeltaNext, out
-        out["inner_status"] = "unsuccessful"                                         # :697-702
+        out["inner_status"] = "unsuccessful"                                         # :697-702 (matrix stays valid)
         out["dual_clipping"] = None
         return x, y, DeltaNext, out
 
     # RIPTRM.py:707-783
-    def _inner_step(self, problem, x, y, mu, Delta, k_inner, tolL, tolC):
+    def _inner_step(self, problem, x, y, mu, Delta, k_inner, tolL, tolC, tolS=None):
         o = self.option
         man = problem.manifold
         lin, emb = o["do_euclidean_lincomb"], o["is_euclidean_embedded"]
@@ -410,23 +516,35 @@ class OracleRIPTRM:
             self.counters["tcg_hessvec"] += 1
             return Hw(dx)
 
-        dx, _Heta, j, stop = steihaug_tcg(                                           # :445-452
-            man, counted_Hw, x, c, Delta, o["tCG_theta"], o["tCG_kappa"], o["tCG_mininner"],
-            man.dim, problem.preconditioner)
-        self.counters["tcg_calls"] += 1
-        info["dxtype"] = f"tCG_{stop}"
-        info["tcg_iters"] = j + 1
+        if o["TRS_solver"] == "Exact_RepMat":                                        # :431-444
+            if self.rep is None:
+                basis = o["basisfun"](man, x)
+                self.rep = (basis, operator_matrix(man, x, Hw, basis), tangent_coords(man, x, basis, c))
+            basis, Hmat, cvec = self.rep
+            coeff, _lam1, kind = trs_gep(Hmat, cvec, np.eye(man.dim), Delta, o["TRS_tolhardcase"])
+            dx = man.zero_vector(x)
+            for i in range(man.dim):
+                dx = dx + coeff[i] * basis[i]
+            info["dxtype"] = kind
+            info["tcg_iters"] = None
+        else:
+            dx, _Heta, j, stop = steihaug_tcg(                                       # :445-452
+                man, counted_Hw, x, c, Delta, o["tCG_theta"], o["tCG_kappa"], o["tCG_mininner"],
+                man.dim, problem.preconditioner)
+            self.counters["tcg_calls"] += 1
+            info["dxtype"] = f"tCG_{stop}"
+            info["tcg_iters"] = j + 1
         normdx = man.norm(x, dx)                                                     # :735
         info["normdx"] = normdx
         dy = -y + mu * (1 / s) - y * Gadj_apply(problem, x, dx, emb) / s             # :743
         xNew = man.retraction(x, dx)                                                 # :744
         yNew = y + dy                                                                # :745
-        t = self._inner_stop_tests(problem, xNew, yNew, mu, tolL, tolC)              # :748
-        info.update(minxfeasi=t["minxfeasi"], minyfeasi=t["minyfeasi"], compl=t["compl"])
-        if t["xfeasi"] and t["yfeasi"] and t["gradL"] and t["compl_ok"]:             # :762-766
+        t = self._inner_stop_tests(problem, xNew, yNew, mu, tolL, tolC, tolS)        # :748
+        info.update(minxfeasi=t["minxfeasi"], minyfeasi=t["minyfeasi"], compl=t["compl"], mineigvalHw=t["mineigvalHw"])
+        if t["xfeasi"] and t["yfeasi"] and t["gradL"] and t["compl_ok"] and t["eig_ok"]:   # :762-766
             info["inner_status"] = "converged"
             return True, xNew, yNew, Delta, info
-        if not t["xfeasi"]:                                                          # :769-775
+        if not t["xfeasi"]:                                                          # :769-775 (matrix stays valid)
             info["inner_status"] = "primal_infeasible"
             return False, x, y, o["gamma"] * normdx, info
         xN, yN, DeltaN, upd = self._rho_test_and_update(                             # :777
@@ -435,14 +553,15 @@ class OracleRIPTRM:
         return False, xN, yN, DeltaN, info
 
     # RIPTRM.py:785-847 (iteration guards only)
-    def _inner_run(self, problem, k_outer, x0, y0, mu, Delta0, tolL, tolC):
+    def _inner_run(self, problem, k_outer, x0, y0, mu, Delta0, tolL, tolC, tolS=None):
         o = self.option
         x, y, Delta = x0, y0, Delta0
+        self.rep = self.rep_new = None                                               # inner_preprocess :415-421
         xPrev = copy.deepcopy(x)
         k = 0
         while True:
             k += 1
-            done, x, y, Delta, info = self._inner_step(problem, x, y, mu, Delta, k, tolL, tolC)
+            done, x, y, Delta, info = self._inner_step(problem, x, y, mu, Delta, k, tolL, tolC, tolS)
             self.counters["inner"] += 1
             if o["save_inner_iteration"]:                                            # :812-818
                 ev = evaluate(problem, xPrev, x, y, o["manviofun"], o["callbackfun"])
@@ -488,7 +607,8 @@ class OracleRIPTRM:
             # outer_step, RIPTRM.py:866-896
             tolL = o["forcing_function_Lagrangian"](mu)
             tolC = o["forcing_function_complementarity"](mu)
-            x, y, Delta, info = self._inner_run(problem, it, x, y, mu, Delta, tolL, tolC)
+            tolS = o["forcing_function_second_order"](mu) if o["second_order_stationarity"] else None
+            x, y, Delta, info = self._inner_run(problem, it, x, y, mu, Delta, tolL, tolC, tolS)
             r_, c_, b_ = (o["barrier_parameter_update_r"], o["barrier_parameter_update_c"],
                           o["barrier_parameter_update_b"])
             if o["do_simple_barrier_parameter_update"]:                              # :890-893

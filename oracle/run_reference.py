@@ -85,7 +85,7 @@ def load_cfg(problem_name, overrides=None):
     return cfg
 
 
-def run_reference(problem_name, overrides=None, solver_name="RIPTRM", solver_path=None):
+def run_reference(problem_name, overrides=None, solver_name="RIPTRM", solver_path=None, extra_option=None):
     """Returns (output, tcg_iters:list[int], scratch_dir).  `solver_path`: a directory put ahead of the
     reference's ./src/solver on sys.path (tests/test_dropin_recognition.py uses it to let the reference's
     Simulator pick up integration/RIPTRM.py instead of its own solver module)."""
@@ -115,6 +115,15 @@ def run_reference(problem_name, overrides=None, solver_name="RIPTRM", solver_pat
         ov.update(overrides or {})
         cfg = load_cfg(problem_name, ov)
         sim = simulator.Simulator(cfg)
+        if extra_option:
+            orig_add = sim.add_solver_option
+
+            def add_solver_option(option):
+                option = orig_add(option)
+                option.update(extra_option)
+                return option
+
+            sim.add_solver_option = add_solver_option
         outputs = {}
         orig_save = sim.save_output
 

@@ -14,11 +14,14 @@ FAMILY_ROSENBROCK_GRASSMANN = 2
 FAMILY_STABLEID_PRODUCT = 3
 FAMILY_NONNEGPCA_COLUMNS = 4
 FAMILY_NONNEGPCA_STIEFEL = 5
-TRACE_FIELDS = 25
+TRACE_FIELDS = 26
 SUMMARY_FIELDS = 16
 
 TCG_STOP_NAMES = ("MAX_INNER_ITER", "NEGATIVE_CURVATURE", "EXCEEDED_TR", "MODEL_INCREASED",
                   "REACHED_TARGET_LINEAR", "REACHED_TARGET_SUPERLINEAR")
+# dxtype of the exact trust-region solver (TRSgep's `type`, RIPTRM.py:262-298): trace codes 6..11
+TRS_TYPE_NAMES = {6: "boundary", 7: "interior", 8: "hardcase_1", 9: "hardcase_3", 10: "hardcase_6", 11: "hardcase_9"}
+TRS_SOLVER_TCG, TRS_SOLVER_EXACT_REPMAT = 0, 1
 INNER_STATUS_NAMES = (None, "converged", "primal_infeasible", "successful", "unsuccessful",
                       "max-time-exceeded", "max-iter-exceeded")
 RADIUS_UPDATE_NAMES = (None, "reduced", "expanded", "unchanged")
@@ -28,7 +31,7 @@ TR = {name: i for i, name in enumerate((
     "iteration", "num_inner", "mu", "TR_radius", "dxtype", "tcg_iters", "normdx", "minxfeasi", "minyfeasi",
     "compl", "ared/pred", "radius_update", "inner_status", "dual_clipping", "maxabsLagmult", "cost",
     "distance", "residual", "gradnorm", "complviolation", "dualviolation", "manviolation", "maxviolation",
-    "meanviolation", "time"))}
+    "meanviolation", "time", "mineigvalHw"))}
 SM = {name: i for i, name in enumerate((
     "cost", "residual", "gradnorm", "complviolation", "dualviolation", "manviolation", "maxviolation",
     "meanviolation", "mu", "TR_radius", "outer_iters", "inner_iters", "tcg_iters", "aux_hessvecs",
@@ -47,6 +50,8 @@ class RiptrmOptions(C.Structure):
         ("tcg_theta", C.c_double), ("tcg_kappa", C.c_double),
         ("mu_sched", C.POINTER(C.c_double)), ("tol_lagrangian_sched", C.POINTER(C.c_double)),
         ("tol_complementarity_sched", C.POINTER(C.c_double)),
+        ("trs_solver", C.c_int32), ("second_order_stationarity", C.c_int32), ("trs_tolhardcase", C.c_double),
+        ("tol_second_order_sched", C.POINTER(C.c_double)),
     ]
 
 
@@ -73,6 +78,10 @@ SYMBOLS = {
                                  C.c_int, C.c_void_p]),
     "riptrm_tcg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
                              C.c_void_p, C.c_int, C.c_void_p]),
+    "riptrm_trs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
+                             C.c_void_p, C.c_int, C.c_void_p]),
+    "riptrm_trs_dense": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
+                                   C.c_void_p, C.c_int, C.c_void_p]),
     "riptrm_generate_nonnegpca": (C.c_int, [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_double, C.c_double,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "riptrm_launch_count": (C.c_int64, [C.c_void_p]),
@@ -96,7 +105,7 @@ def load_library():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.riptrm_abi_version() != 1:
+    if lib.riptrm_abi_version() != 2:
         raise RiptrmError("libriptrm_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib
@@ -108,6 +117,18 @@ def measure_fp64_peaks(device=0, ms_target=20.0, repeats=3, stream=None):
     check(load_library().riptrm_measure_fp64_peaks(int(device), float(ms_target), int(repeats), out,
                                                    C.c_void_p(stream) if stream else None))
     return float(out[0]), float(out[1])
+
+
+def trs_dense(A, a, Delta, tolhardcase=1e-8, device=0):
+    """Batched dense trust-region subproblems on the GPU (`TRSgep` with B = I, RIPTRM.py:218-299): A [count, d, d] symmetric,
+    a [count, d] -> (x [count, d], info [count, 4] = {type code, lam1, ||x||, smallest eigenvalue})."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    count, d = a.shape
+    x, info = np.empty((count, d)), np.empty((count, 4))
+    check(load_library().riptrm_trs_dense(int(device), d, count, ptr(A), ptr(a), float(Delta), float(tolhardcase), ptr(x),
+                                          ptr(info), HOST, None))
+    return x, info
 
 
 def check(rc):

@@ -29,6 +29,7 @@ struct GrassmannFam {
         double alpha, offset;
         bool embedded;
         double* sc;  // shared-memory scratch: 6 slots of 32 doubles
+        double* perp;  // Exact_RepMat: n x (n-p) orthonormal complement of the current point (after the scratch slots)
     };
     struct Pt {
         Vec x;
@@ -44,7 +45,8 @@ struct GrassmannFam {
     };
 
     static constexpr int kScratchDoubles = 6 * 32;
-    static constexpr int smem_doubles(int, int) { return kScratchDoubles; }
+    static constexpr int kPerpDoubles = 128;   // n (n - p) <= 128 for the exact path (the reference's 5 x 2 = 10)
+    static __host__ __device__ constexpr int smem_doubles(int, int) { return kScratchDoubles + kPerpDoubles; }
     static constexpr int kComponents = 1;
     template <class Params>
     static __device__ __forceinline__ Ctx make_ctx(const Params& P, const DevOpts& o, double* smem) {
@@ -56,6 +58,7 @@ struct GrassmannFam {
         c.offset = P.offset;
         c.embedded = o.is_euclidean_embedded != 0;
         c.sc = smem;
+        c.perp = smem + kScratchDoubles;
         return c;
     }
     static __device__ __forceinline__ Vec load_x(const Ctx& c, const double* g) {
@@ -185,6 +188,64 @@ struct GrassmannFam {
     static __device__ __forceinline__ TcgResult tcg(const Ctx& ctx, const DevOpts& o, const Pt& pt, const CVec& y,
                                                     const Step& st, double Delta, Vec& eta, Vec& Heta) {
         return tcg_generic<GrassmannFam>(ctx, o, pt, y, st, Delta, eta, Heta);
+    }
+
+    // ---- Exact_RepMat: orthonormal tangent basis X_perp E_ab (riptrm_b200/basis.py grassmann_basis) -------------------------
+    // X_perp = the last n - p columns of the complete Householder QR factor of X: T_X = { X_perp K }, and K -> X_perp K is an
+    // isometry from R^{(n-p) x p} (Frobenius) since X_perp has orthonormal columns.  n x p is tiny: lane 0 factorises.
+    struct Coord {};
+    static __device__ __noinline__ void coord_setup(const Ctx& c, const Pt& pt, Coord&) {
+        put(c, 0, pt.x);
+        const int n = c.n, p = c.p, q = c.n - c.p;
+        if (lane_id() == 0) {
+            double* R = slot(c, 1);      // working copy of X (n x p)
+            double* Vh = slot(c, 2);     // Householder vectors, column j in Vh[:, j]
+            double* E = c.perp;          // n x q
+            for (int e = 0; e < n * p; ++e) {
+                R[e] = slot(c, 0)[e];
+                Vh[e] = 0.0;
+            }
+            for (int j = 0; j < p; ++j) {
+                double nrm2 = 0.0;
+                for (int i = j; i < n; ++i) nrm2 = fma(R[i * p + j], R[i * p + j], nrm2);
+                const double x0 = R[j * p + j];
+                const double alpha = (x0 >= 0.0) ? -sqrt(nrm2) : sqrt(nrm2);
+                for (int i = j; i < n; ++i) Vh[i * p + j] = R[i * p + j];
+                Vh[j * p + j] = x0 - alpha;
+                double vv = 0.0;
+                for (int i = j; i < n; ++i) vv = fma(Vh[i * p + j], Vh[i * p + j], vv);
+                if (vv > 0.0) {
+                    for (int cidx = j; cidx < p; ++cidx) {
+                        double dot = 0.0;
+                        for (int i = j; i < n; ++i) dot = fma(Vh[i * p + j], R[i * p + cidx], dot);
+                        const double f = 2.0 * dot / vv;
+                        for (int i = j; i < n; ++i) R[i * p + cidx] = R[i * p + cidx] - f * Vh[i * p + j];
+                    }
+                }
+            }
+            for (int i = 0; i < n; ++i)
+                for (int b = 0; b < q; ++b) E[i * q + b] = (i == p + b) ? 1.0 : 0.0;
+            for (int j = p - 1; j >= 0; --j) {   // Q[:, p:] = H_0 ... H_{p-1} [e_p ... e_{n-1}]
+                double vv = 0.0;
+                for (int i = j; i < n; ++i) vv = fma(Vh[i * p + j], Vh[i * p + j], vv);
+                if (!(vv > 0.0)) continue;
+                for (int b = 0; b < q; ++b) {
+                    double dot = 0.0;
+                    for (int i = j; i < n; ++i) dot = fma(Vh[i * p + j], E[i * q + b], dot);
+                    const double f = 2.0 * dot / vv;
+                    for (int i = j; i < n; ++i) E[i * q + b] = E[i * q + b] - f * Vh[i * p + j];
+                }
+            }
+        }
+        __syncwarp();
+    }
+    static __device__ __forceinline__ Vec from_coords(const Ctx& c, const Pt&, const Coord&, const double* coef) {
+        sm::mm(slot(c, 2), c.perp, coef, c.n, c.n - c.p, c.p);          // X_perp K
+        return get(c, 2, c.np);
+    }
+    static __device__ __forceinline__ void to_coords(const Ctx& c, const Pt&, const Coord&, const Vec& v, double* out) {
+        put(c, 0, v);
+        sm::mm(out, c.perp, slot(c, 0), c.n - c.p, c.n, c.p, true, false);   // X_perp' V
     }
 
     // (A'A)^{-1/2} applied to A = X + V: the polar factor (pymanopt: u @ vt of the thin SVD)

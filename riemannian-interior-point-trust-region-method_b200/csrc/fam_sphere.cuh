@@ -389,6 +389,41 @@ struct SphereFam {
         return res;
     }
 
+    // ---- Exact_RepMat: orthonormal tangent basis (solver_warp.cuh `RepWork`; riptrm_b200/basis.py sphere_basis) -------------
+    // H = I - beta u u', u = x + sigma e_0, beta = 2 / u'u maps e_0 to -sigma x / |x|, so its columns 1..n-1 are an orthonormal
+    // basis of the tangent space x^perp: coordinates of v are rows 1..n-1 of H v, and sum_i coef_i b_i = H (0; coef).
+    struct Coord {
+        Vec u;
+        double beta;
+    };
+    static __device__ __forceinline__ void coord_setup(const Ctx&, const Pt& pt, Coord& cc) {
+        const double x0 = wbcast(pt.x.v[0], 0);                 // element 0 lives on lane 0, slot 0
+        cc.u = pt.x;
+        if (lane_id() == 0) cc.u.v[0] = pt.x.v[0] + (x0 >= 0.0 ? 1.0 : -1.0);
+        cc.beta = 2.0 / wdot(cc.u, cc.u);
+    }
+    static __device__ __forceinline__ Vec from_coords(const Ctx& c, const Pt&, const Coord& cc, const double* coef) {
+        Vec w;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int e = elem(k);
+            w.v[k] = (e >= 1 && e < dimn(c)) ? coef[e - 1] : 0.0;
+        }
+        const double f = cc.beta * wdot(cc.u, w);
+#pragma unroll
+        for (int k = 0; k < K; ++k) w.v[k] = w.v[k] - f * cc.u.v[k];
+        return w;
+    }
+    static __device__ __forceinline__ void to_coords(const Ctx& c, const Pt&, const Coord& cc, const Vec& v, double* out) {
+        const double f = cc.beta * wdot(cc.u, v);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int e = elem(k);
+            if (e >= 1 && e < dimn(c)) out[e - 1] = v.v[k] - f * cc.u.v[k];
+        }
+        __syncwarp();
+    }
+
     static __device__ __forceinline__ Vec retract(const Ctx&, const Pt& pt, const Vec& dx) {
         Vec a;
 #pragma unroll

@@ -63,7 +63,7 @@ struct StableIdFam {
         LM PhiL;             // G_A + sum_i y_i Phi_i
     };
 
-    static constexpr int smem_doubles(int d, int N) { return kSlots * 32 + 3 * d * N + d * d; }
+    static __host__ __device__ constexpr int smem_doubles(int d, int N) { return kSlots * 32 + 3 * d * N + d * d; }
 
     template <class Params>
     static __device__ __forceinline__ Ctx make_ctx(const Params& P, const DevOpts& o, double* smem) {
@@ -382,6 +382,89 @@ struct StableIdFam {
     static __device__ __forceinline__ TcgResult tcg(const Ctx& ctx, const DevOpts& o, const Pt& pt, const CVec& y,
                                                     const Step& st, double Delta, Vec& eta, Vec& Heta) {
         return tcg_generic<StableIdFam>(ctx, o, pt, y, st, Delta, eta, Heta);
+    }
+
+    // ---- Exact_RepMat: orthonormal tangent basis of the product (riptrm_b200/basis.py) ----------------------------------------
+    //   Skew(d):           (E_ab - E_ba) / sqrt 2, a < b                                  d (d-1) / 2 coordinates
+    //   SPD(d) at P = LL': L E L' with E = E_aa, (E_ab + E_ba) / sqrt 2                   d (d+1) / 2 coordinates each
+    // (<L E L', L F L'>_P = tr(P^-1 L E L' P^-1 L F L') = tr(E F): orthonormal in the affine-invariant metric.)
+    // Coordinate order: skew pairs (a < b, row-major), then for R and for Q: the d diagonal entries, the pairs.
+    struct Coord {
+        LM LR, LRi, LQ, LQi;   // Cholesky factors and their inverses, one entry per lane
+    };
+    static __device__ __noinline__ void chol_and_inverse(double* sc, int d, LM P, LM& L_out, LM& Li_out) {
+        const int l = lane_id();
+        sc[l] = P;
+        __syncwarp();
+        double L[DMAX][DMAX], Li[DMAX][DMAX];
+        for (int i = 0; i < d; ++i)
+            for (int j = 0; j < d; ++j) L[i][j] = Li[i][j] = 0.0;
+        for (int i = 0; i < d; ++i)
+            for (int j = 0; j <= i; ++j) {
+                double s = sc[i * d + j];
+                for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+                L[i][j] = (i == j) ? sqrt(s) : s / L[j][j];
+            }
+        for (int j = 0; j < d; ++j) {          // forward substitution L Li = I, column by column
+            for (int i = j; i < d; ++i) {
+                double s = (i == j) ? 1.0 : 0.0;
+                for (int k = j; k < i; ++k) s -= L[i][k] * Li[k][j];
+                Li[i][j] = s / L[i][i];
+            }
+        }
+        __syncwarp();
+        const int i = l / d, j = l - i * d;
+        L_out = (l < d * d) ? L[i][j] : 0.0;
+        Li_out = (l < d * d) ? Li[i][j] : 0.0;
+    }
+    static __device__ __forceinline__ void coord_setup(const Ctx& c, const Pt& pt, Coord& cc) {
+        chol_and_inverse(c.sc, c.d, pt.x.v[1], cc.LR, cc.LRi);
+        chol_and_inverse(c.sc, c.d, pt.x.v[2], cc.LQ, cc.LQi);
+    }
+    static __device__ __forceinline__ int pair_index(int d, int a, int b) { return a * d - (a * (a + 1)) / 2 + (b - a - 1); }
+    // symmetric / skew lane matrix from packed coordinates (diag first, then pairs scaled by 1 / sqrt 2)
+    static __device__ __forceinline__ LM unpack(const Ctx& c, const double* coef, bool skewpart) {
+        const int l = lane_id(), d = c.d;
+        if (l >= c.dd) return 0.0;
+        const int i = l / d, j = l - i * d;
+        const double r = 0.70710678118654752440;
+        if (skewpart) {
+            if (i == j) return 0.0;
+            return (i < j) ? coef[pair_index(d, i, j)] * r : -(coef[pair_index(d, j, i)] * r);
+        }
+        if (i == j) return coef[i];
+        return coef[d + pair_index(d, i < j ? i : j, i < j ? j : i)] * r;
+    }
+    static __device__ __forceinline__ Vec from_coords(const Ctx& c, const Pt&, const Coord& cc, const double* coef) {
+        const int ns = c.d * (c.d - 1) / 2, np = c.d * (c.d + 1) / 2;
+        Vec v;
+        v.v[0] = unpack(c, coef, true);
+        const LM KR = unpack(c, coef + ns, false), KQ = unpack(c, coef + ns + np, false);
+        v.v[1] = mul(c, mul(c, cc.LR, KR), cc.LR, false, true);
+        v.v[2] = mul(c, mul(c, cc.LQ, KQ), cc.LQ, false, true);
+        return v;
+    }
+    static __device__ __forceinline__ void pack(const Ctx& c, LM a, double* out, bool skewpart) {
+        put(c, 7, a);
+        const int l = lane_id(), d = c.d;
+        const double r = 0.70710678118654752440;
+        const double* A = slot(c, 7);
+        if (l < c.dd) {
+            const int i = l / d, j = l - i * d;
+            if (skewpart) {
+                if (i < j) out[pair_index(d, i, j)] = (A[i * d + j] - A[j * d + i]) * r;
+            } else {
+                if (i == j) out[i] = A[i * d + i];
+                else if (i < j) out[d + pair_index(d, i, j)] = (A[i * d + j] + A[j * d + i]) * r;
+            }
+        }
+        __syncwarp();
+    }
+    static __device__ __forceinline__ void to_coords(const Ctx& c, const Pt&, const Coord& cc, const Vec& v, double* out) {
+        const int ns = c.d * (c.d - 1) / 2, np = c.d * (c.d + 1) / 2;
+        pack(c, v.v[0], out, true);
+        pack(c, mul(c, mul(c, cc.LRi, v.v[1]), cc.LRi, false, true), out + ns, false);
+        pack(c, mul(c, mul(c, cc.LQi, v.v[2]), cc.LQi, false, true), out + ns + np, false);
     }
 
     static __device__ __forceinline__ Vec retract(const Ctx& c, const Pt& pt, const Vec& dx) {

@@ -163,9 +163,29 @@ __device__ __forceinline__ void store_vec(double* g, const WVec<K>& r, int len) 
     }
 }
 
-// mode 0: whole solve; 1: one Hessian-vector product; 2: one tCG solve
-template <int K, int MODE, int NFIX>
-__global__ void __launch_bounds__(32, (K == 2) ? 10 : 4) sphere_kernel(SphereParams P, DevOpts o, int* counter) {
+// One exact trust-region solve at (pt, y0, mu, Delta) for the riptrm_trs hook: dx and {type, lam1, ||dx||, smallest eigenvalue}
+template <class F>
+__device__ __forceinline__ void trs_hook(const typename F::Ctx& ctx, const DevOpts& o, const typename F::Pt& pt,
+                                         const typename F::CVec& y0, const typename F::Step& st, double Delta, RepWork& rw,
+                                         typename F::Vec& dx, double* info4) {
+    typename F::Coord cc;
+    F::coord_setup(ctx, pt, cc);
+    rep_build<F>(ctx, pt, y0, st, cc, rw, 0);
+    rep_rhs<F>(ctx, pt, st, cc, rw, 0);
+    const dense::TrsOut to = dense::trs_eig(rw.D[0], rw.al[0], rw.d, Delta, o.trs_tolhardcase, rw.col, rw.ws, rw.W, rw.ld);
+    dense::cols_dot(rw.VT[0], rw.d, rw.ld, rw.col, rw.coef);
+    dx = F::from_coords(ctx, pt, cc, rw.coef);
+    const double nrm = sqrt(F::inner(ctx, pt, dx, dx));
+    const double mineig = rep_mineig(rw, 0);
+    const int lane = lane_id();
+    if (info4 != nullptr && lane < 4)
+        info4[lane] = (lane == 0) ? (double)to.kind : (lane == 1) ? to.lam1 : (lane == 2) ? nrm : mineig;
+}
+
+// mode 0: whole solve; 1: one Hessian-vector product; 2: one tCG solve; 3: one exact trust-region solve (EXACT only)
+// EXACT: TRS_solver='Exact_RepMat' -- the representation-matrix workspace (RepWork) follows S in shared memory
+template <int K, int MODE, int NFIX, bool EXACT = false>
+__global__ void __launch_bounds__(32, EXACT ? 1 : ((K == 2) ? 10 : 4)) sphere_kernel(SphereParams P, DevOpts o, int* counter) {
     using F = SphereFam<K, NFIX>;
     extern __shared__ __align__(16) double smem[];
     const int n = P.n;
@@ -180,6 +200,8 @@ __global__ void __launch_bounds__(32, (K == 2) ? 10 : 4) sphere_kernel(SpherePar
     ctx.embedded = o.is_euclidean_embedded != 0;
     const int lane = lane_id();
     int loaded_z = -1;
+    RepWork rw;
+    if (EXACT) rep_init(rw, smem + n * ns + pad + 32 * K, n - 1);
     while (true) {
         int inst = 0;
         if (lane == 0) inst = atomicAdd(counter, 1);
@@ -202,8 +224,16 @@ __global__ void __launch_bounds__(32, (K == 2) ? 10 : 4) sphere_kernel(SpherePar
             double* tr = (P.trace != nullptr && o.trace_mode != 0)
                              ? P.trace + (size_t)inst * o.trace_capacity * RIPTRM_TRACE_FIELDS
                              : nullptr;
-            solve_instance<F>(ctx, o, x0, y0, pt, y, P.summary ? P.summary + (size_t)inst * RIPTRM_SUMMARY_FIELDS : nullptr,
-                              tr, pause, resume, P.pause_at);
+            if constexpr (EXACT) {
+                rw.cur = 0;
+                rw.mat_valid = rw.al_valid = false;
+                solve_instance<F, true, RepWork>(ctx, o, x0, y0, pt, y,
+                                                 P.summary ? P.summary + (size_t)inst * RIPTRM_SUMMARY_FIELDS : nullptr, tr, nullptr,
+                                                 false, -1, &rw);
+            } else {
+                solve_instance<F>(ctx, o, x0, y0, pt, y, P.summary ? P.summary + (size_t)inst * RIPTRM_SUMMARY_FIELDS : nullptr,
+                                  tr, pause, resume, P.pause_at);
+            }
             if (P.x) store_vec<K>(P.x + (size_t)inst * n, pt.x, n);
             if (P.y) store_vec<K>(P.y + (size_t)inst * n, y, n);
         } else {
@@ -215,6 +245,12 @@ __global__ void __launch_bounds__(32, (K == 2) ? 10 : 4) sphere_kernel(SpherePar
                 const typename F::Vec v = load_vec<K>(P.v + (size_t)inst * n, n);
                 const typename F::Vec hv = F::Hw(ctx, pt, y0, st, v);
                 store_vec<K>(P.out + (size_t)inst * n, hv, n);
+            } else if (MODE == 3) {
+                if constexpr (EXACT) {
+                    typename F::Vec dx;
+                    trs_hook<F>(ctx, o, pt, y0, st, P.Delta, rw, dx, P.info ? P.info + (size_t)inst * 4 : nullptr);
+                    store_vec<K>(P.out + (size_t)inst * n, dx, n);
+                }
             } else {
                 typename F::Vec eta, Heta;
                 const TcgResult r = F::tcg(ctx, o, pt, y0, st, P.Delta, eta, Heta);
@@ -745,16 +781,34 @@ extern "C" int riptrm_set_options(riptrm_handle* h, const riptrm_options* o) {
         return fail(RIPTRM_E_INVALID, "schedules are required (length maxiter + 1)");
     if (o->trace_mode < 0 || o->trace_mode > 2) return fail(RIPTRM_E_INVALID, "trace_mode must be 0, 1 or 2");
     if (o->trace_mode != 0 && o->trace_capacity <= 0) return fail(RIPTRM_E_INVALID, "trace_capacity must be positive");
+    if (o->trs_solver != RIPTRM_TRS_SOLVER_TCG && o->trs_solver != RIPTRM_TRS_SOLVER_EXACT_REPMAT)
+        return fail(RIPTRM_E_INVALID, "trs_solver must be RIPTRM_TRS_SOLVER_TCG or RIPTRM_TRS_SOLVER_EXACT_REPMAT");
+    if (o->second_order_stationarity && o->trs_solver != RIPTRM_TRS_SOLVER_EXACT_REPMAT)
+        return fail(RIPTRM_E_INVALID, "second_order_stationarity needs trs_solver = EXACT_REPMAT (RIPTRM.py:599)");
+    if (o->second_order_stationarity && o->tol_second_order_sched == nullptr)
+        return fail(RIPTRM_E_INVALID, "second_order_stationarity needs tol_second_order_sched (length maxiter + 1)");
+    if (o->trs_solver == RIPTRM_TRS_SOLVER_EXACT_REPMAT) {
+        if (h->family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS || is_stiefel(h))
+            return fail(RIPTRM_E_UNSUPPORTED, "Exact_RepMat needs a dim x dim representation matrix: not built for the large-n families");
+        if (h->family == RIPTRM_FAMILY_NONNEGPCA_SPHERE && h->n > 64)
+            return fail(RIPTRM_E_UNSUPPORTED, "Exact_RepMat on Sphere(n): n <= 64 (three dim x dim matrices per pair in shared memory)");
+        if (h->family == RIPTRM_FAMILY_ROSENBROCK_GRASSMANN && h->n * (h->n - h->p) > GrassmannFam::kPerpDoubles)
+            return fail(RIPTRM_E_UNSUPPORTED, "Exact_RepMat on Grassmann(n, p): n (n - p) <= 128");
+    }
     CUDA_TRY(cudaSetDevice(h->device));
     const int len = o->maxiter + 1;
     free_dev(h->d_sched);
-    CUDA_TRY(cudaMalloc(&h->d_sched, (size_t)3 * len * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->d_sched, (size_t)4 * len * sizeof(double)));
+    CUDA_TRY(cudaMemset(h->d_sched, 0, (size_t)4 * len * sizeof(double)));
+    if (o->tol_second_order_sched != nullptr)
+        CUDA_TRY(cudaMemcpy(h->d_sched + 3 * len, o->tol_second_order_sched, len * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(h->d_sched, o->mu_sched, len * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(h->d_sched + len, o->tol_lagrangian_sched, len * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(h->d_sched + 2 * len, o->tol_complementarity_sched, len * sizeof(double), cudaMemcpyHostToDevice));
     h->sched_len = len;
     h->opts = *o;
     h->opts.mu_sched = h->opts.tol_lagrangian_sched = h->opts.tol_complementarity_sched = nullptr;
+    h->opts.tol_second_order_sched = nullptr;
     h->have_opts = true;
     return RIPTRM_OK;
 }
@@ -785,8 +839,12 @@ static DevOpts make_devopts(const riptrm_handle* h) {
     o.mu = h->d_sched;
     o.tolL = h->d_sched + h->sched_len;
     o.tolC = h->d_sched + 2 * h->sched_len;
+    o.tolS = h->d_sched + 3 * h->sched_len;
+    o.second_order = s.second_order_stationarity;
+    o.trs_tolhardcase = s.trs_tolhardcase;
     return o;
 }
+static bool exact_repmat(const riptrm_handle* h) { return h->have_opts && h->opts.trs_solver == RIPTRM_TRS_SOLVER_EXACT_REPMAT; }
 
 static int ensure(double*& p, size_t bytes) {
     if (p != nullptr) return RIPTRM_OK;
@@ -980,12 +1038,12 @@ static int launch_sphere_tmem(riptrm_handle* h, const SphereParams& P, const Dev
     return RIPTRM_OK;
 }
 
-template <int K, int MODE, int NFIX>
+template <int K, int MODE, int NFIX, bool EXACT = false>
 static int launch_sphere(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
     const int n = h->n;
     const int ns = (n + 1) & ~1;
-    const size_t smem = (size_t)(n * ns + 32 * K + 32 * K) * sizeof(double);
-    auto kern = sphere_kernel<K, MODE, NFIX>;
+    const size_t smem = ((size_t)(n * ns + 32 * K + 32 * K) + (EXACT ? rep_doubles(n - 1) : 0)) * sizeof(double);
+    auto kern = sphere_kernel<K, MODE, NFIX, EXACT>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
@@ -1051,6 +1109,14 @@ static bool sibling_units(const riptrm_handle* h) {
     return ipp >= 2 && ipp % 2 == 0 && h->batch >= 2 * h->num_sms * 8;
 }
 
+// TRS_solver='Exact_RepMat': one warp per CTA with the representation-matrix workspace in shared memory, one launch
+template <int MODE>
+static int dispatch_sphere_exact(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
+    if (h->n == 50) return launch_sphere<2, MODE, 50, true>(h, P, o, st);
+    if (h->n <= 64) return launch_sphere<2, MODE, 0, true>(h, P, o, st);
+    return fail(RIPTRM_E_UNSUPPORTED, "Exact_RepMat on Sphere(n): n <= 64");
+}
+
 template <int MODE>
 static int dispatch_sphere(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
     const int n = h->n;
@@ -1095,12 +1161,14 @@ struct SmallParams {
     double* info;
 };
 
-template <class F, int MODE>
-__global__ void __launch_bounds__(32, 16) small_kernel(SmallParams P, DevOpts o, int* counter) {  // <= 128 registers: 16 warps per SM
+template <class F, int MODE, bool EXACT = false>
+__global__ void __launch_bounds__(32, EXACT ? 4 : 16) small_kernel(SmallParams P, DevOpts o, int* counter) {  // <= 128 registers: 16 warps per SM
     extern __shared__ __align__(16) double smem[];
     typename F::Ctx ctx = F::make_ctx(P, o, smem);
     const int lane = lane_id();
     const int xl = (F::kComponents == 1) ? P.n * P.p : P.n * P.n * F::kComponents;
+    RepWork rw;
+    if (EXACT) rep_init(rw, smem + F::smem_doubles(P.n, P.N), F::dim(ctx));
     while (true) {
         int inst = 0;
         if (lane == 0) inst = atomicAdd(counter, 1);
@@ -1114,8 +1182,16 @@ __global__ void __launch_bounds__(32, 16) small_kernel(SmallParams P, DevOpts o,
             double* tr = (P.trace != nullptr && o.trace_mode != 0)
                              ? P.trace + (size_t)inst * o.trace_capacity * RIPTRM_TRACE_FIELDS
                              : nullptr;
-            solve_instance<F>(ctx, o, x0, y0, pt, y, P.summary ? P.summary + (size_t)inst * RIPTRM_SUMMARY_FIELDS : nullptr,
-                              tr, nullptr, false, -1);
+            if constexpr (EXACT) {
+                rw.cur = 0;
+                rw.mat_valid = rw.al_valid = false;
+                solve_instance<F, true, RepWork>(ctx, o, x0, y0, pt, y,
+                                                 P.summary ? P.summary + (size_t)inst * RIPTRM_SUMMARY_FIELDS : nullptr, tr, nullptr,
+                                                 false, -1, &rw);
+            } else {
+                solve_instance<F>(ctx, o, x0, y0, pt, y, P.summary ? P.summary + (size_t)inst * RIPTRM_SUMMARY_FIELDS : nullptr,
+                                  tr, nullptr, false, -1);
+            }
             if (P.x) F::store_x(ctx, P.x + (size_t)inst * xl, pt.x);
             if (P.y) F::store_y(ctx, P.y + (size_t)inst * P.m, y);
         } else {
@@ -1127,6 +1203,12 @@ __global__ void __launch_bounds__(32, 16) small_kernel(SmallParams P, DevOpts o,
                 const typename F::Vec v = F::load_x(ctx, P.v + (size_t)inst * xl);
                 const typename F::Vec hv = F::Hw(ctx, pt, y0, st, v);
                 F::store_x(ctx, P.out + (size_t)inst * xl, hv);
+            } else if (MODE == 3) {
+                if constexpr (EXACT) {
+                    typename F::Vec dx;
+                    trs_hook<F>(ctx, o, pt, y0, st, P.Delta, rw, dx, P.info ? P.info + (size_t)inst * 4 : nullptr);
+                    F::store_x(ctx, P.out + (size_t)inst * xl, dx);
+                }
             } else {
                 typename F::Vec eta, Heta;
                 const TcgResult r = F::tcg(ctx, o, pt, y0, st, P.Delta, eta, Heta);
@@ -1141,10 +1223,17 @@ __global__ void __launch_bounds__(32, 16) small_kernel(SmallParams P, DevOpts o,
     }
 }
 
-template <class F, int MODE>
+template <class F>
+static int small_dim(const SmallParams& P);
+template <>
+int small_dim<GrassmannFam>(const SmallParams& P) { return P.n * P.p - P.p * P.p; }
+template <>
+int small_dim<StableIdFam>(const SmallParams& P) { return P.n * (P.n - 1) / 2 + P.n * (P.n + 1); }
+
+template <class F, int MODE, bool EXACT = false>
 static int launch_small(riptrm_handle* h, const SmallParams& P, const DevOpts& o, cudaStream_t st) {
-    auto kern = small_kernel<F, MODE>;
-    const size_t smem = (size_t)F::smem_doubles(P.n, P.N) * sizeof(double);
+    auto kern = small_kernel<F, MODE, EXACT>;
+    const size_t smem = ((size_t)F::smem_doubles(P.n, P.N) + (EXACT ? rep_doubles(small_dim<F>(P)) : 0)) * sizeof(double);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // one warp per CTA, as many CTAs per SM as registers / shared memory allow (the warps are latency-bound)
     int per_sm = 0;
@@ -1163,6 +1252,15 @@ static int launch_small(riptrm_handle* h, const SmallParams& P, const DevOpts& o
 }
 
 static int dispatch_small(riptrm_handle* h, int mode, const SmallParams& P, const DevOpts& o, cudaStream_t st) {
+    if (mode == 3 || (mode == 0 && exact_repmat(h))) {   // the exact trust-region solver (hook / whole solve)
+        if (h->family == RIPTRM_FAMILY_STABLEID_PRODUCT && o.is_euclidean_embedded)
+            return fail(RIPTRM_E_UNSUPPORTED, "StableIdentification family: is_euclidean_embedded=True is not built");
+        if (h->family == RIPTRM_FAMILY_ROSENBROCK_GRASSMANN)
+            return mode == 3 ? launch_small<GrassmannFam, 3, true>(h, P, o, st) : launch_small<GrassmannFam, 0, true>(h, P, o, st);
+        if (h->family == RIPTRM_FAMILY_STABLEID_PRODUCT)
+            return mode == 3 ? launch_small<StableIdFam, 3, true>(h, P, o, st) : launch_small<StableIdFam, 0, true>(h, P, o, st);
+        return fail(RIPTRM_E_UNSUPPORTED, "family not built into this library");
+    }
     if (h->family == RIPTRM_FAMILY_ROSENBROCK_GRASSMANN) {
         if (mode == 0) return launch_small<GrassmannFam, 0>(h, P, o, st);
         if (mode == 1) return launch_small<GrassmannFam, 1>(h, P, o, st);
@@ -1238,6 +1336,13 @@ static int launch_fast_lane(riptrm_handle* h, const SphereParams& P, const DevOp
 // index order, 1.06-1.23 for one split at 6, 1.04-1.08 at 8, 1.03-1.04 for splits at 8 and 14, 1.005 with perfect
 // knowledge (scripts/schedule_probe.py + offline list scheduling of the measured per-pair work).
 static int solve_scheduled(riptrm_handle* h, SphereParams P, const DevOpts& o, cudaStream_t st) {
+    if (exact_repmat(h)) {
+        P.order = nullptr;
+        P.pause = nullptr;
+        P.resume = 0;
+        P.pause_at = -1;
+        return dispatch_sphere_exact<0>(h, P, o, st);
+    }
     const int user = h->opts.schedule_split;  //: 0 auto, < 0 off, > 0 one split at that outer iteration
     const int maxiter = h->opts.maxiter;
     const int resident = h->num_sms * 10;
@@ -1412,6 +1517,8 @@ static int run_hook(riptrm_handle* h, int mode, const double* x, const double* y
     if (!h->have_problem) return fail(RIPTRM_E_STATE, "riptrm_set_<family> has not been called");
     if (mode == 2 && !h->have_opts) return fail(RIPTRM_E_STATE, "riptrm_set_options has not been called");
     CUDA_TRY(cudaSetDevice(h->device));
+    if (mode == 3 && (h->family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS || is_stiefel(h)))
+        return fail(RIPTRM_E_UNSUPPORTED, "riptrm_trs: not built for the large-n families");
     if (h->family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS || is_stiefel(h)) return columns_run(h, mode, x, y, mu, Delta, v, out, info, where, st);
     const size_t B = h->batch;
     const size_t xb = B * h->vec_len * sizeof(double), yb = B * h->m * sizeof(double), ib = B * 4 * sizeof(double);
@@ -1425,7 +1532,7 @@ static int run_hook(riptrm_handle* h, int mode, const double* x, const double* y
     P.Delta = Delta;
     DevOpts o{};
     if (h->have_opts) o = make_devopts(h);
-    else { o.tcg_maxinner = -1; o.tcg_theta = 1.0; o.tcg_kappa = 0.1; o.tcg_mininner = 1; }
+    else { o.tcg_maxinner = -1; o.tcg_theta = 1.0; o.tcg_kappa = 0.1; o.tcg_mininner = 1; o.trs_tolhardcase = 1e-8; }
     int rc;
     const bool small = (h->family == RIPTRM_FAMILY_ROSENBROCK_GRASSMANN || h->family == RIPTRM_FAMILY_STABLEID_PRODUCT);
     if (where == RIPTRM_DEVICE) {
@@ -1435,6 +1542,7 @@ static int run_hook(riptrm_handle* h, int mode, const double* x, const double* y
             return dispatch_small(h, mode, Q, o, st);
         }
         P.x0 = x; P.y0 = y; P.v = v; P.out = out; P.info = info;
+        if (mode == 3) return dispatch_sphere_exact<3>(h, P, o, st);
         return mode == 1 ? dispatch_sphere<1>(h, P, o, st) : dispatch_sphere<2>(h, P, o, st);
     }
     if ((rc = ensure(h->d_x0, xb)) || (rc = ensure(h->d_y0, yb)) || (rc = ensure(h->d_x, xb)) ||
@@ -1448,7 +1556,9 @@ static int run_hook(riptrm_handle* h, int mode, const double* x, const double* y
         SmallParams Q = small_params(h);
         Q.x0 = P.x0; Q.y0 = P.y0; Q.v = P.v; Q.out = P.out; Q.info = P.info; Q.mu = mu; Q.Delta = Delta;
         rc = dispatch_small(h, mode, Q, o, st);
-    } else
+    } else if (mode == 3)
+        rc = dispatch_sphere_exact<3>(h, P, o, st);
+    else
         rc = mode == 1 ? dispatch_sphere<1>(h, P, o, st) : dispatch_sphere<2>(h, P, o, st);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(out, h->d_x, xb, cudaMemcpyDeviceToHost, st));
@@ -1466,6 +1576,67 @@ extern "C" int riptrm_hessvec(riptrm_handle* h, const double* x, const double* y
 extern "C" int riptrm_tcg(riptrm_handle* h, const double* x, const double* y, double mu, double Delta, double* eta,
                           double* info, int where, void* stream) {
     return run_hook(h, 2, x, y, mu, Delta, nullptr, eta, info, where, (cudaStream_t)stream);
+}
+
+// Batched dense trust-region subproblems, one warp each: A [count][d][d] symmetric, a [count][d] -> x [count][d],
+// info [count][4] = {type, lam1, |x|, smallest eigenvalue of A}
+__global__ void __launch_bounds__(32) trs_dense_kernel(const double* __restrict__ A, const double* __restrict__ a, int d, int count,
+                                                      double Delta, double tolhard, double* x, double* info) {
+    extern __shared__ __align__(16) double smem[];
+    RepWork rw;
+    rep_init(rw, smem, d);
+    const int lane = lane_id();
+    for (int b = blockIdx.x; b < count; b += gridDim.x) {
+        const double* Ab = A + (size_t)b * d * d;
+        for (int e = lane; e < d * d; e += 32) rw.W[(e / d) * rw.ld + (e % d)] = Ab[e];
+        for (int k = lane; k < d; k += 32) rw.col[k] = a[(size_t)b * d + k];
+        __syncwarp();
+        dense::jacobi_sym(rw.W, rw.VT[0], d, rw.ld);
+        for (int k = lane; k < d; k += 32) rw.D[0][k] = rw.W[k * rw.ld + k];
+        __syncwarp();
+        dense::rows_dot(rw.VT[0], d, rw.ld, rw.col, rw.al[0]);
+        const dense::TrsOut to = dense::trs_eig(rw.D[0], rw.al[0], d, Delta, tolhard, rw.col, rw.ws, rw.W, rw.ld);
+        dense::cols_dot(rw.VT[0], d, rw.ld, rw.col, rw.coef);
+        const double nrm = sqrt(dense::vdot(rw.coef, rw.coef, d));
+        const double mineig = rep_mineig(rw, 0);
+        for (int k = lane; k < d; k += 32) x[(size_t)b * d + k] = rw.coef[k];
+        if (lane < 4) info[(size_t)b * 4 + lane] = (lane == 0) ? (double)to.kind : (lane == 1) ? to.lam1 : (lane == 2) ? nrm : mineig;
+        __syncwarp();
+    }
+}
+
+extern "C" int riptrm_trs_dense(int device, int d, int count, const double* A, const double* a, double Delta, double tolhardcase,
+                                double* x, double* info, int where, void* stream) {
+    if (A == nullptr || a == nullptr || x == nullptr || info == nullptr) return fail(RIPTRM_E_INVALID, "NULL argument");
+    if (d < 1 || d > 64 || count < 1 || !(Delta > 0.0)) return fail(RIPTRM_E_INVALID, "trs_dense: 1 <= d <= 64, count >= 1, Delta > 0");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t ab = (size_t)count * d * d * sizeof(double), vb = (size_t)count * d * sizeof(double), ib = (size_t)count * 4 * sizeof(double);
+    double *dA = const_cast<double*>(A), *da = const_cast<double*>(a), *dx = x, *di = info;
+    if (where != RIPTRM_DEVICE) {
+        CUDA_TRY(cudaMalloc(&dA, ab + 2 * vb + ib));
+        da = dA + (size_t)count * d * d;
+        dx = da + (size_t)count * d;
+        di = dx + (size_t)count * d;
+        CUDA_TRY(cudaMemcpyAsync(dA, A, ab, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(da, a, vb, cudaMemcpyHostToDevice, st));
+    }
+    const size_t smem = rep_doubles(d) * sizeof(double);
+    CUDA_TRY(cudaFuncSetAttribute(trs_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    trs_dense_kernel<<<count < 1184 ? count : 1184, 32, smem, st>>>(dA, da, d, count, Delta, tolhardcase, dx, di);
+    CUDA_TRY(cudaGetLastError());
+    if (where != RIPTRM_DEVICE) {
+        CUDA_TRY(cudaMemcpyAsync(x, dx, vb, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(info, di, ib, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(dA);
+    }
+    return RIPTRM_OK;
+}
+
+extern "C" int riptrm_trs(riptrm_handle* h, const double* x, const double* y, double mu, double Delta, double* dx,
+                          double* info, int where, void* stream) {
+    return run_hook(h, 3, x, y, mu, Delta, nullptr, dx, info, where, (cudaStream_t)stream);
 }
 
 extern "C" int64_t riptrm_launch_count(const riptrm_handle* h) { return h ? h->launches : 0; }

@@ -13,6 +13,7 @@
 //   cactive(ctx,k), dim(ctx), typical_dist(ctx)
 #pragma once
 #include "common.cuh"
+#include "dense_trs.cuh"
 #include "../../include/riptrm_b200.h"
 
 namespace riptrm {
@@ -24,7 +25,92 @@ struct DevOpts {
     const double* mu;    // device, length maxiter + 1
     const double* tolL;  // device
     const double* tolC;  // device
+    // TRS_solver='Exact_RepMat' (RIPTRM.py:431-444) and the second-order test (:599-617)
+    int second_order;
+    double trs_tolhardcase;
+    const double* tolS;  // device: forcing_function_second_order(mu) per outer iteration
 };
+
+// ------------------------------------------------------------------------------------------
+// Exact_RepMat: the representation matrix of Hw in an orthonormal tangent basis and its eigen-decomposition.
+// A family provides the isometry between T_x M and R^dim:
+//   Coord                                   per-point data of the basis (registers / the family's scratch)
+//   coord_setup(ctx, pt, Coord&)            basisfun(manifold, x)                              (RIPTRM.py:433, :600)
+//   from_coords(ctx, pt, cc, coef) -> Vec   sum_i coef_i b_i                                   (:441-443)
+//   to_coords(ctx, pt, cc, v, out)          out_i = <v, b_i>_x                                  (:436-438, utils.py:570)
+// `RepWork` is one warp's shared-memory workspace; slot `cur` holds the decomposition that belongs to the current (x, y)
+// (the reference's is_RepMat_available / basisxCur / HwCurmatrix / cxCurvector, :415-421), slot 1 - cur the one built at
+// the trial point for the eigenvalue test (basisxNew / HwNewmatrix / cxNewvector, :613-615).
+// ------------------------------------------------------------------------------------------
+struct RepWork {
+    double* W;       // d x ld scratch: the matrix handed to jacobi_sym; hard-case system afterwards
+    double* VT[2];   // d x ld each: rows = eigenvectors
+    double* D[2];    // eigenvalues
+    double* al[2];   // coordinates of c in the eigenbasis
+    double* coef;    // d
+    double* col;     // d
+    double* ws;      // 6 d
+    int d, ld;
+    int cur;
+    bool mat_valid;  // (D, VT)[cur] belong to the current (x, y)
+    bool al_valid;   // al[cur] belongs to the current (x, mu)
+};
+__host__ __device__ __forceinline__ int rep_ld(int d) { return (d + 1) | 1; }
+__host__ __device__ __forceinline__ size_t rep_doubles(int d) { return (size_t)3 * d * rep_ld(d) + (size_t)12 * d; }
+__device__ __forceinline__ void rep_init(RepWork& rw, double* mem, int d) {
+    const int ld = rep_ld(d);
+    rw.d = d;
+    rw.ld = ld;
+    rw.W = mem;
+    rw.VT[0] = mem + (size_t)d * ld;
+    rw.VT[1] = mem + (size_t)2 * d * ld;
+    double* v = mem + (size_t)3 * d * ld;
+    rw.D[0] = v;
+    rw.D[1] = v + d;
+    rw.al[0] = v + 2 * d;
+    rw.al[1] = v + 3 * d;
+    rw.coef = v + 4 * d;
+    rw.col = v + 5 * d;
+    rw.ws = v + 6 * d;
+    rw.cur = 0;
+    rw.mat_valid = rw.al_valid = false;
+}
+struct NoRep {};
+
+// selfadj_operator2matrix (utils.py:565-573) + eigen-decomposition into slot `slot`: column j = coordinates of Hw[b_j], the
+// upper triangle is kept and mirrored.  Returns the number of Hessian-vector products (dim).
+template <class F>
+__device__ __forceinline__ int rep_build(const typename F::Ctx& ctx, const typename F::Pt& pt, const typename F::CVec& y,
+                                         const typename F::Step& st, const typename F::Coord& cc, RepWork& rw, int slot) {
+    const int d = rw.d, ld = rw.ld, lane = lane_id();
+    for (int j = 0; j < d; ++j) {
+        for (int k = lane; k < d; k += 32) rw.coef[k] = (k == j) ? 1.0 : 0.0;
+        __syncwarp();
+        const typename F::Vec b = F::from_coords(ctx, pt, cc, rw.coef);
+        const typename F::Vec hb = F::Hw(ctx, pt, y, st, b);
+        F::to_coords(ctx, pt, cc, hb, rw.col);
+        for (int i = lane; i <= j; i += 32) {
+            rw.W[i * ld + j] = rw.col[i];
+            rw.W[j * ld + i] = rw.col[i];
+        }
+        __syncwarp();
+    }
+    dense::jacobi_sym(rw.W, rw.VT[slot], d, ld);
+    for (int k = lane; k < d; k += 32) rw.D[slot][k] = rw.W[k * ld + k];
+    __syncwarp();
+    return d;
+}
+template <class F>
+__device__ __forceinline__ void rep_rhs(const typename F::Ctx& ctx, const typename F::Pt& pt, const typename F::Step& st,
+                                        const typename F::Coord& cc, RepWork& rw, int slot) {
+    F::to_coords(ctx, pt, cc, st.c, rw.col);                         // cxCurvector (:436-438)
+    dense::rows_dot(rw.VT[slot], rw.d, rw.ld, rw.col, rw.al[slot]);
+}
+__device__ __forceinline__ double rep_mineig(const RepWork& rw, int slot) {
+    double m = CUDART_INF;
+    for (int k = lane_id(); k < rw.d; k += 32) m = fmin(m, rw.D[slot][k]);
+    return wmin(m);
+}
 
 struct TcgResult {
     int iters;  // j + 1
@@ -178,14 +264,14 @@ __device__ __forceinline__ EvalRow evaluate(const typename F::Ctx& ctx, const ty
 
 struct InnerInfo {
     double num_inner, radius, dxtype, tcg_iters, normdx, minxfeasi, minyfeasi, compl_v, ared_pred, radius_update,
-        inner_status, dual_clipping;
+        inner_status, dual_clipping, mineig;
 };
 
 __device__ __forceinline__ InnerInfo empty_info() {
     const double nan = CUDART_NAN;
     InnerInfo i;
     i.num_inner = i.radius = i.dxtype = i.tcg_iters = i.normdx = i.minxfeasi = i.minyfeasi = i.compl_v = nan;
-    i.ared_pred = i.radius_update = i.inner_status = i.dual_clipping = nan;
+    i.ared_pred = i.radius_update = i.inner_status = i.dual_clipping = i.mineig = nan;
     return i;
 }
 
@@ -220,6 +306,7 @@ __device__ __forceinline__ void write_trace_row(double* row, int iteration, doub
         case RIPTRM_TR_MAXVIOLATION: v = ev.max_v; break;
         case RIPTRM_TR_MEANVIOLATION: v = ev.mean_v; break;
         case RIPTRM_TR_TIME: v = time_s; break;
+        case RIPTRM_TR_MINEIGVALHW: v = in.mineig; break;
         default: break;
     }
     if (l < RIPTRM_TRACE_FIELDS) row[l] = v;
@@ -242,10 +329,10 @@ struct Counters {
     double inner, tcg, aux;
 };
 
-template <class F>
+template <class F, bool EXACT = false, class Rep = NoRep>
 __device__ __forceinline__ bool inner_step(const typename F::Ctx& ctx, const DevOpts& o, typename F::Pt& pt,
                                            typename F::CVec& y, double mu, double& Delta, double tolL, double tolC,
-                                           int k_inner, InnerInfo& info, Counters& cnt) {
+                                           int k_inner, InnerInfo& info, Counters& cnt, Rep& rw, double tolS = 0.0) {
     using Vec = typename F::Vec;
     using CVec = typename F::CVec;
     constexpr int MK = F::MK;
@@ -256,11 +343,32 @@ __device__ __forceinline__ bool inner_step(const typename F::Ctx& ctx, const Dev
     typename F::Step st;
     F::begin_step(ctx, pt, y, mu, st);                              // s, grad f, c  (:724-730)
 
-    Vec dx, Hdx_unused;
-    const TcgResult tr = F::tcg(ctx, o, pt, y, st, Delta, dx, Hdx_unused);  // :733 -> :445-452
-    cnt.tcg += (double)tr.iters;
-    info.dxtype = (double)tr.stop;
-    info.tcg_iters = (double)tr.iters;
+    Vec dx;
+    if constexpr (EXACT) {
+        // compute_direction, Exact_RepMat branch (:431-444)
+        typename F::Coord cc;
+        F::coord_setup(ctx, pt, cc);
+        if (!rw.mat_valid) {
+            cnt.aux += (double)rep_build<F>(ctx, pt, y, st, cc, rw, rw.cur);
+            rw.mat_valid = true;
+            rw.al_valid = false;
+        }
+        if (!rw.al_valid) {
+            rep_rhs<F>(ctx, pt, st, cc, rw, rw.cur);
+            rw.al_valid = true;
+        }
+        const dense::TrsOut to = dense::trs_eig(rw.D[rw.cur], rw.al[rw.cur], rw.d, Delta, o.trs_tolhardcase, rw.col, rw.ws,
+                                                rw.W, rw.ld);
+        dense::cols_dot(rw.VT[rw.cur], rw.d, rw.ld, rw.col, rw.coef);
+        dx = F::from_coords(ctx, pt, cc, rw.coef);                  // :441-443
+        info.dxtype = (double)to.kind;
+    } else {
+        Vec Hdx_unused;
+        const TcgResult tr = F::tcg(ctx, o, pt, y, st, Delta, dx, Hdx_unused);  // :733 -> :445-452
+        cnt.tcg += (double)tr.iters;
+        info.dxtype = (double)tr.stop;
+        info.tcg_iters = (double)tr.iters;
+    }
     const double normdx = sqrt(F::inner(ctx, pt, dx, dx));          // :735
     info.normdx = normdx;
 
@@ -302,11 +410,38 @@ __device__ __forceinline__ bool inner_step(const typename F::Ctx& ctx, const Dev
     info.minxfeasi = wmin(mins);
     info.minyfeasi = wmin(miny);
     info.compl_v = compl_v;
+    bool eig_ok = true;
+    if constexpr (EXACT) {
+        // :599-617: the matrix of Hw at (xNew, yNew) and its smallest eigenvalue.  Not formed at an infeasible trial point
+        // (the reference forms it there too, from negative y/s weights; the value only reaches the log: NaN here)
+        if (o.second_order && xfe) {
+            typename F::Step stN;
+            F::begin_step(ctx, ptN, yNew, mu, stN);
+            typename F::Coord cn;
+            F::coord_setup(ctx, ptN, cn);
+            cnt.aux += (double)rep_build<F>(ctx, ptN, yNew, stN, cn, rw, 1 - rw.cur);
+            rep_rhs<F>(ctx, ptN, stN, cn, rw, 1 - rw.cur);
+            const double mineig = rep_mineig(rw, 1 - rw.cur);
+            info.mineig = mineig;
+            eig_ok = mineig >= -tolS;                               // :611
+        }
+    }
 
-    if (xfe && yfe && ngl <= tolL && compl_v <= tolC) {             // :762-766
+    if (xfe && yfe && ngl <= tolL && compl_v <= tolC && eig_ok) {   // :762-766
         info.inner_status = (double)RIPTRM_INNER_CONVERGED;
         pt = ptN;
         y = yNew;
+        if constexpr (EXACT) {
+            // Hw does not depend on mu: the decomposition built at (xNew, yNew) serves the next outer iteration, whose
+            // inner_preprocess (:415-421) would rebuild the same matrix; only c changes with mu
+            if (o.second_order) {
+                rw.cur = 1 - rw.cur;
+                rw.mat_valid = true;
+            } else {
+                rw.mat_valid = false;
+            }
+            rw.al_valid = false;
+        }
         return true;
     }
     if (!xfe) {                                                     // :769-775
@@ -362,9 +497,18 @@ __device__ __forceinline__ bool inner_step(const typename F::Ctx& ctx, const Dev
                 yNew.v[k] = cl;
             }
         }
-        info.dual_clipping = wany(clipped_any) ? 1.0 : 0.0;         // :685-695
+        const bool clipped = wany(clipped_any);
+        info.dual_clipping = clipped ? 1.0 : 0.0;                   // :685-695
         pt = ptN;
         y = yNew;
+        if constexpr (EXACT) {
+            if (!clipped && o.second_order) {                       // :687-692: HwNewmatrix becomes HwCurmatrix
+                rw.cur = 1 - rw.cur;
+                rw.mat_valid = rw.al_valid = true;
+            } else {
+                rw.mat_valid = rw.al_valid = false;
+            }
+        }
     } else {
         info.inner_status = (double)RIPTRM_INNER_UNSUCCESSFUL;      // :697-702
     }
@@ -386,13 +530,13 @@ struct PauseState {
     double Delta, it, inner, tcg, aux, rows, elapsed_s, paused;
 };
 
-template <class F>
+template <class F, bool EXACT = false, class Rep = NoRep>
 __device__ __forceinline__ void solve_instance(const typename F::Ctx& ctx, const DevOpts& o,
                                                const typename F::Vec& x0, const typename F::CVec& y0,
                                                typename F::Pt& pt, typename F::CVec& y, double* summary,
                                                double* trace /* this instance's rows or nullptr */,
                                                double* pause /* kPauseFields doubles or nullptr */, bool resume,
-                                               int pause_at /* outer iteration to pause at; < 0: never */) {
+                                               int pause_at /* outer iteration to pause at; < 0: never */, Rep* rwp = nullptr) {
     using Vec = typename F::Vec;
     using CVec = typename F::CVec;
     F::eval_point(ctx, x0, pt);                                     // outer_preprocess (:849-864)
@@ -446,6 +590,11 @@ __device__ __forceinline__ void solve_instance(const typename F::Ctx& ctx, const
         // ---- outer_step (:866-896)
         mu = o.mu[it - 1];
         const double tolL = o.tolL[it - 1], tolC = o.tolC[it - 1];  // :881-885
+        double tolS = 0.0;
+        if constexpr (EXACT) {
+            tolS = o.second_order ? o.tolS[it - 1] : 0.0;
+            rwp->al_valid = false;                                  // c depends on mu
+        }
         // ---- inner_run (:785-847)
         const typename F::Pt pt_init = pt;
         const CVec y_init = y;
@@ -455,7 +604,13 @@ __device__ __forceinline__ void solve_instance(const typename F::Ctx& ctx, const
         int k = 0;
         while (true) {
             k += 1;                                                 // :808
-            bool done = inner_step<F>(ctx, o, pt, y, mu, Delta, tolL, tolC, k, info, cnt);  // :810
+            bool done;
+            if constexpr (EXACT) {
+                done = inner_step<F, true, Rep>(ctx, o, pt, y, mu, Delta, tolL, tolC, k, info, cnt, *rwp, tolS);
+            } else {
+                NoRep none;
+                done = inner_step<F>(ctx, o, pt, y, mu, Delta, tolL, tolC, k, info, cnt, none);  // :810
+            }
             cnt.inner += 1.0;
             if (o.trace_mode == 1) {                                // :812-818
                 if (trace != nullptr && rows < o.trace_capacity) {
@@ -485,6 +640,7 @@ __device__ __forceinline__ void solve_instance(const typename F::Ctx& ctx, const
                 pt = pt_init;
                 y = y_init;
                 Delta = Delta_init;
+                if constexpr (EXACT) rwp->mat_valid = rwp->al_valid = false;
             }
             if (done) break;                                        // :844-845
         }

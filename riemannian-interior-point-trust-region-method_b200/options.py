@@ -10,7 +10,11 @@ from . import _lib
 
 
 def default_option():
-    """Same keys and values as RIPTRM.py:305-358.  `basisfun` (Exact_RepMat only) is omitted."""
+    """Same keys and values as RIPTRM.py:305-358.  `basisfun`: the reference's default draws a RANDOM tangent basis
+    (utils.tangentorthobasis); the device builds a fixed orthonormal basis per manifold (basis.deterministic_basisfun is
+    the same construction in NumPy) -- step and eigenvalues do not depend on the basis, so the key is accepted and the
+    callable is not evaluated."""
+    from .basis import deterministic_basisfun
     return {
         # Stopping criteria
         "maxtime": 240,
@@ -46,6 +50,7 @@ def default_option():
         "do_simple_barrier_parameter_update": True,
         "const_left": 0.5,
         "const_right": 1e20,
+        "basisfun": deterministic_basisfun,
         # Display setting
         "verbosity": 0,
         "manviofun": lambda problem, x: 0,
@@ -82,17 +87,19 @@ def barrier_schedule(option):
     return mu, tolL, tolC
 
 
+def second_order_schedule(option, mu):
+    """forcing_function_second_order(mu) per outer iteration (RIPTRM.py:886-887)."""
+    fS = option["forcing_function_second_order"]
+    return np.array([fS(float(m)) for m in mu], dtype=np.float64)
+
+
 def check_supported(option):
-    """The GPU path covers the tCG trust-region solver; anything else raises --
-    there is no CPU fallback."""
-    if option["TRS_solver"] != "tCG":
-        raise NotImplementedError(
-            "riptrm_b200 implements TRS_solver='tCG' (set solver_option.RIPTRM.TRS_solver: 'tCG' as the "
-            "reference's config_simulation.yaml does); 'Exact_RepMat' is not on the GPU path")
-    if option["second_order_stationarity"]:
-        raise NotImplementedError("second_order_stationarity=True needs the Exact_RepMat path (not on the GPU)")
+    """The GPU path covers both trust-region solvers of the reference: 'tCG' and the class default 'Exact_RepMat' (with or
+    without the second-order test); anything else raises -- there is no CPU fallback."""
+    if option["TRS_solver"] not in ("tCG", "Exact_RepMat"):
+        raise ValueError(f"TRS_solver {option['TRS_solver']} is not supported.")        # RIPTRM.py:453-454
     if option.get("checkTRSoptimality"):
-        raise NotImplementedError("checkTRSoptimality is a debug aid of the Exact_RepMat path")
+        raise NotImplementedError("checkTRSoptimality is a print-only debug aid (RIPTRM.py:367-388): not on the GPU path")
 
 
 def to_c_options(option, trace_mode, trace_capacity):
@@ -124,4 +131,11 @@ def to_c_options(option, trace_mode, trace_capacity):
     o.mu_sched = mu.ctypes.data_as(dp)
     o.tol_lagrangian_sched = tolL.ctypes.data_as(dp)
     o.tol_complementarity_sched = tolC.ctypes.data_as(dp)
-    return o, (mu, tolL, tolC)
+    exact = option["TRS_solver"] == "Exact_RepMat"
+    o.trs_solver = _lib.TRS_SOLVER_EXACT_REPMAT if exact else _lib.TRS_SOLVER_TCG
+    # the reference evaluates the eigenvalue test only under Exact_RepMat (RIPTRM.py:599): with tCG the flag has no effect
+    o.second_order_stationarity = int(bool(option["second_order_stationarity"]) and exact)
+    o.trs_tolhardcase = float(option.get("TRS_tolhardcase", 1e-8))
+    tolS = second_order_schedule(option, mu) if o.second_order_stationarity else None
+    o.tol_second_order_sched = tolS.ctypes.data_as(dp) if tolS is not None else None
+    return o, (mu, tolL, tolC, tolS)

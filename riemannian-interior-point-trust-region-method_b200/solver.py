@@ -177,6 +177,16 @@ class BatchSolver:
                                            _lib.ptr(np.ascontiguousarray(v)), _lib.ptr(out), _lib.HOST, None))
         return out
 
+    def trs(self, x, y, mu, Delta):
+        """One exact trust-region solve per pair (RIPTRM.py:431-444, `TRSgep` :218-299): returns (dx [B, n*p],
+        info [B, 4] = {type code, lam1, ||dx||, smallest eigenvalue of the representation matrix of Hw})."""
+        dx = np.empty_like(self.x0)
+        info = np.empty((self.batch, 4))
+        _lib.check(self.lib.riptrm_trs(self.handle.h, _lib.ptr(np.ascontiguousarray(x)),
+                                       _lib.ptr(np.ascontiguousarray(y)), float(mu), float(Delta), _lib.ptr(dx),
+                                       _lib.ptr(info), _lib.HOST, None))
+        return dx, info
+
     def tcg(self, x, y, mu, Delta):
         eta = np.empty_like(self.x0)
         info = np.empty((self.batch, 4))
@@ -464,11 +474,16 @@ def trace_to_log(rows, save_inner_iteration=True):
     log["inner_status"] = [_code(r[T["inner_status"]], _lib.INNER_STATUS_NAMES) for r in rows]
     log["TR_radius"] = [_opt(r[T["TR_radius"]]) for r in rows]
     if save_inner_iteration:
-        log["dxtype"] = [None if math.isnan(r[T["dxtype"]]) else "tCG_" + _lib.TCG_STOP_NAMES[int(r[T["dxtype"]])]
-                         for r in rows]
+        def dxtype(v):
+            if math.isnan(v):
+                return None
+            v = int(v)
+            return _lib.TRS_TYPE_NAMES[v] if v in _lib.TRS_TYPE_NAMES else "tCG_" + _lib.TCG_STOP_NAMES[v]
+        log["dxtype"] = [dxtype(r[T["dxtype"]]) for r in rows]
         for c in ("normdx", "minxfeasi", "minyfeasi", "compl"):
             log[c] = [_opt(r[T[c]]) for r in rows]
-        log["mineigvalHw"] = [None for _ in rows]
+        wide = len(rows) > 0 and len(rows[0]) > T["mineigvalHw"]     # rows of the C oracle have 25 fields
+        log["mineigvalHw"] = [_opt(r[T["mineigvalHw"]]) if wide else None for r in rows]
         log["ared/pred"] = [_opt(r[T["ared/pred"]]) for r in rows]
         log["radius_update"] = [_code(r[T["radius_update"]], _lib.RADIUS_UPDATE_NAMES) for r in rows]
         log["dual_clipping"] = [None if math.isnan(r[T["dual_clipping"]]) else bool(r[T["dual_clipping"]])
@@ -566,7 +581,8 @@ def check_user_functions(option, problem, st, log):
 
 
 class RIPTRM:
-    """Drop-in for the reference's `RIPTRM` class on the tCG path (src/solver/RIPTRM.py:302-976)."""
+    """Drop-in for the reference's `RIPTRM` class (src/solver/RIPTRM.py:302-976): both trust-region solvers, 'tCG' and the
+    class default 'Exact_RepMat' with the second-order stationarity test."""
 
     def __init__(self, option):
         default_option = _options.default_option()

@@ -37,6 +37,15 @@ for _pt in "abcdefghijklmnopqrst":
     CASES[f"stableid_1_{_pt}_K30"] = ("StableIdentification", {"solver_option.common.maxiter": 30,
                                                                  "solver_option.RIPTRM.inner_maxiter": 1000,
                                                                  "problem_initialpoint": _pt})
+# round 2: the reference's class-default trust-region solver (TRS_solver='Exact_RepMat', second_order_stationarity=True,
+# RIPTRM.py:323-324) with a deterministic `basisfun` (riptrm_b200/basis.py; the reference's default basis is random)
+EXACT = {"solver_option.RIPTRM.TRS_solver": "Exact_RepMat", "solver_option.RIPTRM.second_order_stationarity": True,
+         "solver_option.RIPTRM.inner_maxiter": 1000}
+CASES["nonnegpca_1_a_exact_K40"] = ("NonnegPCA", dict(EXACT, **{"solver_option.common.maxiter": 40}))
+CASES["rosenbrock_exact_K14"] = ("Rosenbrock", dict(EXACT, **{"solver_option.common.maxiter": 14}))
+for _pt in "abt":
+    CASES[f"stableid_1_{_pt}_exact_K30"] = ("StableIdentification", dict(EXACT, **{"solver_option.common.maxiter": 30,
+                                                                                   "problem_initialpoint": _pt}))
 REDUCED = {"rosenbrock_K14", "rosenbrock_K20"} | {f"stableid_1_{_pt}_K30" for _pt in "abcdefghijklmnopqrst"}
 # columns whose values depend on the reference's unseeded RNG (Rosenbrock callback,
 # src/Rosenbrock/simulator.py:52-57) or on wall-clock
@@ -66,7 +75,12 @@ def run_case(name):
     problem, ov = CASES[name]
     overrides = dict(COMMON)
     overrides.update(ov)
-    out, tcg, _ = run_reference(problem, overrides)
+    extra = None
+    if overrides.get("solver_option.RIPTRM.TRS_solver") == "Exact_RepMat":
+        import riptrm_b200
+        from riptrm_b200.basis import deterministic_basisfun
+        extra = {"basisfun": deterministic_basisfun}
+    out, tcg, _ = run_reference(problem, overrides, extra_option=extra)
     log = {k: _jsonable(v) for k, v in out.log.items() if k not in SKIP_COLUMNS}
     rows_total = len(log["iteration"])
     inner_per_outer = None

@@ -36,9 +36,9 @@ def test_header_symbols_exported(built):
 
 def test_abi_version_and_struct_layout(built):
     lib = built.load_library()
-    assert lib.riptrm_abi_version() == 1
-    # riptrm_options: 8 x int32, 13 x double, 3 pointers
-    assert ctypes.sizeof(built._lib.RiptrmOptions) == 8 * 4 + 13 * 8 + 3 * 8
+    assert lib.riptrm_abi_version() == 2
+    # riptrm_options: 8 x int32, 13 x double, 3 pointers; ABI 2 appends 2 x int32, 1 double, 1 pointer
+    assert ctypes.sizeof(built._lib.RiptrmOptions) == 8 * 4 + 13 * 8 + 3 * 8 + 2 * 4 + 8 + 8
     src = open(HEADER).read()
     assert int(re.search(r"#define RIPTRM_TRACE_FIELDS (\d+)", src).group(1)) == built._lib.TRACE_FIELDS
     assert int(re.search(r"#define RIPTRM_SUMMARY_FIELDS (\d+)", src).group(1)) == built._lib.SUMMARY_FIELDS

@@ -18,7 +18,7 @@ def test_defaults_match_oracle_defaults():
             for mu in (0.1, 1e-6, 1e-16):
                 if k.startswith("forcing"):
                     assert d[k](mu) == v(mu)
-        elif k not in ("TRS_solver", "second_order_stationarity"):
+        elif k not in ("TRS_solver", "second_order_stationarity", "basisfun"):
             assert d[k] == v, k
     # the reference's class defaults (RIPTRM.py:320-321): Exact_RepMat + second order; configs override to tCG
     assert d["TRS_solver"] == "Exact_RepMat" and d["second_order_stationarity"] is True
@@ -40,13 +40,43 @@ def test_barrier_schedule():
     assert mu2[1] == min(0.8 * 0.1, 0.5 * 0.1 ** 1.01)
 
 
-def test_unsupported_options_raise():
-    for bad in ({"TRS_solver": "Exact_RepMat", "second_order_stationarity": False},
-                {"TRS_solver": "tCG", "second_order_stationarity": True}):
-        opt = options.default_option()
-        opt.update(bad)
-        with pytest.raises(NotImplementedError):
-            options.check_supported(opt)
+def test_trs_solver_options():
+    """Both trust-region solvers of the reference are accepted (the class default is 'Exact_RepMat' with the second-order
+    test, RIPTRM.py:323-324); an unknown solver raises the reference's error (:453-454)."""
+    opt = options.default_option()
+    assert opt["TRS_solver"] == "Exact_RepMat" and opt["second_order_stationarity"] is True and callable(opt["basisfun"])
+    options.check_supported(opt)
+    o, keep = options.to_c_options(dict(opt, maxiter=5), 1, 64)
+    assert (o.trs_solver, o.second_order_stationarity, o.trs_tolhardcase) == (1, 1, 1e-8)
+    assert np.allclose(keep[3], keep[0])                 # forcing_function_second_order(mu) = mu
+    o, keep = options.to_c_options(dict(opt, maxiter=5, TRS_solver="tCG"), 1, 64)
+    assert (o.trs_solver, o.second_order_stationarity) == (0, 0) and keep[3] is None   # no eigenvalue test under tCG (:599)
+    with pytest.raises(ValueError, match="not supported"):
+        options.check_supported(dict(opt, TRS_solver="Newton"))
+    with pytest.raises(NotImplementedError):
+        options.check_supported(dict(opt, checkTRSoptimality=True))
+
+
+def test_deterministic_tangent_bases_are_orthonormal(datasets):
+    """riptrm_b200/basis.py (`basisfun` for reproducible reference runs; the kernels build the same bases): dim vectors,
+    tangent, orthonormal in the manifold's metric."""
+    from oracle import manifolds as M
+    from riptrm_b200.basis import deterministic_basisfun
+    rng = np.random.RandomState(0)
+    d = datasets["StableIdentification/1"]
+    cases = [(M.Sphere(50), datasets["NonnegPCA/1"]["initx_a"]),
+             (M.Grassmann(5, 3), np.linalg.qr(rng.randn(5, 3))[0]),
+             (M.Product([M.SkewSymmetric(5), M.SymmetricPositiveDefinite(5), M.SymmetricPositiveDefinite(5)]),
+              [d["initJ_a"], d["initR_a"], d["initQ_a"]])]
+    for man, x in cases:
+        B = deterministic_basisfun(man, x)
+        assert len(B) == man.dim
+        G = np.array([[man.inner_product(x, a, b) for b in B] for a in B])
+        assert np.max(np.abs(G - np.eye(man.dim))) < 1e-12
+        for b in B[:: max(1, man.dim // 7)]:
+            pb = man.to_tangent_space(x, b)
+            diff = (pb - b) if not isinstance(b, list) else [u - v for u, v in zip(pb, b)]
+            assert man.norm(x, diff) < 1e-12
 
 
 def test_trace_to_log_schema():
@@ -65,6 +95,14 @@ def test_trace_to_log_schema():
     row1[T["radius_update"]] = 2
     row1[T["dual_clipping"]] = 1
     row1[T["tcg_iters"]] = 7
+    row1[T["mineigvalHw"]] = nan
+    row2 = row1.copy()                       # a row of the exact trust-region solver
+    row2[T["dxtype"]] = 7
+    row2[T["tcg_iters"]] = nan
+    row2[T["mineigvalHw"]] = 2.5
+    logx = rb.trace_to_log(np.stack([row0, row2]))
+    assert logx["dxtype"] == [None, "interior"] and logx["mineigvalHw"] == [None, 2.5] and logx["tcg_iters"] == [None, None]
+    assert rb.trace_to_log(np.stack([row0[:25], row1[:25]]))["mineigvalHw"] == [None, None]   # 25-field rows (C oracle)
     log = rb.trace_to_log(np.stack([row0, row1]))
     # reference column order: base_solver.py:58-76, utils.py:356-364, RIPTRM.py:980-1024
     assert list(log)[:11] == ["iteration", "time", "cost", "distance", "residual", "gradnorm", "complviolation",
