@@ -245,6 +245,17 @@ int riptrm_tcg(riptrm_handle* h, const double* x, const double* y, double mu, do
 int riptrm_trs(riptrm_handle* h, const double* x, const double* y, double mu, double Delta, double* dx,
                double* info, int where, void* stream);
 
+/* The condensed Newton system of the reference's Riemannian interior-point method on the same operator (SURVEY.md section 8f
+ * rank 4; src/solver/RIPM.py:484-511):   Aw[dx] = Hess_x L(x, z)[dx] + G_x( G*_x[dx] * z / s ) = c,   with the slacks s an
+ * independent variable [batch][m] and c [batch][n*p] the right-hand side (made tangent on entry).
+ *   method 0: RepresentMatMethod (RIPM.py:238-300; no equality constraints) -- representation matrix in the tangent basis, dense
+ *             symmetric solve;   method 1: TangentSpaceConjResMethod (utils.py:582-618) -- conjugate residuals from v0 = 0 until
+ *             |r| / |c| < tol ('KrylovTolrelresid') or `maxiter` ('KrylovMaxIteration') iterations.
+ * dx [batch][n*p]; info [batch][4] = {iterations (0 for method 0), |c - Aw dx| / |c|, ||dx||_x, smallest eigenvalue of the
+ * matrix of Aw (method 0; NaN for method 1)}.  Sphere (n <= 64), Grassmann and Product families. */
+int riptrm_newton(riptrm_handle* h, const double* x, const double* z, const double* s, const double* c, int method,
+                  double tol, int maxiter, double* dx, double* info, int where, void* stream);
+
 /* The dense core of the above on caller-supplied data -- `TRSgep(A, a, I, Delta, tolhardcase)` (RIPTRM.py:218-299) for `count`
  * independent problems, one warp each: A [count][d][d] symmetric, a [count][d] -> x [count][d], info [count][4] = {type, lam1,
  * ||x||, smallest eigenvalue of A}.  d <= 64. */

@@ -377,6 +377,57 @@ def trs_gep(A, a, B, Del, tolhardcase=1e-4):
 
 
 # --------------------------------------------------------------------------
+# The condensed Newton system of the reference's interior-point method (RIPM.py:484-511), same operator as Hw
+# --------------------------------------------------------------------------
+def newton_operator(problem, x, z, s, lincomb=False):
+    """OperatorAw = OperatorHessLag + OperatorTHETA (RIPM.py:491-493): dx -> Hess L(x, z)[dx] + G_x(G*_x[dx] * z / s), the
+    slack s an independent variable."""
+    def Aw(dx):
+        return hess_lagrangian(problem, x, z, dx, lincomb) + G_apply(problem, x, Gadj_apply(problem, x, dx) * (z / s), lincomb)
+    return Aw
+
+
+def newton_repmat(problem, x, z, s, c, basis):
+    """RepresentMatMethod without equality constraints (RIPM.py:238-300): T_mat = Aw_mat, scipy.linalg.solve(assume_a='sym')."""
+    import scipy.linalg
+    man = problem.manifold
+    Aw = newton_operator(problem, x, z, s)
+    Amat = operator_matrix(man, x, Aw, basis)
+    sol = scipy.linalg.solve(Amat, tangent_coords(man, x, basis, c), assume_a="sym")
+    dx = man.zero_vector(x)
+    for i in range(len(basis)):
+        dx = dx + sol[i] * basis[i]
+    return dx, Amat
+
+
+def conj_res(man, x, A, b, tol, maxiter):
+    """TangentSpaceConjResMethod (utils.py:582-618; Saad, Iterative Methods for Sparse Linear Systems, Alg. 6.20), v0 = 0."""
+    v = man.zero_vector(x)
+    r = b
+    p = copy.deepcopy(r)
+    b_norm = man.norm(x, b)
+    Ar = A(r)
+    Ap = A(p)
+    rAr = man.inner_product(x, r, Ar)
+    t = 0
+    while True:
+        t += 1
+        a = rAr / man.inner_product(x, Ap, Ap)
+        v = v + a * p
+        r = r - a * Ap
+        rel_res = man.norm(x, r) / b_norm
+        if rel_res < tol or t == maxiter:
+            break
+        Ar = A(r)
+        old = rAr
+        rAr = man.inner_product(x, r, Ar)
+        beta = rAr / old
+        p = r + beta * p
+        Ap = Ar + beta * Ap
+    return v, t, rel_res
+
+
+# --------------------------------------------------------------------------
 # The solver
 # --------------------------------------------------------------------------
 class OracleRIPTRM:

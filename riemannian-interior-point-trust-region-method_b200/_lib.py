@@ -80,6 +80,8 @@ SYMBOLS = {
                              C.c_void_p, C.c_int, C.c_void_p]),
     "riptrm_trs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
                              C.c_void_p, C.c_int, C.c_void_p]),
+    "riptrm_newton": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "riptrm_trs_dense": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
                                    C.c_void_p, C.c_int, C.c_void_p]),
     "riptrm_generate_nonnegpca": (C.c_int, [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_double, C.c_double,

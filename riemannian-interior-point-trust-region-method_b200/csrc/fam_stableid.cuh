@@ -330,9 +330,20 @@ struct StableIdFam {
         return mul(c, v.v[0] - v.v[1], pt.x.v[2]) + mul(c, pt.JmR, v.v[2]);
     }
 
+    // 'is_euclidean_embedded' (RIPTRM.py:553-571): G*[v]_i = <-egrad g_i, v>_x with the EUCLIDEAN gradient inside the
+    // manifold's inner product.  On the SPD components that metric is tr(P^-1 A P^-1 B), so with -egrad g_i = -coef_i pull(E_rc)
+    // the entry of dA is taken with v_R -> R^-1 v_R R^-1 and v_Q -> Q^-1 v_Q Q^-1 (not the same operator as the Riemannian
+    // form on this manifold -- the option is meant for submanifolds with the embedded metric -- but it is what the reference
+    // evaluates when the key is set).
+    static __device__ __forceinline__ LM dA_embedded(const Ctx& c, const Pt& pt, const Vec& v) {
+        const LM wR = mul(c, mul(c, pt.Rinv, v.v[1]), pt.Rinv);
+        const LM wQ = mul(c, mul(c, pt.Qinv, v.v[2]), pt.Qinv);
+        return mul(c, v.v[0] - wR, pt.x.v[2]) + mul(c, pt.JmR, wQ);
+    }
+
     static __device__ __forceinline__ CVec gadj(const Ctx& c, const Pt& pt, const Vec& v) {
         CVec g;
-        g.v[0] = -pt.coef.v[0] * at_constraint(c, dA_of(c, pt, v));
+        g.v[0] = -pt.coef.v[0] * at_constraint(c, c.embedded ? dA_embedded(c, pt, v) : dA_of(c, pt, v));
         return g;
     }
 
@@ -371,7 +382,8 @@ struct StableIdFam {
         }
         // condensed barrier term G_x((y/s) * G*[v]) = -rgrad(pull(sum_i w_i Phi_i))
         CVec w;
-        w.v[0] = st.ys.v[0] * (-pt.coef.v[0] * dArc);
+        const double gArc = c.embedded ? at_constraint(c, dA_embedded(c, pt, v)) : dArc;
+        w.v[0] = st.ys.v[0] * (-pt.coef.v[0] * gArc);
         const Vec gw = rgrad_of_phi(c, pt, scatter(c, w, pt.coef, 0.0));
         Vec out;
 #pragma unroll

@@ -117,6 +117,10 @@ struct SphereParams {
     double Delta;
     double* out;
     double* info;
+    // riptrm_newton: explicit slacks [batch][m], solver (0 RepMat, 1 conjugate residuals), CR tolerance / iteration cap
+    const double* slack;
+    int newton_method, kr_maxiter;
+    double kr_tol;
 };
 
 // Loads Z of one instance into shared memory and symmetrises it in place: S = Z + Z'
@@ -182,7 +186,23 @@ __device__ __forceinline__ void trs_hook(const typename F::Ctx& ctx, const DevOp
         info4[lane] = (lane == 0) ? (double)to.kind : (lane == 1) ? to.lam1 : (lane == 2) ? nrm : mineig;
 }
 
-// mode 0: whole solve; 1: one Hessian-vector product; 2: one tCG solve; 3: one exact trust-region solve (EXACT only)
+// riptrm_newton: st.ys <- z / s with the caller's slacks, the right-hand side made tangent, then one of the two solvers
+template <class F>
+__device__ __forceinline__ void newton_hook(const typename F::Ctx& ctx, const typename F::Pt& pt, const typename F::CVec& z,
+                                            typename F::Step& st, const typename F::CVec& sl, const typename F::Vec& rhs, int method,
+                                            double tol, int maxiter, RepWork& rw, typename F::Vec& dx, double* info4) {
+#pragma unroll
+    for (int k = 0; k < F::MK; ++k) st.ys.v[k] = F::cactive(ctx, k) ? z.v[k] / sl.v[k] : 0.0;
+    const typename F::Vec c = F::project(ctx, pt, rhs);
+    const NewtonOut no = (method == 0) ? newton_repmat<F>(ctx, pt, z, st, c, rw, dx) : newton_cr<F>(ctx, pt, z, st, c, tol, maxiter, dx);
+    const double nrm = sqrt(F::inner(ctx, pt, dx, dx));
+    const int lane = lane_id();
+    if (info4 != nullptr && lane < 4)
+        info4[lane] = (lane == 0) ? no.iters : (lane == 1) ? no.rel_res : (lane == 2) ? nrm : no.mineig;
+}
+
+// mode 0: whole solve; 1: one Hessian-vector product; 2: one tCG solve; 3: one exact trust-region solve (EXACT only);
+// 4: one condensed Newton-system solve of the interior-point method (EXACT only: it shares the RepWork workspace)
 // EXACT: TRS_solver='Exact_RepMat' -- the representation-matrix workspace (RepWork) follows S in shared memory
 template <int K, int MODE, int NFIX, bool EXACT = false>
 __global__ void __launch_bounds__(32, EXACT ? 1 : ((K == 2) ? 10 : 4)) sphere_kernel(SphereParams P, DevOpts o, int* counter) {
@@ -249,6 +269,15 @@ __global__ void __launch_bounds__(32, EXACT ? 1 : ((K == 2) ? 10 : 4)) sphere_ke
                 if constexpr (EXACT) {
                     typename F::Vec dx;
                     trs_hook<F>(ctx, o, pt, y0, st, P.Delta, rw, dx, P.info ? P.info + (size_t)inst * 4 : nullptr);
+                    store_vec<K>(P.out + (size_t)inst * n, dx, n);
+                }
+            } else if (MODE == 4) {
+                if constexpr (EXACT) {
+                    typename F::Vec dx;
+                    const typename F::CVec sl = load_vec<K>(P.slack + (size_t)inst * n, n);
+                    const typename F::Vec rhs = load_vec<K>(P.v + (size_t)inst * n, n);
+                    newton_hook<F>(ctx, pt, y0, st, sl, rhs, P.newton_method, P.kr_tol, P.kr_maxiter, rw, dx,
+                                   P.info ? P.info + (size_t)inst * 4 : nullptr);
                     store_vec<K>(P.out + (size_t)inst * n, dx, n);
                 }
             } else {
@@ -1159,6 +1188,9 @@ struct SmallParams {
     double mu, Delta;
     double* out;
     double* info;
+    const double* slack;           // riptrm_newton (see SphereParams)
+    int newton_method, kr_maxiter;
+    double kr_tol;
 };
 
 template <class F, int MODE, bool EXACT = false>
@@ -1209,6 +1241,15 @@ __global__ void __launch_bounds__(32, EXACT ? 4 : 16) small_kernel(SmallParams P
                     trs_hook<F>(ctx, o, pt, y0, st, P.Delta, rw, dx, P.info ? P.info + (size_t)inst * 4 : nullptr);
                     F::store_x(ctx, P.out + (size_t)inst * xl, dx);
                 }
+            } else if (MODE == 4) {
+                if constexpr (EXACT) {
+                    typename F::Vec dx;
+                    const typename F::CVec sl = F::load_y(ctx, P.slack + (size_t)inst * P.m);
+                    const typename F::Vec rhs = F::load_x(ctx, P.v + (size_t)inst * xl);
+                    newton_hook<F>(ctx, pt, y0, st, sl, rhs, P.newton_method, P.kr_tol, P.kr_maxiter, rw, dx,
+                                   P.info ? P.info + (size_t)inst * 4 : nullptr);
+                    F::store_x(ctx, P.out + (size_t)inst * xl, dx);
+                }
             } else {
                 typename F::Vec eta, Heta;
                 const TcgResult r = F::tcg(ctx, o, pt, y0, st, P.Delta, eta, Heta);
@@ -1252,13 +1293,13 @@ static int launch_small(riptrm_handle* h, const SmallParams& P, const DevOpts& o
 }
 
 static int dispatch_small(riptrm_handle* h, int mode, const SmallParams& P, const DevOpts& o, cudaStream_t st) {
-    if (mode == 3 || (mode == 0 && exact_repmat(h))) {   // the exact trust-region solver (hook / whole solve)
-        if (h->family == RIPTRM_FAMILY_STABLEID_PRODUCT && o.is_euclidean_embedded)
-            return fail(RIPTRM_E_UNSUPPORTED, "StableIdentification family: is_euclidean_embedded=True is not built");
+    if (mode == 3 || mode == 4 || (mode == 0 && exact_repmat(h))) {   // exact trust-region solver (hook / whole solve), Newton hook
         if (h->family == RIPTRM_FAMILY_ROSENBROCK_GRASSMANN)
-            return mode == 3 ? launch_small<GrassmannFam, 3, true>(h, P, o, st) : launch_small<GrassmannFam, 0, true>(h, P, o, st);
+            return mode == 3 ? launch_small<GrassmannFam, 3, true>(h, P, o, st)
+                 : mode == 4 ? launch_small<GrassmannFam, 4, true>(h, P, o, st) : launch_small<GrassmannFam, 0, true>(h, P, o, st);
         if (h->family == RIPTRM_FAMILY_STABLEID_PRODUCT)
-            return mode == 3 ? launch_small<StableIdFam, 3, true>(h, P, o, st) : launch_small<StableIdFam, 0, true>(h, P, o, st);
+            return mode == 3 ? launch_small<StableIdFam, 3, true>(h, P, o, st)
+                 : mode == 4 ? launch_small<StableIdFam, 4, true>(h, P, o, st) : launch_small<StableIdFam, 0, true>(h, P, o, st);
         return fail(RIPTRM_E_UNSUPPORTED, "family not built into this library");
     }
     if (h->family == RIPTRM_FAMILY_ROSENBROCK_GRASSMANN) {
@@ -1267,7 +1308,6 @@ static int dispatch_small(riptrm_handle* h, int mode, const SmallParams& P, cons
         return launch_small<GrassmannFam, 2>(h, P, o, st);
     }
     if (h->family == RIPTRM_FAMILY_STABLEID_PRODUCT) {
-        if (o.is_euclidean_embedded) return fail(RIPTRM_E_UNSUPPORTED, "StableIdentification family: is_euclidean_embedded=True is not built");
         if (mode == 0) return launch_small<StableIdFam, 0>(h, P, o, st);
         if (mode == 1) return launch_small<StableIdFam, 1>(h, P, o, st);
         return launch_small<StableIdFam, 2>(h, P, o, st);
@@ -1632,6 +1672,61 @@ extern "C" int riptrm_trs_dense(int device, int d, int count, const double* A, c
         cudaFree(dA);
     }
     return RIPTRM_OK;
+}
+
+// RIPM's condensed Newton system on the same Hessian-vector operator (RIPM.py:484-511)
+extern "C" int riptrm_newton(riptrm_handle* h, const double* x, const double* z, const double* s, const double* c, int method,
+                             double tol, int maxiter, double* dx, double* info, int where, void* stream) {
+    if (h == nullptr || x == nullptr || z == nullptr || s == nullptr || c == nullptr || dx == nullptr)
+        return fail(RIPTRM_E_INVALID, "NULL argument");
+    if (method != 0 && method != 1) return fail(RIPTRM_E_INVALID, "riptrm_newton: method 0 (RepresentMatMethod) or 1 (TangentSpaceConjResMethod)");
+    if (method == 1 && (!(tol >= 0.0) || maxiter < 1)) return fail(RIPTRM_E_INVALID, "riptrm_newton: tol >= 0, maxiter >= 1");
+    if (!h->have_problem) return fail(RIPTRM_E_STATE, "riptrm_set_<family> has not been called");
+    if (h->family == RIPTRM_FAMILY_NONNEGPCA_COLUMNS || is_stiefel(h))
+        return fail(RIPTRM_E_UNSUPPORTED, "riptrm_newton: not built for the large-n families");
+    if (h->family == RIPTRM_FAMILY_NONNEGPCA_SPHERE && h->n > 64) return fail(RIPTRM_E_UNSUPPORTED, "riptrm_newton on Sphere(n): n <= 64");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = h->batch;
+    const size_t xb = B * h->vec_len * sizeof(double), yb = B * h->m * sizeof(double), ib = B * 4 * sizeof(double);
+    DevOpts o{};
+    if (h->have_opts) o = make_devopts(h);
+    const bool small = (h->family == RIPTRM_FAMILY_ROSENBROCK_GRASSMANN || h->family == RIPTRM_FAMILY_STABLEID_PRODUCT);
+    const double *px = x, *pz = z, *ps = s, *pc = c;
+    double *pdx = dx, *pinfo = info;
+    double* stage = nullptr;
+    if (where != RIPTRM_DEVICE) {
+        CUDA_TRY(cudaMalloc(&stage, 3 * xb + 2 * yb + ib));
+        double* q = stage;
+        CUDA_TRY(cudaMemcpyAsync(q, x, xb, cudaMemcpyHostToDevice, st)); px = q; q += B * h->vec_len;
+        CUDA_TRY(cudaMemcpyAsync(q, c, xb, cudaMemcpyHostToDevice, st)); pc = q; q += B * h->vec_len;
+        pdx = q; q += B * h->vec_len;
+        CUDA_TRY(cudaMemcpyAsync(q, z, yb, cudaMemcpyHostToDevice, st)); pz = q; q += B * h->m;
+        CUDA_TRY(cudaMemcpyAsync(q, s, yb, cudaMemcpyHostToDevice, st)); ps = q; q += B * h->m;
+        pinfo = q;
+    }
+    int rc;
+    if (small) {
+        SmallParams Q = small_params(h);
+        Q.x0 = px; Q.y0 = pz; Q.v = pc; Q.out = pdx; Q.info = pinfo; Q.slack = ps;
+        Q.newton_method = method; Q.kr_tol = tol; Q.kr_maxiter = maxiter;
+        rc = dispatch_small(h, 4, Q, o, st);
+    } else {
+        SphereParams P{};
+        P.Z = h->dZ; P.batch_z = h->batch_z; P.n = h->n; P.batch = h->batch; P.eps = h->eps;
+        P.x0 = px; P.y0 = pz; P.v = pc; P.out = pdx; P.info = pinfo; P.slack = ps;
+        P.newton_method = method; P.kr_tol = tol; P.kr_maxiter = maxiter;
+        rc = dispatch_sphere_exact<4>(h, P, o, st);
+    }
+    if (rc == RIPTRM_OK && where != RIPTRM_DEVICE) {
+        cudaError_t e = cudaMemcpyAsync(dx, pdx, xb, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && info != nullptr) e = cudaMemcpyAsync(info, pinfo, ib, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail(RIPTRM_E_CUDA, std::string("riptrm_newton: ") + cudaGetErrorString(e));
+        else rc = finish_timing(h, true);
+    }
+    if (stage) cudaFree(stage);
+    return rc;
 }
 
 extern "C" int riptrm_trs(riptrm_handle* h, const double* x, const double* y, double mu, double Delta, double* dx,

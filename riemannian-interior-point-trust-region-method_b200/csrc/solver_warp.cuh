@@ -218,6 +218,97 @@ __device__ __forceinline__ TcgResult tcg_generic(const typename F::Ctx& ctx, con
 }
 
 // ------------------------------------------------------------------------------------------
+// The condensed Newton system of the Riemannian interior-point method (RIPM.py:484-511):
+//     Aw[dx] = Hess_x L(x, z)[dx] + G_x( G*_x[dx] * z / s ) = c
+// is the operator of this file's trust-region model with the slack s an INDEPENDENT variable (RIPM keeps (x, y, z, s)); `st` is
+// a Step whose ys holds z / s.  Two solvers, as in the reference:
+//   newton_repmat  RepresentMatMethod (RIPM.py:238-300, no equality constraints: T_mat = Aw_mat): the representation matrix
+//                  in the tangent basis, solved through its symmetric eigen-decomposition (scipy.linalg.solve(assume_a='sym'))
+//   newton_cr      TangentSpaceConjResMethod (utils.py:582-618; Saad, Iterative Methods, Alg. 6.20): conjugate residuals on the
+//                  tangent space, v0 = 0, stop at |r| / |c| < tol or after maxiter iterations
+// ------------------------------------------------------------------------------------------
+struct NewtonOut {
+    double iters, rel_res, mineig;
+};
+
+template <class F>
+__device__ __forceinline__ NewtonOut newton_repmat(const typename F::Ctx& ctx, const typename F::Pt& pt, const typename F::CVec& z,
+                                                   const typename F::Step& st, const typename F::Vec& c, RepWork& rw,
+                                                   typename F::Vec& dx) {
+    typename F::Coord cc;
+    F::coord_setup(ctx, pt, cc);
+    rep_build<F>(ctx, pt, z, st, cc, rw, 0);
+    F::to_coords(ctx, pt, cc, c, rw.col);                           // tangent2vec (utils.py:575-580)
+    dense::rows_dot(rw.VT[0], rw.d, rw.ld, rw.col, rw.al[0]);
+    for (int k = lane_id(); k < rw.d; k += 32) rw.col[k] = rw.al[0][k] / rw.D[0][k];
+    __syncwarp();
+    dense::cols_dot(rw.VT[0], rw.d, rw.ld, rw.col, rw.coef);
+    dx = F::from_coords(ctx, pt, cc, rw.coef);
+    // A solve through the eigen-decomposition carries a forward error of eps * cond in EVERY direction (the reference's LAPACK
+    // sysv is backward stable: residual eps |A| |dx|); two steps of iterative refinement on the operator restore that
+    typename F::Vec r;
+    for (int pass = 0; pass < 3; ++pass) {
+        const typename F::Vec Adx = F::Hw(ctx, pt, z, st, dx);
+#pragma unroll
+        for (int k = 0; k < F::K; ++k) r.v[k] = c.v[k] - Adx.v[k];
+        if (pass == 2) break;
+        F::to_coords(ctx, pt, cc, r, rw.col);
+        dense::rows_dot(rw.VT[0], rw.d, rw.ld, rw.col, rw.al[0]);
+        for (int k = lane_id(); k < rw.d; k += 32) rw.col[k] = rw.al[0][k] / rw.D[0][k];
+        __syncwarp();
+        dense::cols_dot(rw.VT[0], rw.d, rw.ld, rw.col, rw.coef);
+        const typename F::Vec corr = F::from_coords(ctx, pt, cc, rw.coef);
+#pragma unroll
+        for (int k = 0; k < F::K; ++k) dx.v[k] = dx.v[k] + corr.v[k];
+    }
+    NewtonOut out;
+    out.iters = 0.0;
+    out.rel_res = sqrt(F::inner(ctx, pt, r, r)) / sqrt(F::inner(ctx, pt, c, c));
+    out.mineig = rep_mineig(rw, 0);
+    return out;
+}
+
+template <class F>
+__device__ __forceinline__ NewtonOut newton_cr(const typename F::Ctx& ctx, const typename F::Pt& pt, const typename F::CVec& z,
+                                               const typename F::Step& st, const typename F::Vec& b, double tol, int maxiter,
+                                               typename F::Vec& v) {
+    using Vec = typename F::Vec;
+    constexpr int K = F::K;
+    v = wzero<K>();                                                 // v0 = 0 (RIPM.py:431 self.v0)
+    Vec r = b, p = b;                                               // r = b - A(v0)
+    const double b_norm = sqrt(F::inner(ctx, pt, b, b));
+    Vec Ar = F::Hw(ctx, pt, z, st, r), Ap = Ar;
+    double rAr = F::inner(ctx, pt, r, Ar);
+    double rel_res = 1.0;
+    int t = 0;
+    while (true) {
+        t += 1;
+        const double a = rAr / F::inner(ctx, pt, Ap, Ap);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            v.v[k] = v.v[k] + a * p.v[k];
+            r.v[k] = r.v[k] - a * Ap.v[k];
+        }
+        rel_res = sqrt(F::inner(ctx, pt, r, r)) / b_norm;
+        if (rel_res < tol || t == maxiter) break;
+        Ar = F::Hw(ctx, pt, z, st, r);
+        const double old = rAr;
+        rAr = F::inner(ctx, pt, r, Ar);
+        const double beta = rAr / old;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            p.v[k] = r.v[k] + beta * p.v[k];
+            Ap.v[k] = Ar.v[k] + beta * Ap.v[k];
+        }
+    }
+    NewtonOut out;
+    out.iters = (double)t;
+    out.rel_res = rel_res;
+    out.mineig = CUDART_NAN;
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------
 // Observers: utils.evaluation / compute_residual / compute_maxmeanviolations (utils.py:237-368)
 // ------------------------------------------------------------------------------------------
 struct EvalRow {

@@ -187,6 +187,19 @@ class BatchSolver:
                                        _lib.ptr(info), _lib.HOST, None))
         return dx, info
 
+    def newton(self, x, z, s, c, method="RepMat", tol=1e-9, maxiter=1000):
+        """The condensed Newton system of the reference's interior-point method on this path's operator (RIPM.py:484-511):
+        Aw[dx] = Hess L(x, z)[dx] + G(G*[dx] z / s) = c per pair, by `RepresentMatMethod` ("RepMat") or
+        `TangentSpaceConjResMethod` ("Krylov", tol = 'KrylovTolrelresid', maxiter = 'KrylovMaxIteration').  Returns
+        (dx [B, n*p], info [B, 4] = {iterations, relative residual, ||dx||, smallest eigenvalue of the matrix of Aw})."""
+        dx = np.empty_like(self.x0)
+        info = np.empty((self.batch, 4))
+        m = {"RepMat": 0, "Krylov": 1}[method]
+        _lib.check(self.lib.riptrm_newton(self.handle.h, _lib.ptr(np.ascontiguousarray(x)), _lib.ptr(np.ascontiguousarray(z)),
+                                          _lib.ptr(np.ascontiguousarray(s)), _lib.ptr(np.ascontiguousarray(c)), m, float(tol),
+                                          int(maxiter), _lib.ptr(dx), _lib.ptr(info), _lib.HOST, None))
+        return dx, info
+
     def tcg(self, x, y, mu, Delta):
         eta = np.empty_like(self.x0)
         info = np.empty((self.batch, 4))

@@ -130,3 +130,31 @@ def test_sweep_of_1024_initial_points(rb, datasets):
         J, R, Q = o.x
         assert np.max(np.abs(J + J.T)) < 1e-13 and np.linalg.eigvalsh(R).min() > 0 and np.linalg.eigvalsh(Q).min() > 0
         assert stableid_constraint_values((J - R) @ Q, conspec).max() < 1e-9
+
+
+def test_hessvec_with_is_euclidean_embedded(rb, datasets):
+    """'is_euclidean_embedded'=True on the Product family (RIPTRM.py:553-571; VERDICT r1 missing #5): G* uses the Euclidean
+    constraint gradients inside the manifold's (affine-invariant) inner product -- the oracle's generic per-constraint
+    evaluation of exactly that."""
+    from oracle import riptrm_oracle as O
+    rng = np.random.RandomState(8)
+    P = stableid_problem(datasets, "d")
+    P.initialineqLagmult = 0.5 + rng.rand(16)
+    st = _structure(rb, P)
+    x, y = P.initialpoint, P.initialineqLagmult
+    v = P.manifold.projection(x, [rng.randn(5, 5) for _ in range(3)])
+    flat = np.concatenate([a.reshape(-1) for a in v])[None]
+    bs = rb.BatchSolver([st])
+    opt = rb.options.default_option()
+    opt.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=1, is_euclidean_embedded=True)
+    bs.set_options(opt)
+    hv = _unpack(bs.hessvec(bs.x0, bs.y0, 0.1, flat)[0])
+    s = O.slack(P, x)
+    va = O._amb(P.manifold, v)
+    ref = O.hess_lagrangian(P, x, y, va) + O.G_apply(P, x, (y * O.Gadj_apply(P, x, va, True)) / s)
+    plain = O.hess_lagrangian(P, x, y, va) + O.G_apply(P, x, (y * O.Gadj_apply(P, x, va, False)) / s)
+    scale = max(np.max(np.abs(r)) for r in ref)
+    for k in range(3):
+        assert np.max(np.abs(hv[k] - ref[k])) < 1e-9 * scale, k
+    assert max(np.max(np.abs(a - b)) for a, b in zip(ref, plain)) > 1e-3 * scale     # the two settings do differ here
+    bs.close()
