@@ -44,9 +44,16 @@ struct StableIdFam {
         const double* XXt;  // shared memory [d][d]
         double* sc;         // scratch: kSlots slots of 32 doubles + E [d][N]
         double* E;
+        bool generic_tcg;   // measurement switch: tCG in the reference's operation order on unwhitened vectors (tcg_generic)
         // this lane's constraint (lane < m)
         int kind, rc;
         double ca, cb;
+        // lane geometry of a d x d lane matrix: row / column of this lane's entry, the lane holding the transposed entry
+        int li, lj, tlane;
+        // scatter: the (at most 4) constraints whose entry (r, c) is this lane's, in constraint order (-1: none); when an
+        // entry is hit by more than 4 constraints nsrc = -1 and scatter falls back to the serial shared-memory form
+        int src[4];
+        int nsrc;
     };
     struct Pt {
         Vec x;
@@ -54,6 +61,8 @@ struct StableIdFam {
         double cost;
         LM A, GA, JmR;       // (J-R) Q, df/dA, J - R
         LM Rinv, Qinv;
+        LM LR, LRi, LQ, LQi; // Cholesky factors of R, Q and their inverses (R^-1 = LRi' LRi): one factorisation per point
+                             // serves the metric, the retraction, the positive-definiteness test and the whitened tCG
         CVec coef;           // Phi_i = coef_i E_rc
         bool spd_ok;
     };
@@ -74,6 +83,7 @@ struct StableIdFam {
         c.N = P.N;
         c.h = P.hstep;
         c.embedded = o.is_euclidean_embedded != 0;
+        c.generic_tcg = P.generic_tcg != 0;
         c.sc = smem;
         double* X = smem + kSlots * 32;
         double* XP = X + c.d * c.N;
@@ -98,6 +108,22 @@ struct StableIdFam {
             c.ca = row[3];
             c.cb = row[4];
         }
+        const int l = lane_id();
+        c.li = l / c.d;
+        c.lj = l - c.li * c.d;
+        c.tlane = (l < c.dd) ? c.lj * c.d + c.li : l;
+        int cnt = 0, over = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c.src[q] = -1;
+        for (int i = 0; i < c.m; ++i) {
+            const int rci = __shfl_sync(kFull, c.rc, i);
+            if (rci == l && l < c.dd) {
+                if (cnt < 4) c.src[cnt] = i;
+                else over = 1;
+                ++cnt;
+            }
+        }
+        c.nsrc = __any_sync(kFull, over) ? -1 : 0;
         return c;
     }
 
@@ -165,8 +191,26 @@ struct StableIdFam {
         __syncwarp();
         return s;
     }
+    // d == 5 (the reference's dimension): inlined, the transposition flags are compile-time constants at every call site and
+    // the row / column offsets come from the lane geometry in Ctx -- 2 STS + 10 LDS + 5 DFMA + 2 barriers, no index arithmetic
+    // (the out-of-line general version spent 55 instructions per product, most of them integer division by a runtime d;
+    // profiles/r02b_stableid_*).  Same order of additions as mul_impl.
     static __device__ __forceinline__ LM mul(const Ctx& c, LM a, LM b, bool tA = false, bool tB = false) {
-        return mul_impl(c.sc, c.d, a, b, tA, tB);
+        if (c.d != 5) return mul_impl(c.sc, c.d, a, b, tA, tB);
+        const int l = lane_id();
+        double* sc = c.sc;
+        sc[l] = a;
+        sc[32 + l] = b;
+        __syncwarp();
+        double s = 0.0;
+        if (l < 25) {
+            const double* A = tA ? sc + c.li : sc + 5 * c.li;
+            const double* B = tB ? sc + 32 + 5 * c.lj : sc + 32 + c.lj;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) s = fma(tA ? A[5 * k] : A[k], tB ? B[k] : B[5 * k], s);
+        }
+        __syncwarp();
+        return s;
     }
     static __device__ __noinline__ LM transpose_impl(double* sc, int d, LM a) {
         const int l = lane_id();
@@ -180,7 +224,8 @@ struct StableIdFam {
         __syncwarp();
         return r;
     }
-    static __device__ __forceinline__ LM transpose(const Ctx& c, LM a) { return transpose_impl(c.sc, c.d, a); }
+    // the transposed entry lives on lane `tlane`: one 64-bit shuffle (was a shared-memory round trip, 57 instructions)
+    static __device__ __forceinline__ LM transpose(const Ctx& c, LM a) { return __shfl_sync(kFull, a, c.tlane); }
     static __device__ __forceinline__ LM symm(const Ctx& c, LM a) { return 0.5 * (a + transpose(c, a)); }
     static __device__ __forceinline__ LM skew(const Ctx& c, LM a) { return 0.5 * (a - transpose(c, a)); }
     static __device__ __forceinline__ LM inverse(const Ctx& c, LM a, bool& ok) {
@@ -208,7 +253,16 @@ struct StableIdFam {
         return r;
     }
     static __device__ __forceinline__ LM scatter(const Ctx& c, const CVec& w, const CVec& coef, LM base) {
-        return scatter_impl(c.sc, c.m, c.dd, c.rc, w.v[0] * coef.v[0], base);
+        const double wc = w.v[0] * coef.v[0];
+        if (c.nsrc < 0) return scatter_impl(c.sc, c.m, c.dd, c.rc, wc, base);
+        // every entry gathers its constraints' weights in constraint order: the same sums as the serial form
+        double r = base;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double v = __shfl_sync(kFull, wc, c.src[q] < 0 ? 0 : c.src[q]);
+            if (c.src[q] >= 0) r = r + v;
+        }
+        return (lane_id() < c.dd) ? r : 0.0;
     }
     // value of a lane matrix at this lane's constraint entry (r_i, c_i)
     static __device__ __noinline__ double at_constraint_impl(double* sc, int m, int my_rc, LM a) {
@@ -218,7 +272,10 @@ struct StableIdFam {
         __syncwarp();
         return r;
     }
-    static __device__ __forceinline__ double at_constraint(const Ctx& c, LM a) { return at_constraint_impl(c.sc, c.m, c.rc, a); }
+    static __device__ __forceinline__ double at_constraint(const Ctx& c, LM a) {
+        const double v = __shfl_sync(kFull, a, c.rc);      // entry (r, c) of a lane matrix lives on lane r d + c
+        return (lane_id() < c.m) ? v : 0.0;
+    }
 
     // Euclidean -> Riemannian gradient, componentwise
     static __device__ __forceinline__ Vec egrad2rgrad(const Ctx& c, const Pt& pt, LM egJ, LM egR, LM egQ) {
@@ -280,16 +337,12 @@ struct StableIdFam {
         }
         pt.s.v[0] = -g;
         pt.coef.v[0] = coef;
-        bool okR, okQ;
-        pt.Rinv = inverse(c, x.v[1], okR);
-        pt.Qinv = inverse(c, x.v[2], okQ);
-        put(c, 2, x.v[1]);
-        const bool pdR = sm::is_spd<DMAX>(slot(c, 2), c.d);
-        __syncwarp();
-        put(c, 2, x.v[2]);
-        const bool pdQ = sm::is_spd<DMAX>(slot(c, 2), c.d);
-        __syncwarp();
-        pt.spd_ok = okR && okQ && pdR && pdQ;
+        // one Cholesky factorisation per SPD block: positive definite iff it succeeds, P^-1 = L^-T L^-1
+        const bool okR = chol_and_inverse(c.sc, c.d, x.v[1], pt.LR, pt.LRi);
+        const bool okQ = chol_and_inverse(c.sc, c.d, x.v[2], pt.LQ, pt.LQi);
+        pt.Rinv = mul(c, pt.LRi, pt.LRi, true, false);
+        pt.Qinv = mul(c, pt.LQi, pt.LQi, true, false);
+        pt.spd_ok = okR && okQ;
     }
 
     // <a, b>_x = <aJ, bJ> + tr(R^-1 aR R^-1 bR) + tr(Q^-1 aQ Q^-1 bQ): per-lane partial
@@ -391,9 +444,170 @@ struct StableIdFam {
         return out;
     }
 
+    // ---- tCG in whitened coordinates ---------------------------------------------------------------------------------------
+    // With R = LR LR', Q = LQ LQ' (Cholesky) the map v -> vh = (vJ, LR^-1 vR LR^-T, LQ^-1 vQ LQ^-T) is an isometry from the
+    // tangent space with the product metric (Frobenius + two affine-invariant traces) onto matrices with the FROBENIUS inner
+    // product.  Steihaug-Toint tCG (RIPTRM.py:41-216) on vh is the same iteration with
+    //   * every inner product a lane-wise product and one butterfly (tcg_generic: two whitening congruences per operand);
+    //   * the Hessian-vector product conjugated: LR'[R-block of the Euclidean part]LR has the manifold's P . P cancelled, the
+    //     curvature term sym(V sym(eg) P) becomes sym(vh Gh) with Gh = LR' sym(eg) LR cached per call, and the barrier term
+    //     folds into the Euclidean Hessian of the Lagrangian before the pull-back (both are linear in Phi):
+    //         dPhi' = dG_A + sum_i (y_i dcoef_i - w_i coef_i) E_rc,   w_i = (y_i / s_i) G*[v]_i
+    //     17 5 x 5 products per iteration instead of 22 + 16 (4 per inner product).
+    // Same algorithm, same exits; rounding differs from tcg_generic by the usual few ulp.
+    struct White {
+        LM LR, LRi, LQ, LQi;   // Cholesky factors of R, Q and their inverses (the point's)
+        LM GR, GQ;             // LR' sym(-gJ) LR, LQ' sym(gQ) LQ: whitened Riemannian gradient blocks of the Lagrangian
+    };
+    static __device__ __forceinline__ void white_setup(const Ctx& c, const Pt& pt, const Step& st, White& w) {
+        w.LR = pt.LR;
+        w.LRi = pt.LRi;
+        w.LQ = pt.LQ;
+        w.LQi = pt.LQi;
+        const LM gJ = mul(c, st.PhiL, pt.x.v[2], false, true);
+        const LM gQ = mul(c, pt.JmR, st.PhiL, true, false);
+        w.GR = mul(c, mul(c, w.LR, symm(c, -gJ), true, false), w.LR);
+        w.GQ = mul(c, mul(c, w.LQ, symm(c, gQ), true, false), w.LQ);
+    }
+    static __device__ __forceinline__ Vec whiten(const Ctx& c, const White& w, const Vec& v) {
+        Vec r;
+        r.v[0] = v.v[0];
+        r.v[1] = mul(c, mul(c, w.LRi, v.v[1]), w.LRi, false, true);
+        r.v[2] = mul(c, mul(c, w.LQi, v.v[2]), w.LQi, false, true);
+        return r;
+    }
+    static __device__ __forceinline__ Vec unwhiten(const Ctx& c, const White& w, const Vec& v) {
+        Vec r;
+        r.v[0] = v.v[0];
+        r.v[1] = mul(c, mul(c, w.LR, v.v[1]), w.LR, false, true);
+        r.v[2] = mul(c, mul(c, w.LQ, v.v[2]), w.LQ, false, true);
+        return r;
+    }
+    // whitened Hw: vh -> whiten(Hw[unwhiten(vh)])
+    static __device__ __forceinline__ Vec Hw_white(const Ctx& c, const Pt& pt, const CVec& y, const Step& st, const White& w,
+                                                   const Vec& vh) {
+        const LM vR = mul(c, mul(c, w.LR, vh.v[1]), w.LR, false, true);
+        const LM vQ = mul(c, mul(c, w.LQ, vh.v[2]), w.LQ, false, true);
+        const LM D1 = vh.v[0] - vR;
+        const LM dA = mul(c, D1, pt.x.v[2]) + mul(c, pt.JmR, vQ);
+        put(c, 7, dA);
+        double dga = 0.0;
+        if (on(c)) {
+            const int d = c.d, i = lane_id() / d, j = lane_id() - i * d;
+            double s = 0.0;
+            for (int k = 0; k < d; ++k) s = fma(slot(c, 7)[i * d + k], c.XXt[k * d + j], s);
+            dga = (2.0 * c.h * c.h) * s / (double)c.N;
+        }
+        __syncwarp();
+        const double dArc = at_constraint(c, dA);
+        double gArc = dArc;
+        if (c.embedded) {
+            Vec v;
+            v.v[0] = vh.v[0];
+            v.v[1] = vR;
+            v.v[2] = vQ;
+            gArc = at_constraint(c, dA_embedded(c, pt, v));
+        }
+        CVec wc, ones;
+        const double dcoef = (lane_id() < c.m && c.kind == 2) ? -2.0 * dArc : 0.0;
+        const double wi = st.ys.v[0] * (-pt.coef.v[0] * gArc);
+        wc.v[0] = y.v[0] * dcoef - wi * pt.coef.v[0];
+        ones.v[0] = 1.0;
+        const LM dPhi = scatter(c, wc, ones, dga);
+        const LM hJ = mul(c, dPhi, pt.x.v[2], false, true) + mul(c, st.PhiL, vQ, false, true);
+        const LM hQ = mul(c, D1, st.PhiL, true, false) + mul(c, pt.JmR, dPhi, true, false);
+        const LM hJt = transpose(c, hJ);
+        Vec out;
+        out.v[0] = 0.5 * (hJ - hJt);
+        out.v[1] = mul(c, mul(c, w.LR, -0.5 * (hJ + hJt), true, false), w.LR) + symm(c, mul(c, vh.v[1], w.GR));
+        out.v[2] = mul(c, mul(c, w.LQ, symm(c, hQ), true, false), w.LQ) + symm(c, mul(c, vh.v[2], w.GQ));
+        return out;
+    }
+    static __device__ __forceinline__ double dotw(const Vec& a, const Vec& b) {
+        return fma(a.v[2], b.v[2], fma(a.v[1], b.v[1], a.v[0] * b.v[0]));
+    }
+
     static __device__ __forceinline__ TcgResult tcg(const Ctx& ctx, const DevOpts& o, const Pt& pt, const CVec& y,
                                                     const Step& st, double Delta, Vec& eta, Vec& Heta) {
-        return tcg_generic<StableIdFam>(ctx, o, pt, y, st, Delta, eta, Heta);
+        if (ctx.generic_tcg) return tcg_generic<StableIdFam>(ctx, o, pt, y, st, Delta, eta, Heta);
+        White w;
+        white_setup(ctx, pt, st, w);
+        const Vec ch = whiten(ctx, w, st.c);
+        Vec e = wzero<3>(), He = wzero<3>();                  // :47
+        Vec r = ch, delta;                                    // :48
+#pragma unroll
+        for (int k = 0; k < 3; ++k) delta.v[k] = -r.v[k];     // :71
+        double r_r = wsum(dotw(r, r));                        // :56
+        const double norm_r0 = sqrt(r_r);
+        double z_r = r_r, d_Pd = r_r, e_Pe = 0.0, e_Pd = 0.0, model_value = 0.0;
+        TcgResult res;
+        res.stop = RIPTRM_TCG_MAX_INNER_ITER;                 // :95
+        const int maxinner = o.tcg_maxinner < 0 ? dim(ctx) : o.tcg_maxinner;
+        const double Delta2 = Delta * Delta;
+        const double nr_theta = (o.tcg_theta == 1.0) ? norm_r0 : pow(norm_r0, o.tcg_theta);
+        const double target = norm_r0 * fmin(nr_theta, o.tcg_kappa);
+        int j = 0;
+        for (; j < maxinner; ++j) {                           // :98
+            const Vec Hd = Hw_white(ctx, pt, y, st, w, delta);   // :100
+            const double d_Hd = wsum(dotw(delta, Hd));        // :103
+            double alpha = 0.0, e_Pe_new = e_Pe;
+            if (d_Hd != 0.0) {                                // :106-114
+                alpha = z_r / d_Hd;
+                e_Pe_new = (e_Pe + (2.0 * alpha) * e_Pd) + (alpha * alpha) * d_Pd;
+            }
+            if (d_Hd <= 0.0 || e_Pe_new >= Delta2) {          // :118
+                const double tau = (-e_Pd + sqrt(e_Pd * e_Pd + d_Pd * (Delta2 - e_Pe))) / d_Pd;   // :123-125
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    e.v[k] = e.v[k] + tau * delta.v[k];       // :127
+                    He.v[k] = He.v[k] + tau * Hd.v[k];        // :132
+                }
+                res.stop = (d_Hd <= 0.0) ? RIPTRM_TCG_NEGATIVE_CURVATURE : RIPTRM_TCG_EXCEEDED_TR;
+                ++j;
+                break;
+            }
+            e_Pe = e_Pe_new;                                  // :149
+            Vec ne, nHe, rn;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                ne.v[k] = e.v[k] + alpha * delta.v[k];        // :150
+                nHe.v[k] = He.v[k] + alpha * Hd.v[k];         // :154
+                rn.v[k] = r.v[k] + alpha * Hd.v[k];           // :172
+            }
+            double ip_ec = dotw(ne, ch), ip_eh = dotw(ne, nHe), ip_rr = dotw(rn, rn);
+            wsum3(ip_ec, ip_eh, ip_rr);
+            const double new_model = ip_ec + 0.5 * ip_eh;     // :86-87, :162
+            if (new_model >= model_value) {                   // :163
+                res.stop = RIPTRM_TCG_MODEL_INCREASED;
+                ++j;
+                break;
+            }
+            e = ne;                                           // :167-169
+            He = nHe;
+            model_value = new_model;
+            r = rn;
+            r_r = ip_rr;                                      // :175
+            if (j >= o.tcg_mininner && sqrt(r_r) <= target) { // :183-191
+                res.stop = (o.tcg_kappa < nr_theta) ? RIPTRM_TCG_REACHED_TARGET_LINEAR
+                                                    : RIPTRM_TCG_REACHED_TARGET_SUPERLINEAR;
+                ++j;
+                break;
+            }
+            const double beta = r_r / z_r;                    // :200-205
+            z_r = r_r;
+            // :206, :210 -- the re-projection onto the tangent space is skew / sym of the blocks in these coordinates
+            const LM dJ = -r.v[0] + beta * delta.v[0], dR = -r.v[1] + beta * delta.v[1], dQ = -r.v[2] + beta * delta.v[2];
+            delta.v[0] = skew(ctx, dJ);
+            delta.v[1] = symm(ctx, dR);
+            delta.v[2] = symm(ctx, dQ);
+            e_Pd = beta * (e_Pd + alpha * d_Pd);              // :213
+            d_Pd = z_r + (beta * beta) * d_Pd;                // :214
+        }
+        eta = unwhiten(ctx, w, e);
+        Heta = unwhiten(ctx, w, He);
+        res.iters = j;
+        res.model_value = model_value;
+        return res;
     }
 
     // ---- Exact_RepMat: orthonormal tangent basis of the product (riptrm_b200/basis.py) ----------------------------------------
@@ -404,34 +618,84 @@ struct StableIdFam {
     struct Coord {
         LM LR, LRi, LQ, LQi;   // Cholesky factors and their inverses, one entry per lane
     };
-    static __device__ __noinline__ void chol_and_inverse(double* sc, int d, LM P, LM& L_out, LM& Li_out) {
-        const int l = lane_id();
-        sc[l] = P;
-        __syncwarp();
-        double L[DMAX][DMAX], Li[DMAX][DMAX];
-        for (int i = 0; i < d; ++i)
-            for (int j = 0; j < d; ++j) L[i][j] = Li[i][j] = 0.0;
-        for (int i = 0; i < d; ++i)
-            for (int j = 0; j <= i; ++j) {
+    // Cholesky factor L (P = L L') and L^-1 of a d x d lane matrix, every lane redundantly on a private copy (25 flops of
+    // latency-bound serial work either way); returns false when P is not positive definite.  D > 0: compile-time size, the
+    // private matrices stay in registers (the runtime-d version indexes local memory).
+    template <int D>
+    static __device__ __forceinline__ bool chol_core(const double* sc, int d_rt, int li, int lj, LM& L_out, LM& Li_out) {
+        constexpr int DM = (D > 0) ? D : DMAX;
+        const int d = (D > 0) ? D : d_rt;
+        double L[DM][DM], Li[DM][DM];
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < DM; ++i)
+#pragma unroll
+            for (int j = 0; j < DM; ++j) L[i][j] = Li[i][j] = 0.0;
+#pragma unroll
+        for (int i = 0; i < DM; ++i) {
+            if (i >= d) break;
+#pragma unroll
+            for (int j = 0; j < DM; ++j) {
+                if (j > i) break;
                 double s = sc[i * d + j];
-                for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
-                L[i][j] = (i == j) ? sqrt(s) : s / L[j][j];
+#pragma unroll
+                for (int k = 0; k < DM; ++k) {
+                    if (k >= j) break;
+                    s -= L[i][k] * L[j][k];
+                }
+                if (i == j) {
+                    ok = ok && (s > 0.0);
+                    L[i][i] = sqrt(s);
+                } else {
+                    L[i][j] = s / L[j][j];
+                }
             }
-        for (int j = 0; j < d; ++j) {          // forward substitution L Li = I, column by column
-            for (int i = j; i < d; ++i) {
+        }
+#pragma unroll
+        for (int j = 0; j < DM; ++j) {          // forward substitution L Li = I, column by column
+            if (j >= d) break;
+#pragma unroll
+            for (int i = 0; i < DM; ++i) {
+                if (i < j) continue;
+                if (i >= d) break;
                 double s = (i == j) ? 1.0 : 0.0;
-                for (int k = j; k < i; ++k) s -= L[i][k] * Li[k][j];
+#pragma unroll
+                for (int k = 0; k < DM; ++k) {
+                    if (k < j) continue;
+                    if (k >= i) break;
+                    s -= L[i][k] * Li[k][j];
+                }
                 Li[i][j] = s / L[i][i];
             }
         }
-        __syncwarp();
-        const int i = l / d, j = l - i * d;
-        L_out = (l < d * d) ? L[i][j] : 0.0;
-        Li_out = (l < d * d) ? Li[i][j] : 0.0;
+        double lo = 0.0, lio = 0.0;
+#pragma unroll
+        for (int i = 0; i < DM; ++i)
+#pragma unroll
+            for (int j = 0; j < DM; ++j)
+                if (i == li && j == lj) {
+                    lo = L[i][j];
+                    lio = Li[i][j];
+                }
+        L_out = lo;
+        Li_out = lio;
+        return ok;
     }
-    static __device__ __forceinline__ void coord_setup(const Ctx& c, const Pt& pt, Coord& cc) {
-        chol_and_inverse(c.sc, c.d, pt.x.v[1], cc.LR, cc.LRi);
-        chol_and_inverse(c.sc, c.d, pt.x.v[2], cc.LQ, cc.LQi);
+    static __device__ __noinline__ bool chol_and_inverse(double* sc, int d, LM P, LM& L_out, LM& Li_out) {
+        const int l = lane_id();
+        sc[l] = P;
+        __syncwarp();
+        const int li = l / d, lj = l - li * d;
+        const bool ok = (d == 5) ? chol_core<5>(sc, d, li, lj, L_out, Li_out) : chol_core<0>(sc, d, li, lj, L_out, Li_out);
+        __syncwarp();
+        if (l >= d * d) L_out = Li_out = 0.0;
+        return ok;
+    }
+    static __device__ __forceinline__ void coord_setup(const Ctx&, const Pt& pt, Coord& cc) {
+        cc.LR = pt.LR;
+        cc.LRi = pt.LRi;
+        cc.LQ = pt.LQ;
+        cc.LQi = pt.LQi;
     }
     static __device__ __forceinline__ int pair_index(int d, int a, int b) { return a * d - (a * (a + 1)) / 2 + (b - a - 1); }
     // symmetric / skew lane matrix from packed coordinates (diag first, then pairs scaled by 1 / sqrt 2)

@@ -1191,6 +1191,7 @@ struct SmallParams {
     const double* slack;           // riptrm_newton (see SphereParams)
     int newton_method, kr_maxiter;
     double kr_tol;
+    int generic_tcg;               // StableIdentification: tCG on unwhitened vectors (measurement switch RIPTRM_STABLEID_GENERIC_TCG)
 };
 
 template <class F, int MODE, bool EXACT = false>
@@ -1323,6 +1324,7 @@ static SmallParams small_params(const riptrm_handle* h) {
     P.batch = h->batch;
     P.alpha = h->ros_alpha;
     P.offset = h->ros_offset;
+    P.generic_tcg = getenv("RIPTRM_STABLEID_GENERIC_TCG") != nullptr ? 1 : 0;
     if (h->d_sid != nullptr) {
         const size_t dn = (size_t)h->n * h->sid_N;
         P.Xd = h->d_sid;

@@ -61,7 +61,7 @@ def test_newton_system_matches_oracle(rb, datasets, which):
     assert abs(info[0, 3] - eig[0]) <= 1e-10 * max(abs(eig[0]), abs(eig[-1]))
     # ---- TangentSpaceConjResMethod, the reference's defaults (KrylovTolrelresid 1e-9, KrylovMaxIteration 1000) and a cap
     norm_c = man.norm(x, c)
-    for tol, cap in ((1e-9, 1000), (1e-3, 1000), (0.0, 7)):
+    for tol, cap in ((1e-9, 1000), (1e-6, 1000), (1e-3, 1000), (0.0, 7)):
         v, t, rel = O.conj_res(man, x, Aw, c, tol, cap)
         dx, info = bs.newton(bs.x0, z[None], s[None], _flat(st, c), "Krylov", tol=tol, maxiter=cap)
         got = st.unpack_x(dx[0])
@@ -75,8 +75,13 @@ def test_newton_system_matches_oracle(rb, datasets, which):
             for g, r in parts:
                 assert np.max(np.abs(np.asarray(g) - np.asarray(r))) <= 1e-6 * man.norm(x, v), (which, tol)
             assert abs(info[0, 1] - rel) <= 1e-6 * max(rel, 1e-12) + 1e-14
-        else:
+        elif tol >= 1e-6:
             assert abs(it - t) <= max(3, 0.2 * t), (which, tol, it, t)
+        else:
+            # at the reference's default 1e-9 these systems sit close to the attainable accuracy (eps * cond = 1e-9 / 1e-12):
+            # the residual curve plateaus and the iteration at which it dips under the tolerance depends on the last bits
+            # (observed 130 / 141 / 337 on the Product system for three arithmetic variants) -- only the result is checked
+            assert it <= cap
         if tol > 0:
             # whatever the count, the stopping rule holds for the returned point (checked with the oracle's operator) and it
             # agrees with the direct solve up to tol * cond
