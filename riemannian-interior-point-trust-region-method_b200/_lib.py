@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libriptrm_b200.so")
+# RIPTRM_B200_LIB: an alternative build of the same library (A/B measurements of compile-time variants)
+LIB_PATH = os.environ.get("RIPTRM_B200_LIB") or os.path.join(HERE, "csrc", "libriptrm_b200.so")
 
 HOST, DEVICE = 0, 1
 FAMILY_NONNEGPCA_SPHERE = 1

@@ -210,6 +210,28 @@ __host__ __device__ __forceinline__ double det_log(double x) {
     return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
 }
 
+// Explicit shared-memory accesses through 32-bit shared-space addresses: a pointer that has been through a spilled context
+// struct loses its address space and the compiler falls back to generic LD / ST (profiles/r02c_stableid_*: 15 % of the
+// instructions of the small-matrix kernel).  "memory" keeps them ordered with respect to __syncwarp().
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+// the same with a compile-time byte offset folded into the instruction's immediate
+template <int OFF>
+__device__ __forceinline__ double lds_f64_off(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF) : "memory");
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts_f64_off(uint32_t a, double v) {
+    asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "d"(v) : "memory");
+}
+
 __device__ __forceinline__ uint64_t global_timer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -54,6 +54,12 @@ struct StableIdFam {
         // entry is hit by more than 4 constraints nsrc = -1 and scatter falls back to the serial shared-memory form
         int src[4];
         int nsrc;
+        // d == 5: shared-space addresses of this lane's operands in the product scratch (two independent scratch pairs, so
+        // that two products share one pair of barriers): write slots, row / column starts for op(A), op(B)
+        // (five registers; the second scratch pair and the B operand are compile-time offsets of these)
+        uint32_t sW, sAn, sAt, sBn, sBt;
+        uint32_t sChol;      // 192 doubles after the scratch slots: R, Q, L and L^-1 of both
+        LM XXt_lm;           // X X' as a lane matrix
     };
     struct Pt {
         Vec x;
@@ -72,7 +78,8 @@ struct StableIdFam {
         LM PhiL;             // G_A + sum_i y_i Phi_i
     };
 
-    static __host__ __device__ constexpr int smem_doubles(int d, int N) { return kSlots * 32 + 3 * d * N + d * d; }
+    static constexpr int kCholDoubles = 192;
+    static __host__ __device__ constexpr int smem_doubles(int d, int N) { return kSlots * 32 + kCholDoubles + 3 * d * N + d * d; }
 
     template <class Params>
     static __device__ __forceinline__ Ctx make_ctx(const Params& P, const DevOpts& o, double* smem) {
@@ -85,7 +92,7 @@ struct StableIdFam {
         c.embedded = o.is_euclidean_embedded != 0;
         c.generic_tcg = P.generic_tcg != 0;
         c.sc = smem;
-        double* X = smem + kSlots * 32;
+        double* X = smem + kSlots * 32 + kCholDoubles;
         double* XP = X + c.d * c.N;
         c.E = XP + c.d * c.N;
         double* XXt = c.E + c.d * c.N;
@@ -124,6 +131,14 @@ struct StableIdFam {
             }
         }
         c.nsrc = __any_sync(kFull, over) ? -1 : 0;
+        const uint32_t sb = smem_u32(smem);
+        c.sW = sb + 8 * l;                    // slot 0 / 1 (+ 256) hold A / B of the first product, slots 2 / 3 (+ 512) of the second
+        c.sAn = sb + 40 * c.li;
+        c.sAt = sb + 8 * c.li;
+        c.sBn = sb + 256 + 8 * c.lj;
+        c.sBt = sb + 256 + 40 * c.lj;
+        c.sChol = sb + 8 * (kSlots * 32);
+        c.XXt_lm = (l < c.dd) ? XXt[l] : 0.0;
         return c;
     }
 
@@ -191,26 +206,69 @@ struct StableIdFam {
         __syncwarp();
         return s;
     }
-    // d == 5 (the reference's dimension): inlined, the transposition flags are compile-time constants at every call site and
-    // the row / column offsets come from the lane geometry in Ctx -- 2 STS + 10 LDS + 5 DFMA + 2 barriers, no index arithmetic
-    // (the out-of-line general version spent 55 instructions per product, most of them integer division by a runtime d;
-    // profiles/r02b_stableid_*).  Same order of additions as mul_impl.
+    // d == 5 (the reference's dimension): inlined, the transposition flags are compile-time constants at every call site, the
+    // operand addresses are per-lane constants of Ctx and the accesses are explicit ld / st.shared -- 2 STS + 10 LDS + 5 DFMA
+    // + 2 barriers, no index arithmetic, no divergence (lanes 25..31 compute on in-bounds scratch and return 0).  The
+    // out-of-line general version spent 55 instructions per product, most of them integer division by a runtime d
+    // (profiles/r02b_stableid_*).  Same order of additions as mul_impl.
+    template <int Q, bool TA, bool TB>
+    static __device__ __forceinline__ double dot5s(uint32_t a0, uint32_t b0) {
+        constexpr int SA = TA ? 40 : 8, SB = TB ? 8 : 40, O = 512 * Q;
+        double s = 0.0;
+        s = fma(lds_f64_off<O>(a0), lds_f64_off<O>(b0), s);
+        s = fma(lds_f64_off<O + SA>(a0), lds_f64_off<O + SB>(b0), s);
+        s = fma(lds_f64_off<O + 2 * SA>(a0), lds_f64_off<O + 2 * SB>(b0), s);
+        s = fma(lds_f64_off<O + 3 * SA>(a0), lds_f64_off<O + 3 * SB>(b0), s);
+        s = fma(lds_f64_off<O + 4 * SA>(a0), lds_f64_off<O + 4 * SB>(b0), s);
+        return s;
+    }
     static __device__ __forceinline__ LM mul(const Ctx& c, LM a, LM b, bool tA = false, bool tB = false) {
         if (c.d != 5) return mul_impl(c.sc, c.d, a, b, tA, tB);
-        const int l = lane_id();
-        double* sc = c.sc;
-        sc[l] = a;
-        sc[32 + l] = b;
+        sts_f64_off<0>(c.sW, a);
+        sts_f64_off<256>(c.sW, b);
         __syncwarp();
-        double s = 0.0;
-        if (l < 25) {
-            const double* A = tA ? sc + c.li : sc + 5 * c.li;
-            const double* B = tB ? sc + 32 + 5 * c.lj : sc + 32 + c.lj;
-#pragma unroll
-            for (int k = 0; k < 5; ++k) s = fma(tA ? A[5 * k] : A[k], tB ? B[k] : B[5 * k], s);
+        const uint32_t a0 = tA ? c.sAt : c.sAn, b0 = tB ? c.sBt : c.sBn;
+        const double s = tA ? (tB ? dot5s<0, true, true>(a0, b0) : dot5s<0, true, false>(a0, b0))
+                            : (tB ? dot5s<0, false, true>(a0, b0) : dot5s<0, false, false>(a0, b0));
+        __syncwarp();
+        return (lane_id() < 25) ? s : 0.0;
+    }
+    // Two independent products behind one pair of barriers (the R and Q blocks of every formula come in such pairs): twice the
+    // instruction-level parallelism of two mul() calls at half the barrier latency.  OUT OF LINE, one copy per combination
+    // of transposition flags, operands and addresses by value: with every product inlined the kernel was 35 k instructions
+    // (570 KB) and a third of all stall cycles were instruction-cache misses (profiles/r02d_stableid_*).
+    template <bool TA1, bool TB1, bool TA2, bool TB2>
+    static __device__ __noinline__ double2 mul2_d5(uint32_t sW, uint32_t a1s, uint32_t b1s, uint32_t a2s, uint32_t b2s, double a1,
+                                                   double b1, double a2, double b2) {
+        sts_f64_off<0>(sW, a1);
+        sts_f64_off<256>(sW, b1);
+        sts_f64_off<512>(sW, a2);
+        sts_f64_off<768>(sW, b2);
+        __syncwarp();
+        const double s1 = dot5s<0, TA1, TB1>(a1s, b1s);
+        const double s2 = dot5s<1, TA2, TB2>(a2s, b2s);
+        __syncwarp();
+        const bool in = lane_id() < 25;
+        return make_double2(in ? s1 : 0.0, in ? s2 : 0.0);
+    }
+    template <bool TA1, bool TB1, bool TA2, bool TB2>
+    static __device__ __forceinline__ void mul2(const Ctx& c, LM a1, LM b1, LM a2, LM b2, LM& o1, LM& o2) {
+        if (c.d != 5) {
+            o1 = mul_impl(c.sc, c.d, a1, b1, TA1, TB1);
+            o2 = mul_impl(c.sc, c.d, a2, b2, TA2, TB2);
+            return;
         }
-        __syncwarp();
-        return s;
+        const double2 r = mul2_d5<TA1, TB1, TA2, TB2>(c.sW, TA1 ? c.sAt : c.sAn, TB1 ? c.sBt : c.sBn, TA2 ? c.sAt : c.sAn,
+                                                      TB2 ? c.sBt : c.sBn, a1, b1, a2, b2);
+        o1 = r.x;
+        o2 = r.y;
+    }
+    // op(A1) M1 op(C1) and op(A2) M2 op(C2): two chained product pairs (congruences L . L', L' . L, P . P, ...)
+    template <bool TA1, bool TC1, bool TA2, bool TC2>
+    static __device__ __forceinline__ void chain2(const Ctx& c, LM a1, LM m1, LM c1, LM a2, LM m2, LM c2, LM& o1, LM& o2) {
+        LM u, v;
+        mul2<TA1, false, TA2, false>(c, a1, m1, a2, m2, u, v);
+        mul2<false, TC1, false, TC2>(c, u, c1, v, c2, o1, o2);
     }
     static __device__ __noinline__ LM transpose_impl(double* sc, int d, LM a) {
         const int l = lane_id();
@@ -252,17 +310,24 @@ struct StableIdFam {
         __syncwarp();
         return r;
     }
+    // every entry gathers its constraints' weights in constraint order: the same sums as the serial form (out of line: ~30
+    // call sites)
+    static __device__ __noinline__ double scatter_gather(double wc, double base, int s0, int s1, int s2, int s3, int dd) {
+        double r = base;
+        const double v0 = __shfl_sync(kFull, wc, s0 < 0 ? 0 : s0);
+        const double v1 = __shfl_sync(kFull, wc, s1 < 0 ? 0 : s1);
+        const double v2 = __shfl_sync(kFull, wc, s2 < 0 ? 0 : s2);
+        const double v3 = __shfl_sync(kFull, wc, s3 < 0 ? 0 : s3);
+        if (s0 >= 0) r = r + v0;
+        if (s1 >= 0) r = r + v1;
+        if (s2 >= 0) r = r + v2;
+        if (s3 >= 0) r = r + v3;
+        return (lane_id() < dd) ? r : 0.0;
+    }
     static __device__ __forceinline__ LM scatter(const Ctx& c, const CVec& w, const CVec& coef, LM base) {
         const double wc = w.v[0] * coef.v[0];
         if (c.nsrc < 0) return scatter_impl(c.sc, c.m, c.dd, c.rc, wc, base);
-        // every entry gathers its constraints' weights in constraint order: the same sums as the serial form
-        double r = base;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const double v = __shfl_sync(kFull, wc, c.src[q] < 0 ? 0 : c.src[q]);
-            if (c.src[q] >= 0) r = r + v;
-        }
-        return (lane_id() < c.dd) ? r : 0.0;
+        return scatter_gather(wc, base, c.src[0], c.src[1], c.src[2], c.src[3], c.dd);
     }
     // value of a lane matrix at this lane's constraint entry (r_i, c_i)
     static __device__ __noinline__ double at_constraint_impl(double* sc, int m, int my_rc, LM a) {
@@ -281,14 +346,13 @@ struct StableIdFam {
     static __device__ __forceinline__ Vec egrad2rgrad(const Ctx& c, const Pt& pt, LM egJ, LM egR, LM egQ) {
         Vec r;
         r.v[0] = skew(c, egJ);
-        r.v[1] = mul(c, mul(c, pt.x.v[1], symm(c, egR)), pt.x.v[1]);
-        r.v[2] = mul(c, mul(c, pt.x.v[2], symm(c, egQ)), pt.x.v[2]);
+        chain2<false, false, false, false>(c, pt.x.v[1], symm(c, egR), pt.x.v[1], pt.x.v[2], symm(c, egQ), pt.x.v[2], r.v[1], r.v[2]);
         return r;
     }
     // pull(Phi) = [Phi Q', -Phi Q', (J-R)' Phi], then egrad2rgrad
     static __device__ __forceinline__ Vec rgrad_of_phi(const Ctx& c, const Pt& pt, LM Phi) {
-        const LM gJ = mul(c, Phi, pt.x.v[2], false, true);
-        const LM gQ = mul(c, pt.JmR, Phi, true, false);
+        LM gJ, gQ;
+        mul2<false, true, true, false>(c, Phi, pt.x.v[2], pt.JmR, Phi, gJ, gQ);
         return egrad2rgrad(c, pt, gJ, -gJ, gQ);
     }
 
@@ -338,19 +402,16 @@ struct StableIdFam {
         pt.s.v[0] = -g;
         pt.coef.v[0] = coef;
         // one Cholesky factorisation per SPD block: positive definite iff it succeeds, P^-1 = L^-T L^-1
-        const bool okR = chol_and_inverse(c.sc, c.d, x.v[1], pt.LR, pt.LRi);
-        const bool okQ = chol_and_inverse(c.sc, c.d, x.v[2], pt.LQ, pt.LQi);
-        pt.Rinv = mul(c, pt.LRi, pt.LRi, true, false);
-        pt.Qinv = mul(c, pt.LQi, pt.LQi, true, false);
-        pt.spd_ok = okR && okQ;
+        pt.spd_ok = chol_pair(c, x.v[1], x.v[2], pt.LR, pt.LRi, pt.LQ, pt.LQi);
+        mul2<true, false, true, false>(c, pt.LRi, pt.LRi, pt.LQi, pt.LQi, pt.Rinv, pt.Qinv);
     }
 
     // <a, b>_x = <aJ, bJ> + tr(R^-1 aR R^-1 bR) + tr(Q^-1 aQ Q^-1 bQ): per-lane partial
     // (taking this and the gradient conversions out of line as well costs registers -- 12 instead of 16 warps per SM --
     // and was slower: 442 vs 367 ms for the 2048-pair sweep)
     static __device__ __forceinline__ double inner_partial(const Ctx& c, const Pt& pt, const Vec& a, const Vec& b) {
-        const LM tR = mul(c, mul(c, pt.Rinv, a.v[1]), pt.Rinv);
-        const LM tQ = mul(c, mul(c, pt.Qinv, a.v[2]), pt.Qinv);
+        LM tR, tQ;
+        chain2<false, false, false, false>(c, pt.Rinv, a.v[1], pt.Rinv, pt.Qinv, a.v[2], pt.Qinv, tR, tQ);
         const LM bRt = transpose(c, b.v[1]), bQt = transpose(c, b.v[2]);
         return (a.v[0] * b.v[0] + tR * bRt) + tQ * bQt;
     }
@@ -380,7 +441,9 @@ struct StableIdFam {
 
     // dA along v
     static __device__ __forceinline__ LM dA_of(const Ctx& c, const Pt& pt, const Vec& v) {
-        return mul(c, v.v[0] - v.v[1], pt.x.v[2]) + mul(c, pt.JmR, v.v[2]);
+        LM p1, p2;
+        mul2<false, false, false, false>(c, v.v[0] - v.v[1], pt.x.v[2], pt.JmR, v.v[2], p1, p2);
+        return p1 + p2;
     }
 
     // 'is_euclidean_embedded' (RIPTRM.py:553-571): G*[v]_i = <-egrad g_i, v>_x with the EUCLIDEAN gradient inside the
@@ -389,9 +452,10 @@ struct StableIdFam {
     // form on this manifold -- the option is meant for submanifolds with the embedded metric -- but it is what the reference
     // evaluates when the key is set).
     static __device__ __forceinline__ LM dA_embedded(const Ctx& c, const Pt& pt, const Vec& v) {
-        const LM wR = mul(c, mul(c, pt.Rinv, v.v[1]), pt.Rinv);
-        const LM wQ = mul(c, mul(c, pt.Qinv, v.v[2]), pt.Qinv);
-        return mul(c, v.v[0] - wR, pt.x.v[2]) + mul(c, pt.JmR, wQ);
+        LM wR, wQ, p1, p2;
+        chain2<false, false, false, false>(c, pt.Rinv, v.v[1], pt.Rinv, pt.Qinv, v.v[2], pt.Qinv, wR, wQ);
+        mul2<false, false, false, false>(c, v.v[0] - wR, pt.x.v[2], pt.JmR, wQ, p1, p2);
+        return p1 + p2;
     }
 
     static __device__ __forceinline__ CVec gadj(const Ctx& c, const Pt& pt, const Vec& v) {
@@ -420,18 +484,21 @@ struct StableIdFam {
         ydc.v[0] = y.v[0] * dcoef.v[0];
         const LM dPhiL = scatter(c, ydc, ones, dga);
         // pull_d: hJ = dPhi Q' + Phi dQ' ; hR = -hJ ; hQ = (dJ - dR)' Phi + (J - R)' dPhi
-        const LM hJ = mul(c, dPhiL, pt.x.v[2], false, true) + mul(c, st.PhiL, v.v[2], false, true);
-        const LM hQ = mul(c, v.v[0] - v.v[1], st.PhiL, true, false) + mul(c, pt.JmR, dPhiL, true, false);
+        LM h1, h2, h3, h4, gJ, gQ;
+        mul2<false, true, false, true>(c, dPhiL, pt.x.v[2], st.PhiL, v.v[2], h1, h2);
+        mul2<true, false, true, false>(c, v.v[0] - v.v[1], st.PhiL, pt.JmR, dPhiL, h3, h4);
+        const LM hJ = h1 + h2, hQ = h3 + h4;
         // Euclidean gradient of the Lagrangian
-        const LM gJ = mul(c, st.PhiL, pt.x.v[2], false, true);
-        const LM gQ = mul(c, pt.JmR, st.PhiL, true, false);
+        mul2<false, true, true, false>(c, st.PhiL, pt.x.v[2], pt.JmR, st.PhiL, gJ, gQ);
         Vec hl;
         hl.v[0] = skew(c, hJ);
         {
-            const LM R = pt.x.v[1];
-            hl.v[1] = mul(c, mul(c, R, symm(c, -hJ)), R) + symm(c, mul(c, mul(c, v.v[1], symm(c, -gJ)), R));
-            const LM Q = pt.x.v[2];
-            hl.v[2] = mul(c, mul(c, Q, symm(c, hQ)), Q) + symm(c, mul(c, mul(c, v.v[2], symm(c, gQ)), Q));
+            const LM R = pt.x.v[1], Q = pt.x.v[2];
+            LM a1, a2, b1, b2;
+            chain2<false, false, false, false>(c, R, symm(c, -hJ), R, Q, symm(c, hQ), Q, a1, a2);
+            chain2<false, false, false, false>(c, v.v[1], symm(c, -gJ), R, v.v[2], symm(c, gQ), Q, b1, b2);
+            hl.v[1] = a1 + symm(c, b1);
+            hl.v[2] = a2 + symm(c, b2);
         }
         // condensed barrier term G_x((y/s) * G*[v]) = -rgrad(pull(sum_i w_i Phi_i))
         CVec w;
@@ -464,41 +531,32 @@ struct StableIdFam {
         w.LRi = pt.LRi;
         w.LQ = pt.LQ;
         w.LQi = pt.LQi;
-        const LM gJ = mul(c, st.PhiL, pt.x.v[2], false, true);
-        const LM gQ = mul(c, pt.JmR, st.PhiL, true, false);
-        w.GR = mul(c, mul(c, w.LR, symm(c, -gJ), true, false), w.LR);
-        w.GQ = mul(c, mul(c, w.LQ, symm(c, gQ), true, false), w.LQ);
+        LM gJ, gQ;
+        mul2<false, true, true, false>(c, st.PhiL, pt.x.v[2], pt.JmR, st.PhiL, gJ, gQ);
+        chain2<true, false, true, false>(c, w.LR, symm(c, -gJ), w.LR, w.LQ, symm(c, gQ), w.LQ, w.GR, w.GQ);
     }
     static __device__ __forceinline__ Vec whiten(const Ctx& c, const White& w, const Vec& v) {
         Vec r;
         r.v[0] = v.v[0];
-        r.v[1] = mul(c, mul(c, w.LRi, v.v[1]), w.LRi, false, true);
-        r.v[2] = mul(c, mul(c, w.LQi, v.v[2]), w.LQi, false, true);
+        chain2<false, true, false, true>(c, w.LRi, v.v[1], w.LRi, w.LQi, v.v[2], w.LQi, r.v[1], r.v[2]);
         return r;
     }
     static __device__ __forceinline__ Vec unwhiten(const Ctx& c, const White& w, const Vec& v) {
         Vec r;
         r.v[0] = v.v[0];
-        r.v[1] = mul(c, mul(c, w.LR, v.v[1]), w.LR, false, true);
-        r.v[2] = mul(c, mul(c, w.LQ, v.v[2]), w.LQ, false, true);
+        chain2<false, true, false, true>(c, w.LR, v.v[1], w.LR, w.LQ, v.v[2], w.LQ, r.v[1], r.v[2]);
         return r;
     }
     // whitened Hw: vh -> whiten(Hw[unwhiten(vh)])
     static __device__ __forceinline__ Vec Hw_white(const Ctx& c, const Pt& pt, const CVec& y, const Step& st, const White& w,
                                                    const Vec& vh) {
-        const LM vR = mul(c, mul(c, w.LR, vh.v[1]), w.LR, false, true);
-        const LM vQ = mul(c, mul(c, w.LQ, vh.v[2]), w.LQ, false, true);
+        LM vR, vQ, p1, p2;
+        chain2<false, true, false, true>(c, w.LR, vh.v[1], w.LR, w.LQ, vh.v[2], w.LQ, vR, vQ);
         const LM D1 = vh.v[0] - vR;
-        const LM dA = mul(c, D1, pt.x.v[2]) + mul(c, pt.JmR, vQ);
-        put(c, 7, dA);
-        double dga = 0.0;
-        if (on(c)) {
-            const int d = c.d, i = lane_id() / d, j = lane_id() - i * d;
-            double s = 0.0;
-            for (int k = 0; k < d; ++k) s = fma(slot(c, 7)[i * d + k], c.XXt[k * d + j], s);
-            dga = (2.0 * c.h * c.h) * s / (double)c.N;
-        }
-        __syncwarp();
+        // dA = D1 Q + (J-R) vQ, and dA (X X') for dG_A = 2 h^2 dA (X X') / N: XXt sits in the product scratch as a lane matrix
+        mul2<false, false, false, false>(c, D1, pt.x.v[2], pt.JmR, vQ, p1, p2);
+        const LM dA = p1 + p2;
+        const double dga = (2.0 * c.h * c.h) * mul(c, dA, c.XXt_lm) / (double)c.N;
         const double dArc = at_constraint(c, dA);
         double gArc = dArc;
         if (c.embedded) {
@@ -514,13 +572,17 @@ struct StableIdFam {
         wc.v[0] = y.v[0] * dcoef - wi * pt.coef.v[0];
         ones.v[0] = 1.0;
         const LM dPhi = scatter(c, wc, ones, dga);
-        const LM hJ = mul(c, dPhi, pt.x.v[2], false, true) + mul(c, st.PhiL, vQ, false, true);
-        const LM hQ = mul(c, D1, st.PhiL, true, false) + mul(c, pt.JmR, dPhi, true, false);
+        LM h1, h2, h3, h4, g1, g2, o1, o2;
+        mul2<false, true, false, true>(c, dPhi, pt.x.v[2], st.PhiL, vQ, h1, h2);
+        mul2<true, false, true, false>(c, D1, st.PhiL, pt.JmR, dPhi, h3, h4);
+        const LM hJ = h1 + h2, hQ = h3 + h4;
         const LM hJt = transpose(c, hJ);
+        mul2<false, false, false, false>(c, vh.v[1], w.GR, vh.v[2], w.GQ, g1, g2);
+        chain2<true, false, true, false>(c, w.LR, -0.5 * (hJ + hJt), w.LR, w.LQ, symm(c, hQ), w.LQ, o1, o2);
         Vec out;
         out.v[0] = 0.5 * (hJ - hJt);
-        out.v[1] = mul(c, mul(c, w.LR, -0.5 * (hJ + hJt), true, false), w.LR) + symm(c, mul(c, vh.v[1], w.GR));
-        out.v[2] = mul(c, mul(c, w.LQ, symm(c, hQ), true, false), w.LQ) + symm(c, mul(c, vh.v[2], w.GQ));
+        out.v[1] = o1 + symm(c, g1);
+        out.v[2] = o2 + symm(c, g2);
         return out;
     }
     static __device__ __forceinline__ double dotw(const Vec& a, const Vec& b) {
@@ -681,6 +743,77 @@ struct StableIdFam {
         Li_out = lio;
         return ok;
     }
+    // Cholesky factors and their inverses of BOTH SPD blocks at once: lanes 0..15 factor R, lanes 16..31 factor Q (every lane
+    // of a half redundantly, in registers: d == 5 is unrolled), one reciprocal square root per pivot and no division; lanes 0
+    // and 16 publish their half's result and every lane picks up its entries.  (Two calls of the general routine were 10 %
+    // of the kernel's time: 30 dependent divisions / square roots each.)
+    static __device__ __noinline__ bool chol_pair(const Ctx& c, LM R, LM Q, LM& LR, LM& LRi, LM& LQ, LM& LQi) {
+        if (c.d != 5) {
+            const bool a = chol_and_inverse(c.sc, c.d, R, LR, LRi);
+            const bool b = chol_and_inverse(c.sc, c.d, Q, LQ, LQi);
+            return a && b;
+        }
+        const int l = lane_id();
+        const uint32_t base = c.sChol;
+        sts_f64(base + 8 * l, R);              // [0, 32): R, [32, 64): Q
+        sts_f64(base + 256 + 8 * l, Q);
+        __syncwarp();
+        const uint32_t mine = base + ((l >= 16) ? 256u : 0u);
+        double P[5][5], L[5][5], Li[5][5], ri[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) P[i][j] = lds_f64(mine + 8 * (5 * i + j));
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            double s = P[j][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) s = fma(-L[j][k], L[j][k], s);
+            ok = ok && (s > 0.0);
+            ri[j] = rsqrt(s);
+            L[j][j] = s * ri[j];
+#pragma unroll
+            for (int i = j + 1; i < 5; ++i) {
+                double t = P[i][j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) t = fma(-L[i][k], L[j][k], t);
+                L[i][j] = t * ri[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {          // L Li = I, column by column
+            Li[j][j] = ri[j];
+#pragma unroll
+            for (int i = j + 1; i < 5; ++i) {
+                double t = 0.0;
+#pragma unroll
+                for (int k = j; k < i; ++k) t = fma(L[i][k], Li[k][j], t);
+                Li[i][j] = -t * ri[i];
+            }
+        }
+        __syncwarp();
+        if ((l & 15) == 0) {                    // [64, 96): L, [96, 128): Li of R ; Q 32 doubles further on -- 2 x 64 = 128
+            const uint32_t o = base + 512 + ((l >= 16) ? 512u : 0u);
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    sts_f64(o + 8 * (5 * i + j), (j <= i) ? L[i][j] : 0.0);
+                    sts_f64(o + 256 + 8 * (5 * i + j), (j <= i) ? Li[i][j] : 0.0);
+                }
+        }
+        __syncwarp();
+        const bool in = l < 25;
+        const uint32_t e = base + 512 + 8 * (in ? l : 0);
+        LR = in ? lds_f64(e) : 0.0;
+        LRi = in ? lds_f64(e + 256) : 0.0;
+        LQ = in ? lds_f64(e + 512) : 0.0;
+        LQi = in ? lds_f64(e + 768) : 0.0;
+        const bool okR = __shfl_sync(kFull, ok ? 1 : 0, 0) != 0, okQ = __shfl_sync(kFull, ok ? 1 : 0, 16) != 0;
+        __syncwarp();
+        return okR && okQ;
+    }
     static __device__ __noinline__ bool chol_and_inverse(double* sc, int d, LM P, LM& L_out, LM& Li_out) {
         const int l = lane_id();
         sc[l] = P;
@@ -716,8 +849,7 @@ struct StableIdFam {
         Vec v;
         v.v[0] = unpack(c, coef, true);
         const LM KR = unpack(c, coef + ns, false), KQ = unpack(c, coef + ns + np, false);
-        v.v[1] = mul(c, mul(c, cc.LR, KR), cc.LR, false, true);
-        v.v[2] = mul(c, mul(c, cc.LQ, KQ), cc.LQ, false, true);
+        chain2<false, true, false, true>(c, cc.LR, KR, cc.LR, cc.LQ, KQ, cc.LQ, v.v[1], v.v[2]);
         return v;
     }
     static __device__ __forceinline__ void pack(const Ctx& c, LM a, double* out, bool skewpart) {
@@ -738,16 +870,20 @@ struct StableIdFam {
     }
     static __device__ __forceinline__ void to_coords(const Ctx& c, const Pt&, const Coord& cc, const Vec& v, double* out) {
         const int ns = c.d * (c.d - 1) / 2, np = c.d * (c.d + 1) / 2;
+        LM kR, kQ;
+        chain2<false, true, false, true>(c, cc.LRi, v.v[1], cc.LRi, cc.LQi, v.v[2], cc.LQi, kR, kQ);
         pack(c, v.v[0], out, true);
-        pack(c, mul(c, mul(c, cc.LRi, v.v[1]), cc.LRi, false, true), out + ns, false);
-        pack(c, mul(c, mul(c, cc.LQi, v.v[2]), cc.LQi, false, true), out + ns + np, false);
+        pack(c, kR, out + ns, false);
+        pack(c, kQ, out + ns + np, false);
     }
 
     static __device__ __forceinline__ Vec retract(const Ctx& c, const Pt& pt, const Vec& dx) {
         Vec r;
         r.v[0] = pt.x.v[0] + dx.v[0];
-        r.v[1] = symm(c, (pt.x.v[1] + dx.v[1]) + mul(c, dx.v[1], mul(c, pt.Rinv, dx.v[1])) / 2.0);
-        r.v[2] = symm(c, (pt.x.v[2] + dx.v[2]) + mul(c, dx.v[2], mul(c, pt.Qinv, dx.v[2])) / 2.0);
+        LM qR, qQ;
+        chain2<false, false, false, false>(c, dx.v[1], pt.Rinv, dx.v[1], dx.v[2], pt.Qinv, dx.v[2], qR, qQ);
+        r.v[1] = symm(c, (pt.x.v[1] + dx.v[1]) + qR / 2.0);
+        r.v[2] = symm(c, (pt.x.v[2] + dx.v[2]) + qQ / 2.0);
         return r;
     }
 
@@ -772,27 +908,34 @@ struct StableIdFam {
     }
 
     // eigenvalues of P^{-1/2} B P^{-1/2} (= those of chol(P)^-1 B chol(P)^-T): || log w ||
-    static __device__ __forceinline__ double spd_dist(const Ctx& c, LM P, LM B) {
-        put(c, 2, P);
+    // (out of line, scalars by value: only evaluated when a trace row is written)
+    static __device__ __noinline__ double spd_dist_impl(double* sc, int d, int tlane, LM P, LM B) {
+        const int l = lane_id();
+        double* s2 = sc + 64;
+        s2[l] = P;
+        __syncwarp();
         double w[DMAX], V[DMAX][DMAX];
-        sm::jacobi_eig<DMAX>(slot(c, 2), c.d, w, V);
+        sm::jacobi_eig<DMAX>(s2, d, w, V);
         __syncwarp();
         double ih = 0.0;
-        if (on(c)) {
-            const int d = c.d, i = lane_id() / d, j = lane_id() - i * d;
+        if (l < d * d) {
+            const int i = l / d, j = l - i * d;
             for (int k = 0; k < d; ++k) ih = fma(V[i][k] * (1.0 / sqrt(w[k])), V[j][k], ih);
         }
-        const LM M = symm(c, mul(c, mul(c, ih, B), ih));
-        put(c, 2, M);
-        sm::jacobi_eig<DMAX>(slot(c, 2), c.d, w, V);
+        const LM t = mul_impl(sc, d, mul_impl(sc, d, ih, B, false, false), ih, false, false);
+        const LM M = 0.5 * (t + __shfl_sync(kFull, t, tlane));
+        s2[l] = M;
+        __syncwarp();
+        sm::jacobi_eig<DMAX>(s2, d, w, V);
         __syncwarp();
         double acc = 0.0;
-        for (int k = 0; k < c.d; ++k) {
+        for (int k = 0; k < d; ++k) {
             const double lg = log(w[k]);
             acc += lg * lg;
         }
         return sqrt(acc);
     }
+    static __device__ __forceinline__ double spd_dist(const Ctx& c, LM P, LM B) { return spd_dist_impl(c.sc, c.d, c.tlane, P, B); }
     static __device__ __forceinline__ double dist(const Ctx& c, const Vec& xPrev, const Pt& pt) {
         const double dj = xPrev.v[0] - pt.x.v[0];
         const double nJ = sqrt(wsum(dj * dj));

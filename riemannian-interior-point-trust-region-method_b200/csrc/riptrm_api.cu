@@ -1194,8 +1194,11 @@ struct SmallParams {
     int generic_tcg;               // StableIdentification: tCG on unwhitened vectors (measurement switch RIPTRM_STABLEID_GENERIC_TCG)
 };
 
+#ifndef RIPTRM_SMALL_MINBLOCKS
+#define RIPTRM_SMALL_MINBLOCKS 16
+#endif
 template <class F, int MODE, bool EXACT = false>
-__global__ void __launch_bounds__(32, EXACT ? 4 : 16) small_kernel(SmallParams P, DevOpts o, int* counter) {  // <= 128 registers: 16 warps per SM
+__global__ void __launch_bounds__(32, EXACT ? 4 : RIPTRM_SMALL_MINBLOCKS) small_kernel(SmallParams P, DevOpts o, int* counter) {  // <= 128 registers: 16 warps per SM
     extern __shared__ __align__(16) double smem[];
     typename F::Ctx ctx = F::make_ctx(P, o, smem);
     const int lane = lane_id();
