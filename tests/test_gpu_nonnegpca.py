@@ -156,7 +156,8 @@ def test_gpu_trace_is_bit_identical_to_the_c_oracle(rb, datasets):
     rows = int(sm[0, _lib.SM["trace_rows"]])
     assert rows == len(tro) == int(smo[15])
     T = _lib.TR
-    exact = [i for name, i in T.items() if name not in ("time", "distance")]
+    exact = [i for name, i in T.items() if name not in ("time", "distance", "mineigvalHw")]   # the C oracle writes 25 fields
+    assert np.isnan(tr[0, :rows, T["mineigvalHw"]]).all()                                      # (no eigenvalue test under tCG)
     a, b = tr[0, :rows][:, exact], tro[:, exact]
     same = (a == b) | (np.isnan(a) & np.isnan(b))
     assert same.all(), f"first differing (row, field): {np.argwhere(~same)[:5]}"
@@ -248,8 +249,12 @@ def test_error_paths_through_the_c_abi(rb):
     assert lib.riptrm_destroy(h) == 0
     with pytest.raises(rb.RiptrmError, match="n <= 128"):
         rb._lib.check(lib.riptrm_create(1, 129, 1, 129, 1, 0, C.byref(h)))
-    with pytest.raises(NotImplementedError):
-        rb.RIPTRM({"TRS_solver": "Exact_RepMat"}).run_batch([None], structures=[rb.NonnegPCAStructure(Z=Z[0], x0=x[0], y0=x[0])])
+    with pytest.raises(ValueError, match="not supported"):        # the reference's own error (RIPTRM.py:453-454)
+        rb.RIPTRM({"TRS_solver": "Newton"}).run_batch([None], structures=[rb.NonnegPCAStructure(Z=Z[0], x0=x[0], y0=x[0])])
+    # the exact solver keeps three dim x dim matrices per pair in shared memory: Sphere(n) up to n = 64
+    big = rb.NonnegPCAStructure(Z=np.eye(80), x0=np.full(80, 80 ** -0.5), y0=np.ones(80))
+    with pytest.raises(rb.RiptrmError, match="n <= 64"):
+        rb.RIPTRM({"TRS_solver": "Exact_RepMat", "maxiter": 1}).run_batch([None], structures=[big])
 
 
 def test_tmem_and_shared_memory_kernels_agree_bit_for_bit(rb, monkeypatch):
