@@ -225,7 +225,9 @@ int riptrm_set_options(riptrm_handle* h, const riptrm_options* opts);
  * Outputs (any may be NULL): x [batch][n*p], y [batch][m], summary [batch][RIPTRM_SUMMARY_FIELDS],
  * trace [batch][trace_capacity][RIPTRM_TRACE_FIELDS].  `stream` is a cudaStream_t (or NULL).
  * With `where` == RIPTRM_HOST the call returns after the results are in the host buffers;
- * with RIPTRM_DEVICE it only enqueues work on `stream`. */
+ * with RIPTRM_DEVICE the batched families (1-3) only enqueue work on `stream`.  The COLUMNS / STIEFEL families (4, 5) are
+ * sequenced by the host -- one tCG launch and one post launch per trust-region iteration, with a one-int device-to-host poll
+ * of the "all done" flag in between -- so their solve returns when the solve has finished, in either mode. */
 int riptrm_solve(riptrm_handle* h, const double* x0, const double* y0, double* x, double* y,
                  double* summary, double* trace, int where, void* stream);
 
@@ -269,6 +271,12 @@ int riptrm_trs_dense(int device, int d, int count, const double* A, const double
  * function of (instance id, stream, index) through Philox4x32-10, so ranks draw their own shares independently. */
 int riptrm_generate_nonnegpca(int device, int n, long long first_instance, int instances, int points_per_instance,
                               double snr, double delta, double* Z, double* x0, double* y0, void* stream);
+
+/* Diagnostic: where and when the CTAs of the last launch of a Sphere solve with a fast lane ran.  out[i] = (SM id << 4) | role
+ * (role 1: main CTA, 2: lane CTA, 3: stepped aside for a lane CTA; 0: no record), times[2 i], times[2 i + 1] = %globaltimer at
+ * the CTA's entry and exit (ns; may be NULL).  Records [0, 2 x SMs) are the main kernel's CTAs, the lane kernel's CTAs of the
+ * two-kernel form follow.  Returns the number of records written (0: no lane in the last solve, < 0: CUDA error). */
+int riptrm_lane_placement(riptrm_handle* h, int* out, unsigned long long* times, int capacity);
 
 /* number of kernel launches the handle has issued (for bench.py's gpu_launches) */
 int64_t riptrm_launch_count(const riptrm_handle* h);

@@ -87,6 +87,7 @@ SYMBOLS = {
                                    C.c_void_p, C.c_int, C.c_void_p]),
     "riptrm_generate_nonnegpca": (C.c_int, [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_double, C.c_double,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "riptrm_lane_placement": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "riptrm_launch_count": (C.c_int64, [C.c_void_p]),
     "riptrm_matvec_passes": (C.c_int64, [C.c_void_p]),
     "riptrm_last_kernel_ms": (C.c_double, [C.c_void_p]),

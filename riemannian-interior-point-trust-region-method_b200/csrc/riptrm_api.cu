@@ -73,6 +73,9 @@ struct riptrm_handle {
     size_t trace_bytes = 0;
     int* d_counter = nullptr;   // [2]: work queue of the main kernel, work queue of the fast lane
     int* d_fast_order = nullptr;  // fast lane: the pairs of the longest units
+    int* d_lane_state = nullptr;  // fast lane: election state (2 + 2 * 256 ints) + per-CTA placement records
+    unsigned long long* d_lane_times = nullptr;   // entry / exit globaltimer of the recorded CTAs
+    int lane_debug_len = 0;
     cudaStream_t lane_stream = nullptr;
     cudaEvent_t lane_ev0 = nullptr, lane_ev1 = nullptr;
     // two-launch schedule of the batched families (longest pairs first in the second launch)
@@ -111,6 +114,13 @@ struct SphereParams {
     int pause_at;      // first launch: outer iteration to pause at (< 0: run to the end)
     int sibling_units; // 1: the queue (and `order`) counts units of two consecutive pairs that share a Z (sphere_tmem2_kernel)
     int queue_len;     // entries of the work queue (0: batch, or batch / 2 units)
+    // fast lane inside sphere_tmem2_kernel: `lane_ctas` CTAs, each alone on its SM, solve the pairs of `fast_order` one warp
+    // per scheduler; lane_state = {lanes taken, CTAs arrived, arrivals per SM [256], role per SM [256]}; lane_debug [grid]
+    int lane_ctas, fast_len;
+    const int* fast_order;
+    int* lane_state;
+    int* lane_debug;
+    unsigned long long* lane_times;   // [CTA][2]: globaltimer at entry / exit of the CTAs that write a lane_debug record
     // hooks
     const double* v;
     double mu;
@@ -122,6 +132,9 @@ struct SphereParams {
     int newton_method, kr_maxiter;
     double kr_tol;
 };
+
+enum { kLaneMain = 1, kLaneLane = 2, kLaneExit = 3 };   // roles in the fast-lane placement record (riptrm_lane_placement)
+constexpr int kLaneMaxSms = 256;
 
 // Loads Z of one instance into shared memory and symmetrises it in place: S = Z + Z'
 // (Z is not symmetric: src/NonnegPCA/generator.py:25-28; Hessian of -x'Zx is -(Z+Z')).
@@ -380,6 +393,8 @@ extern "C" int riptrm_destroy(riptrm_handle* h) {
     free_any(h->d_passes);
     free_any(h->d_counter);
     free_any(h->d_fast_order);
+    free_any(h->d_lane_state);
+    free_any(h->d_lane_times);
     if (h->lane_stream) cudaStreamDestroy(h->lane_stream);
     if (h->lane_ev0) cudaEventDestroy(h->lane_ev0);
     if (h->lane_ev1) cudaEventDestroy(h->lane_ev1);
@@ -893,6 +908,12 @@ __global__ void __launch_bounds__(128, 2) sphere_tmem_kernel(SphereParams P, Dev
     const int n = 50, ns = 50, pad = 64;
     const int warp = threadIdx.x >> 5, lane = lane_id();
     double* my = smem + (size_t)warp * (n * ns + pad + 64);
+    if (P.lane_debug != nullptr && threadIdx.x == 0) {   // placement record of the two-kernel lane: (smid << 4) | role
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        P.lane_debug[blockIdx.x] = (int)(smid << 4) | kLaneLane;
+        if (P.lane_times != nullptr) P.lane_times[2 * blockIdx.x] = global_timer_ns();
+    }
     if (warp == 0) tmem::alloc(&tmem_base, 256);
     tmem::fence_before_sync();
     __syncthreads();
@@ -957,6 +978,7 @@ __global__ void __launch_bounds__(128, 2) sphere_tmem_kernel(SphereParams P, Dev
     tmem::fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem::dealloc(tmem_base, 256);
+    if (P.lane_times != nullptr && threadIdx.x == 0) P.lane_times[2 * blockIdx.x + 1] = global_timer_ns();
 }
 
 // The same with two warps per copy of S.  Consecutive pairs of one instance (its initial points) share Z, and a warp of the
@@ -964,6 +986,16 @@ __global__ void __launch_bounds__(128, 2) sphere_tmem_kernel(SphereParams P, Dev
 // the two pairs of a unit from one copy of S in sub-partition w % 4.  16 resident warps per SM instead of 8 (the
 // register file then allows 128 registers per thread), TMEM and staging traffic per pair halved.  The pairs of an
 // instance do nearly the same work (correlation 0.99), so the warps of a unit finish together.
+// Fast lane BY CONSTRUCTION (round 2; replaces a second kernel on a priority stream whose CTAs were given their SMs by a
+// 30 us sleep kernel and a 150 KB shared-memory request).  The grid is two CTAs per SM, which is what fits (128 registers x 256
+// threads, 86 KB).  The first CTA to arrive on an SM (an atomic per %smid) claims one of `lane_ctas` lane slots or declares
+// the SM a main SM; the second CTA reads that decision -- the first one is running, so the wait is bounded -- and, on a lane
+// SM, steps aside: it waits until all CTAs of the grid have arrived (none is pending that could be placed next to the lane
+// CTA; the wait is capped at 200 us so that a smaller residency than expected costs speed, never progress) and exits.
+// A lane CTA therefore owns its SM: its warps
+// 0..3 -- one per scheduler, the residency at which a tCG iteration takes 1.0 us instead of 2.4 -- solve the pairs of the
+// longest units (`fast_order`), its warps 4..7 have nothing to do.  `lane_debug` records (smid, role) per CTA for the test.
+
 template <int MODE>
 __global__ void __launch_bounds__(256, 2) sphere_tmem2_kernel(SphereParams P, DevOpts o, int* counter) {
     using F = SphereFam<2, 50, true, 32>;
@@ -971,10 +1003,51 @@ __global__ void __launch_bounds__(256, 2) sphere_tmem2_kernel(SphereParams P, De
     extern __shared__ __align__(16) double smem[];
     __shared__ uint32_t tmem_base;
     __shared__ int unit_slot[4];
+    __shared__ int cta_role;
     const int n = 50, ns = 50, pad = 64;
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int q = warp & 3, role = warp >> 2;
     double* stage = smem + (size_t)q * (n * ns + pad);
+    if (P.lane_ctas > 0) {
+        if (threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            int* st = P.lane_state;
+            int r = kLaneMain;
+            if (smid < (unsigned)kLaneMaxSms) {
+                const int slot = atomicAdd(st + 2 + smid, 1);
+                if (slot == 0) {
+                    r = (atomicAdd(st, 1) < P.lane_ctas) ? kLaneLane : kLaneMain;
+                    __threadfence();
+                    atomicExch(st + 2 + kLaneMaxSms + smid, r);
+                } else {
+                    int first;
+                    do {
+                        first = atomicAdd(st + 2 + kLaneMaxSms + smid, 0);   // the first CTA of this SM is running: bounded wait
+                    } while (first == 0);
+                    r = (first == kLaneLane) ? kLaneExit : kLaneMain;
+                }
+            }
+            atomicAdd(st + 1, 1);
+            if (r == kLaneExit) {   // all CTAs placed: nobody can follow us onto this SM
+                const uint64_t t0 = global_timer_ns();
+                while (atomicAdd(st + 1, 0) < (int)gridDim.x && global_timer_ns() - t0 < 200000ull) __nanosleep(200);
+            }
+            if (P.lane_debug != nullptr) P.lane_debug[blockIdx.x] = (int)(smid << 4) | r;
+            if (P.lane_times != nullptr) P.lane_times[2 * blockIdx.x] = global_timer_ns();
+            cta_role = r;
+        }
+        __syncthreads();
+        if (cta_role == kLaneExit) return;
+    } else if (threadIdx.x == 0) {
+        cta_role = kLaneMain;
+        if (P.lane_debug != nullptr) {   // main kernel next to the two-kernel lane: record where this CTA runs
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            P.lane_debug[blockIdx.x] = (int)(smid << 4) | kLaneMain;
+            if (P.lane_times != nullptr) P.lane_times[2 * blockIdx.x] = global_timer_ns();
+        }
+    }
     if (warp == 0) tmem::alloc(&tmem_base, 256);
     tmem::fence_before_sync();
     __syncthreads();
@@ -990,7 +1063,34 @@ __global__ void __launch_bounds__(256, 2) sphere_tmem2_kernel(SphereParams P, De
     const int units = P.batch / 2, ipp = P.batch / P.batch_z;
     auto pair_bar = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
     int loaded_z = -1;
-    while (true) {
+    const bool lane_cta = cta_role == kLaneLane;
+    while (lane_cta && role == 0) {
+        // lane worker: one pair at a time from the fast queue, this warp's own copy of S in its TMEM sub-partition
+        int i = 0;
+        if (lane == 0) i = atomicAdd(counter + 1, 1);
+        i = __shfl_sync(kFull, i, 0);
+        if (i >= P.fast_len) break;
+        const int inst = P.fast_order[i];
+        double* pause = P.pause + (size_t)inst * kPauseFields;
+        if (pause[7] != 2.0) continue;           // finished in an earlier launch
+        const int zi = inst / ipp;
+        if (zi != loaded_z) {
+            load_S(P.Z + (size_t)zi * n * n, stage, n, ns, pad);
+            F::stage_to_tmem(ctx);
+            loaded_z = zi;
+        }
+        const typename F::Vec x0 = load_vec<K>(P.x + (size_t)inst * n, n);
+        const typename F::CVec y0 = load_vec<K>(P.y + (size_t)inst * n, n);
+        typename F::Pt pt;
+        typename F::CVec y;
+        double* tr = (P.trace != nullptr && o.trace_mode != 0) ? P.trace + (size_t)inst * o.trace_capacity * RIPTRM_TRACE_FIELDS
+                                                               : nullptr;
+        solve_instance<F>(ctx, o, x0, y0, pt, y, P.summary ? P.summary + (size_t)inst * RIPTRM_SUMMARY_FIELDS : nullptr, tr,
+                          pause, true, P.pause_at);
+        if (P.x) store_vec<K>(P.x + (size_t)inst * n, pt.x, n);
+        if (P.y) store_vec<K>(P.y + (size_t)inst * n, y, n);
+    }
+    while (!lane_cta) {
         if (role == 0 && lane == 0) unit_slot[q] = atomicAdd(counter, 1);
         pair_bar();
         int unit = unit_slot[q];
@@ -1030,6 +1130,7 @@ __global__ void __launch_bounds__(256, 2) sphere_tmem2_kernel(SphereParams P, De
     tmem::fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem::dealloc(tmem_base, 256);
+    if (P.lane_times != nullptr && threadIdx.x == 0) P.lane_times[2 * blockIdx.x + 1] = global_timer_ns();
 }
 
 static int launch_sphere_tmem2(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
@@ -1042,11 +1143,17 @@ static int launch_sphere_tmem2(riptrm_handle* h, const SphereParams& P, const De
     if (grid > need) grid = need;
     CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
     CUDA_TRY(cudaEventRecord(h->ev0, st));
+    if (P.lane_ctas > 0) grid = h->num_sms * 2;   // the lane election counts on two CTAs per SM
     kern<<<grid, 256, smem, st>>>(P, o, h->d_counter);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(h->ev1, st));
     h->launches += 1;
     return RIPTRM_OK;
+}
+
+// can the lane be carved out of the main kernel's own grid?  (SM ids within the election table, enough units to fill the grid)
+static bool lane_in_kernel_possible(riptrm_handle* h) {
+    return h->num_sms <= kLaneMaxSms && h->batch / 2 >= h->num_sms * 8;
 }
 
 template <int MODE>
@@ -1339,6 +1446,44 @@ static SmallParams small_params(const riptrm_handle* h) {
     return P;
 }
 
+// election state + placement records (main-kernel CTAs in [0, 2 sms), lane-kernel CTAs of the two-kernel form after them)
+static int ensure_lane_buffers(riptrm_handle* h, cudaStream_t st) {
+    const int records = h->num_sms * 2 + 64, total = 2 + 2 * kLaneMaxSms + records;
+    if (h->d_lane_state == nullptr || h->lane_debug_len < records) {
+        free_any(h->d_lane_state);
+        free_any(h->d_lane_times);
+        CUDA_TRY(cudaMalloc(&h->d_lane_state, (size_t)total * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&h->d_lane_times, (size_t)2 * records * sizeof(unsigned long long)));
+        h->lane_debug_len = records;
+    }
+    CUDA_TRY(cudaMemsetAsync(h->d_lane_state, 0, (size_t)total * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(h->d_lane_times, 0, (size_t)2 * records * sizeof(unsigned long long), st));
+    return RIPTRM_OK;
+}
+
+// Fast lane of the last launch, carved out of the main kernel's grid (see sphere_tmem2_kernel): marks the pairs of the
+// `fast_units` longest units for the lane, resets the election state and fills the lane fields of P.
+static int prepare_lane_in_kernel(riptrm_handle* h, SphereParams& P, cudaStream_t st) {
+    int fast_units = 16;   // 32 pairs: 8 lane CTAs x 4 warps
+    if (const char* e = getenv("RIPTRM_FAST_UNITS")) fast_units = std::max(1, std::min(64, atoi(e)));   // tuning knob
+    fast_units = std::min(fast_units, h->batch / 2);
+    if (h->d_fast_order == nullptr) CUDA_TRY(cudaMalloc(&h->d_fast_order, 2 * 64 * sizeof(int)));
+    int rc0;
+    if ((rc0 = ensure_lane_buffers(h, st))) return rc0;
+    mark_fast_lane_kernel<<<(fast_units + 31) / 32, 32, 0, st>>>(h->d_order, fast_units, h->d_pause, h->d_fast_order);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemsetAsync(h->d_counter + 1, 0, sizeof(int), st));
+    P.lane_ctas = (2 * fast_units + 3) / 4;
+    P.fast_len = 2 * fast_units;
+    P.fast_order = h->d_fast_order;
+    P.lane_state = h->d_lane_state;
+    P.lane_debug = h->d_lane_state + 2 + 2 * kLaneMaxSms;
+    P.lane_times = h->d_lane_times;
+    h->launches += 1;
+    return RIPTRM_OK;
+}
+
+// (legacy form, RIPTRM_FAST_LANE_LEGACY=1: a second kernel on a priority stream, placed by timing)
 static int launch_fast_lane(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
     int fast_units = 16;   // 32 pairs: 8 CTAs of the 4-warp kernel on 8 SMs of their own
     if (const char* e = getenv("RIPTRM_FAST_UNITS")) fast_units = std::max(1, std::min(64, atoi(e)));   // tuning knob
@@ -1360,6 +1505,8 @@ static int launch_fast_lane(riptrm_handle* h, const SphereParams& P, const DevOp
     F.sibling_units = 0;
     F.order = h->d_fast_order;
     F.queue_len = 2 * fast_units;
+    F.lane_debug = (h->d_lane_state != nullptr) ? h->d_lane_state + 2 + 2 * kLaneMaxSms + h->num_sms * 2 : nullptr;
+    F.lane_times = (h->d_lane_times != nullptr) ? h->d_lane_times + 2 * (h->num_sms * 2) : nullptr;
     // 150 KB of shared memory per CTA: no CTA of the main kernel (86 KB) fits next to it
     const size_t smem = 150 * 1024;
     auto kern = sphere_tmem_kernel<0>;
@@ -1448,10 +1595,27 @@ static int solve_scheduled(riptrm_handle* h, SphereParams P, const DevOpts& o, c
         P.pause_at = (phase < nsplit) ? splits[phase] : -1;
         const bool lane = P.sibling_units && user == 0 && phase == nsplit && nsplit >= 1 && splits[nsplit - 1] * 3 >= maxiter * 2 - 2 &&
                           getenv("RIPTRM_SPHERE_NO_FAST_LANE") == nullptr;   // needs the ranking of outer iteration ~ 2/3 maxiter
-        if (lane && (rc = launch_fast_lane(h, P, o, st))) break;
+        // two forms of the lane: a second kernel on a priority stream (default: its one-warp-per-copy
+        // code at 254 registers is 2-4 % faster end to end) or CTAs elected inside the main kernel (RIPTRM_FAST_LANE_IN_KERNEL=1)
+        const bool legacy_lane = getenv("RIPTRM_FAST_LANE_IN_KERNEL") == nullptr;
+        if (getenv("RIPTRM_DEBUG_LANE") != nullptr)
+            fprintf(stderr, "[riptrm] phase %d/%d lane %d sibling %d user %d last split %d maxiter %d\n", phase, nsplit, (int)lane,
+                    P.sibling_units, user, nsplit ? splits[nsplit - 1] : -1, maxiter);
+        const bool in_kernel = lane && !legacy_lane && lane_in_kernel_possible(h);
+        P.lane_ctas = 0;
+        if (in_kernel && (rc = prepare_lane_in_kernel(h, P, st))) break;
+        if (lane && !in_kernel) {
+            if ((rc = ensure_lane_buffers(h, st))) break;
+            if ((rc = launch_fast_lane(h, P, o, st))) break;
+            P.lane_debug = h->d_lane_state + 2 + 2 * kLaneMaxSms;
+            P.lane_times = h->d_lane_times;
+        }
         if ((rc = dispatch_sphere<0>(h, P, o, st))) break;
-        if (lane && cudaStreamWaitEvent(st, h->lane_ev1, 0) != cudaSuccess) { rc = fail(RIPTRM_E_CUDA, "fast lane join failed"); break; }
-        if (lane) cudaEventRecord(h->ev1, st);   // the reported time ends when both kernels have
+        P.lane_ctas = 0;
+        P.lane_debug = nullptr;
+        P.lane_times = nullptr;
+        if (lane && !in_kernel && cudaStreamWaitEvent(st, h->lane_ev1, 0) != cudaSuccess) { rc = fail(RIPTRM_E_CUDA, "fast lane join failed"); break; }
+        if (lane && !in_kernel) cudaEventRecord(h->ev1, st);   // the reported time ends when both kernels have
         if (phase == 0) {   // keep the start of the first launch: the reported time spans all
             std::swap(first_start, h->ev0);
             swapped = true;
@@ -1737,6 +1901,18 @@ extern "C" int riptrm_newton(riptrm_handle* h, const double* x, const double* z,
 extern "C" int riptrm_trs(riptrm_handle* h, const double* x, const double* y, double mu, double Delta, double* dx,
                           double* info, int where, void* stream) {
     return run_hook(h, 3, x, y, mu, Delta, nullptr, dx, info, where, (cudaStream_t)stream);
+}
+
+// Placement record of the last solve's fast lane (sphere_tmem2_kernel): out[i] = (smid << 4) | role for CTA i, role 1 main,
+// 2 lane, 3 stepped aside; returns the number of records (0: the last solve had no in-kernel lane)
+extern "C" int riptrm_lane_placement(riptrm_handle* h, int* out, unsigned long long* times, int capacity) {
+    if (h == nullptr || out == nullptr || h->d_lane_state == nullptr) return 0;
+    const int n = std::min(capacity, h->lane_debug_len);
+    if (cudaMemcpy(out, h->d_lane_state + 2 + 2 * kLaneMaxSms, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (times != nullptr && h->d_lane_times != nullptr &&
+        cudaMemcpy(times, h->d_lane_times, (size_t)2 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -1;
+    return n;
 }
 
 extern "C" int64_t riptrm_launch_count(const riptrm_handle* h) { return h ? h->launches : 0; }
