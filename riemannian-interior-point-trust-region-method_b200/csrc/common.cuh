@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace riptrm {
 
@@ -230,6 +231,83 @@ __device__ __forceinline__ double lds_f64_off(uint32_t a) {
 template <int OFF>
 __device__ __forceinline__ void sts_f64_off(uint32_t a, double v) {
     asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "d"(v) : "memory");
+}
+
+// 128-bit forms
+template <int OFF>
+__device__ __forceinline__ double2 lds_v2f64_off(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(a), "n"(OFF) : "memory");
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts_v2f64_off(uint32_t a, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "d"(x), "d"(y) : "memory");
+}
+
+// compile-time loop: f(std::integral_constant<int, I>) for I = 0 .. N-1 (indices usable as template arguments / immediates)
+template <int I, int N, class Fn>
+__device__ __forceinline__ void static_for(Fn&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+// a value the compiler must keep (or spill) instead of recomputing it from %tid at every use
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t x) {
+    asm volatile("" : "+r"(x));
+    return x;
+}
+
+// Warp sums of NV (4 or 6) values THROUGH SHARED MEMORY, same summation tree -- hence the same bits -- as wsum() of each value
+// (pairing (l, l^16), (l, l^8), (l, l^4), (l, l^2), (l, l^1)), in ~30 instructions instead of the ~65 (SHFL + FSEL + moves) of
+// wsum8x / ~50 of wsum4x: every lane stores its NV partials (NV/2 STS.128), lane 4v + g then adds the eight partials of value v
+// held by the lanes {g + 4k} in the tree's order (the xor-16, xor-8, xor-4 levels: 8 LDS.64, 7 DADD), two butterfly steps over
+// g finish the tree, and the totals go back through shared memory (one STS.64, NV/2 broadcast LDS.128).  The whole-solve
+// Sphere kernels are bound by issue slots, not by shared-memory bandwidth.
+// Scratch: kRedDoubles doubles per warp, 16-byte aligned: three rows (one per value pair) of 36 double2 -- 32 lanes' partials,
+// then the pair's totals -- which puts the rows 16 banks apart (two wavefronts per LDS.64, the minimum for 24 lanes x 8 bytes).
+// The three addresses are per-thread constants the caller computes once (`WarpScratch`).
+constexpr int kRedRow = 36 * 16;                   // bytes per row
+constexpr int kRedTotOff = 32 * 16;                // byte offset of a row's totals
+constexpr int kRedDoubles = 3 * kRedRow / 8;       // 216
+struct WarpScratch {
+    uint32_t wb;   // shared-space address of the warp's scratch: [0, 512) broadcast operand of S.v, then the reduction rows
+    uint32_t wl;   // wb + 16 * lane
+    uint32_t rd;   // wb + 512 + row(v) + 8 * (v & 1) + 16 * g with v = min(lane / 4, 5), g = lane % 4: this lane's tree reads
+    __device__ __forceinline__ void init(const void* base) {
+        const int lane = lane_id();
+        const int vv = min(lane >> 2, 5), g = lane & 3;
+        const uint32_t b = smem_u32(base);
+        wb = opaque_u32(b);
+        wl = opaque_u32(b + 16u * lane);
+        rd = opaque_u32(b + 512u + (uint32_t)((vv >> 1) * kRedRow + (vv & 1) * 8 + g * 16));
+    }
+};
+constexpr int kWarpScratchDoubles = 64 + kRedDoubles;   // 280
+template <int NV>
+__device__ __forceinline__ void wsum_smem(double (&v)[NV], const WarpScratch& ws) {
+    static_assert(NV == 4 || NV == 6, "wsum_smem: 4 or 6 values");
+    sts_v2f64_off<512>(ws.wl, v[0], v[1]);
+    sts_v2f64_off<512 + kRedRow>(ws.wl, v[2], v[3]);
+    if (NV == 6) sts_v2f64_off<512 + 2 * kRedRow>(ws.wl, v[4], v[5]);
+    __syncwarp();
+    const uint32_t rd = ws.rd;   // with NV = 4 the lanes of values 4, 5 add up stale data nobody reads
+    const double p0 = lds_f64_off<0>(rd), p1 = lds_f64_off<64>(rd), p2 = lds_f64_off<128>(rd), p3 = lds_f64_off<192>(rd);
+    const double p4 = lds_f64_off<256>(rd), p5 = lds_f64_off<320>(rd), p6 = lds_f64_off<384>(rd), p7 = lds_f64_off<448>(rd);
+    const double a0 = p0 + p4, a1 = p1 + p5, a2 = p2 + p6, a3 = p3 + p7;   // lanes i, i ^ 16
+    const double b0 = a0 + a2, b1 = a1 + a3;                               // i, i ^ 8
+    double c = b0 + b1;                                                    // i, i ^ 4
+    c = c + __shfl_xor_sync(kFull, c, 2);
+    c = c + __shfl_xor_sync(kFull, c, 1);
+    if ((lane_id() & 3) == 0) sts_f64_off<kRedTotOff>(rd, c);
+    __syncwarp();
+    const double2 t0 = lds_v2f64_off<512 + kRedTotOff>(ws.wb), t1 = lds_v2f64_off<512 + kRedRow + kRedTotOff>(ws.wb);
+    v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
+    if (NV == 6) {
+        const double2 t2 = lds_v2f64_off<512 + 2 * kRedRow + kRedTotOff>(ws.wb);
+        v[4] = t2.x; v[5] = t2.y;
+    }
 }
 
 __device__ __forceinline__ uint64_t global_timer_ns() {

@@ -24,7 +24,10 @@ namespace riptrm {
 // consecutive 32-bit TMEM columns of the warp's own TMEM lane l, fetched with tcgen05.ld.32x32b (SASS LDTM).  With
 // every SM full, S.v from shared memory costs ~1890 cycles (the shared-memory pipe is the bottleneck: 83 % busy),
 // from TMEM ~630 (scripts/tmem_test.cu); the values and their order are the same, so results stay bit-identical.
-template <int K_, int NFIX = 0, bool TM = false, int TCH = 64>
+// RS = true takes the two merged reductions of a tCG iteration through shared memory (wsum_smem: same trees, fewer
+// instructions); Ctx::ws then holds the addresses of kWarpScratchDoubles doubles of this warp
+// (the broadcast operand of S.v moves there too).
+template <int K_, int NFIX = 0, bool TM = false, int TCH = 64, bool RS = false>
 struct SphereFam {
     static_assert(!TM || (NFIX == 50 && K_ == 2), "the TMEM layout is built for n = 50");
     static constexpr int K = K_;
@@ -40,6 +43,7 @@ struct SphereFam {
         double eps;
         bool embedded;    // 'is_euclidean_embedded'
         uint32_t taddr;   // TM: TMEM address of this warp's copy of S (lane field = 32 * (warp % 4))
+        WarpScratch ws;   // RS: shared-space addresses of the warp scratch (kWarpScratchDoubles doubles, 16-byte aligned)
     };
     struct Pt {
         Vec x;
@@ -82,10 +86,42 @@ struct SphereFam {
 
     static __device__ __forceinline__ Vec matvec_tmem(const Ctx& c, const Vec& v) {
         const int lane = lane_id();
-        reinterpret_cast<double2*>(c.vbuf)[lane] = make_double2(v.v[0], v.v[1]);
+        if (TCH == 16) sts_v2f64_off<0>(c.ws.wl, v.v[0], v.v[1]);
+        else reinterpret_cast<double2*>(c.vbuf)[lane] = make_double2(v.v[0], v.v[1]);
         __syncwarp();
         double a0x = 0.0, a0y = 0.0, a1x = 0.0, a1y = 0.0;
-        if (TCH == 32) {
+        if (TCH == 16) {
+            // 16-column chunks (the 128-register kernel: a chunk's S registers are half as many again; same order of
+            // additions), operand broadcast through the warp scratch with explicit shared-space addresses
+            static_for<0, 12>([&](auto chc) {
+                constexpr int ch = decltype(chc)::value;
+                uint32_t r[16];
+                tmem::tmem_ld_x16(c.taddr + 16 * ch, r);
+                tmem::wait_ld();
+                const double2 v0 = lds_v2f64_off<32 * ch>(c.ws.wb), v1 = lds_v2f64_off<32 * ch + 16>(c.ws.wb);
+                a0x = fma(__hiloint2double((int)r[1], (int)r[0]), v0.x, a0x);
+                a0y = fma(__hiloint2double((int)r[3], (int)r[2]), v0.x, a0y);
+                a1x = fma(__hiloint2double((int)r[5], (int)r[4]), v0.y, a1x);
+                a1y = fma(__hiloint2double((int)r[7], (int)r[6]), v0.y, a1y);
+                a0x = fma(__hiloint2double((int)r[9], (int)r[8]), v1.x, a0x);
+                a0y = fma(__hiloint2double((int)r[11], (int)r[10]), v1.x, a0y);
+                a1x = fma(__hiloint2double((int)r[13], (int)r[12]), v1.y, a1x);
+                a1y = fma(__hiloint2double((int)r[15], (int)r[14]), v1.y, a1y);
+            });
+            uint32_t r[8];
+            tmem::tmem_ld_x8(c.taddr + 192, r);
+            tmem::wait_ld();
+            const double2 vj = lds_v2f64_off<8 * 48>(c.ws.wb);
+            a0x = fma(__hiloint2double((int)r[1], (int)r[0]), vj.x, a0x);
+            a0y = fma(__hiloint2double((int)r[3], (int)r[2]), vj.x, a0y);
+            a1x = fma(__hiloint2double((int)r[5], (int)r[4]), vj.y, a1x);
+            a1y = fma(__hiloint2double((int)r[7], (int)r[6]), vj.y, a1y);
+            __syncwarp();
+            Vec out;
+            out.v[0] = active(c, 0) ? (a0x + a1x) : 0.0;
+            out.v[1] = active(c, 1) ? (a0y + a1y) : 0.0;
+            return out;
+        } else if (TCH == 32) {
             // 32-column chunks for the 128-register kernel (same order of additions)
 #pragma unroll
             for (int ch = 0; ch < 6; ++ch) {
@@ -309,10 +345,18 @@ struct SphereFam {
             Vec tmp;
 #pragma unroll
             for (int k = 0; k < K; ++k) tmp.v[k] = st.ys.v[k] * delta.v[k];
-            double s6[8] = {wdot_partial(pt.x, Sv), wdot_partial(pt.x, delta), wdot_partial(wv, delta),
-                            wdot_partial(delta, Sv), wdot_partial(delta, delta), wdot_partial(delta, tmp), 0.0, 0.0};
-            wsum8x<6>(s6);
-            const double a = s6[0], b = s6[1], g1 = s6[2], h1 = s6[3], h2 = s6[4], h3 = s6[5];
+            double a, b, g1, h1, h2, h3;
+            if (RS) {
+                double s6[6] = {wdot_partial(pt.x, Sv), wdot_partial(pt.x, delta), wdot_partial(wv, delta),
+                                wdot_partial(delta, Sv), wdot_partial(delta, delta), wdot_partial(delta, tmp)};
+                wsum_smem<6>(s6, ctx.ws);
+                a = s6[0], b = s6[1], g1 = s6[2], h1 = s6[3], h2 = s6[4], h3 = s6[5];
+            } else {
+                double s6[8] = {wdot_partial(pt.x, Sv), wdot_partial(pt.x, delta), wdot_partial(wv, delta),
+                                wdot_partial(delta, Sv), wdot_partial(delta, delta), wdot_partial(delta, tmp), 0.0, 0.0};
+                wsum8x<6>(s6);
+                a = s6[0], b = s6[1], g1 = s6[2], h1 = s6[3], h2 = s6[4], h3 = s6[5];
+            }
             const double d = ctx.embedded ? g1 : (g1 - b * q);
             Vec Hd;
 #pragma unroll
@@ -342,16 +386,16 @@ struct SphereFam {
                 break;
             }
             e_Pe = e_Pe_new;                                   // :149
-            Vec new_eta, new_Heta, r_new;
+            Vec new_eta, new_Heta;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 new_eta.v[k] = eta.v[k] + alpha * delta.v[k];  // :150
                 new_Heta.v[k] = Heta.v[k] + alpha * Hd.v[k];   // :154
-                r_new.v[k] = r.v[k] + alpha * Hd.v[k];         // :172
+                r.v[k] = r.v[k] + alpha * Hd.v[k];             // :172 (in place: r is not read after the :163 exit)
             }
-            double s4[4] = {wdot_partial(new_eta, st.c), wdot_partial(new_eta, new_Heta), wdot_partial(r_new, r_new),
-                            wdot_partial(pt.x, r_new)};
-            wsum4x(s4);
+            double s4[4] = {wdot_partial(new_eta, st.c), wdot_partial(new_eta, new_Heta), wdot_partial(r, r),
+                            wdot_partial(pt.x, r)};
+            if (RS) wsum_smem<4>(s4, ctx.ws); else wsum4x(s4);
             const double new_model = s4[0] + 0.5 * s4[1];      // :86-87, :162
             if (new_model >= model_value) {                    // :163
                 res.stop = RIPTRM_TCG_MODEL_INCREASED;
@@ -360,7 +404,6 @@ struct SphereFam {
             }
             eta = new_eta;                                     // :167-169
             Heta = new_Heta;
-            r = r_new;
             model_value = new_model;
             r_r = s4[2];                                       // :175
             // ||r|| <= target tested on squares: no square root on the critical path

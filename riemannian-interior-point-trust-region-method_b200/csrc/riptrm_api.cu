@@ -521,6 +521,9 @@ static int stiefel_launch(riptrm_handle* h, col::Params& prm, cudaStream_t st) {
 
 template <int MODE>
 static int columns_dispatch(riptrm_handle* h, col::Params& prm, cudaStream_t st) {
+#ifdef RIPTRM_DEV_SPHERE_ONLY   // diagnostic builds (seconds instead of minutes): only the n = 50 TMEM kernels
+    return fail(RIPTRM_E_UNSUPPORTED, "RIPTRM_DEV_SPHERE_ONLY build");
+#else
     if (is_stiefel(h)) {
         if (MODE == 3) return fail(RIPTRM_E_UNSUPPORTED, "stream-only diagnostic: COLUMNS family only");
         constexpr int M = (MODE == 3) ? 2 : MODE;
@@ -540,6 +543,7 @@ static int columns_dispatch(riptrm_handle* h, col::Params& prm, cudaStream_t st)
         case 16: return columns_launch<16, MODE>(h, prm, st);
     }
     return fail(RIPTRM_E_UNSUPPORTED, "unsupported column count");
+#endif
 }
 
 // copies a caller array [n][p] (host or device) into the padded device layout [n_pad][P]
@@ -656,6 +660,9 @@ static int stiefel_launch_post(riptrm_handle* h, col::Params& prm, cudaStream_t 
 }
 template <bool INIT>
 static int columns_dispatch_post(riptrm_handle* h, col::Params& prm, cudaStream_t st) {
+#ifdef RIPTRM_DEV_SPHERE_ONLY   // diagnostic builds (seconds instead of minutes): only the n = 50 TMEM kernels
+    return fail(RIPTRM_E_UNSUPPORTED, "RIPTRM_DEV_SPHERE_ONLY build");
+#else
     if (is_stiefel(h)) {
         switch (h->colP) {
             case 4: return stiefel_launch_post<4, INIT>(h, prm, st);
@@ -673,6 +680,7 @@ static int columns_dispatch_post(riptrm_handle* h, col::Params& prm, cudaStream_
         case 16: return columns_launch_post<16, INIT>(h, prm, st);
     }
     return fail(RIPTRM_E_UNSUPPORTED, "unsupported column count");
+#endif
 }
 
 // riptrm_solve on the COLUMNS family: p independent RIPTRM runs sharing S, advanced in lock-step.  The host only
@@ -996,9 +1004,16 @@ __global__ void __launch_bounds__(128, 2) sphere_tmem_kernel(SphereParams P, Dev
 // 0..3 -- one per scheduler, the residency at which a tCG iteration takes 1.0 us instead of 2.4 -- solve the pairs of the
 // longest units (`fast_order`), its warps 4..7 have nothing to do.  `lane_debug` records (smid, role) per CTA for the test.
 
+#ifndef RIPTRM_RS2
+#define RIPTRM_RS2 1     // the two reductions of a tCG iteration through shared memory (wsum_smem) instead of shuffles
+#endif
+#ifndef RIPTRM_TCH2
+#define RIPTRM_TCH2 16   // TMEM columns per chunk of S in S.v (16 / 32; same order of additions).  16: the chunk's registers no
+                         // longer force ptxas to shuffle S data around (83 -> 39 register moves per tCG iteration)
+#endif
 template <int MODE>
 __global__ void __launch_bounds__(256, 2) sphere_tmem2_kernel(SphereParams P, DevOpts o, int* counter) {
-    using F = SphereFam<2, 50, true, 32>;
+    using F = SphereFam<2, 50, true, RIPTRM_TCH2, RIPTRM_RS2 != 0>;
     constexpr int K = 2;
     extern __shared__ __align__(16) double smem[];
     __shared__ uint32_t tmem_base;
@@ -1054,7 +1069,8 @@ __global__ void __launch_bounds__(256, 2) sphere_tmem2_kernel(SphereParams P, De
     tmem::fence_after_sync();
     typename F::Ctx ctx;
     ctx.S = stage;                    // staging copy of the sub-partition; S.v reads the TMEM copy
-    ctx.vbuf = smem + (size_t)4 * (n * ns + pad) + (size_t)warp * 64;
+    ctx.vbuf = smem + (size_t)4 * (n * ns + pad) + (size_t)warp * kWarpScratchDoubles;
+    ctx.ws.init(ctx.vbuf);
     ctx.n = n;
     ctx.ns = ns;
     ctx.eps = P.eps;
@@ -1134,7 +1150,7 @@ __global__ void __launch_bounds__(256, 2) sphere_tmem2_kernel(SphereParams P, De
 }
 
 static int launch_sphere_tmem2(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
-    const size_t smem = ((size_t)4 * (50 * 50 + 64) + 8 * 64) * sizeof(double);
+    const size_t smem = ((size_t)4 * (50 * 50 + 64) + 8 * kWarpScratchDoubles) * sizeof(double);
     auto kern = sphere_tmem2_kernel<0>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1248,9 +1264,13 @@ static bool sibling_units(const riptrm_handle* h) {
 // TRS_solver='Exact_RepMat': one warp per CTA with the representation-matrix workspace in shared memory, one launch
 template <int MODE>
 static int dispatch_sphere_exact(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
+#ifdef RIPTRM_DEV_SPHERE_ONLY   // diagnostic builds (seconds instead of minutes): only the n = 50 TMEM kernels
+    return fail(RIPTRM_E_UNSUPPORTED, "RIPTRM_DEV_SPHERE_ONLY build");
+#else
     if (h->n == 50) return launch_sphere<2, MODE, 50, true>(h, P, o, st);
     if (h->n <= 64) return launch_sphere<2, MODE, 0, true>(h, P, o, st);
     return fail(RIPTRM_E_UNSUPPORTED, "Exact_RepMat on Sphere(n): n <= 64");
+#endif
 }
 
 template <int MODE>
@@ -1259,9 +1279,13 @@ static int dispatch_sphere(riptrm_handle* h, const SphereParams& P, const DevOpt
     const bool no_tmem = getenv("RIPTRM_SPHERE_NO_TMEM") != nullptr;  // A/B switch (measurements, tests)
     if (MODE == 0 && P.sibling_units) return launch_sphere_tmem2(h, P, o, st);
     if (n == 50 && !no_tmem) return launch_sphere_tmem<MODE>(h, P, o, st);      // the reference's dim, S in TMEM
+#ifdef RIPTRM_DEV_SPHERE_ONLY
+    return fail(RIPTRM_E_UNSUPPORTED, "RIPTRM_DEV_SPHERE_ONLY build");
+#else
     if (n == 50) return launch_sphere<2, MODE, 50>(h, P, o, st);  // the reference's dim (config_dataset.yaml:6)
     if (n <= 64) return launch_sphere<2, MODE, 0>(h, P, o, st);
     return launch_sphere<4, MODE, 0>(h, P, o, st);
+#endif
 }
 
 static int finish_timing(riptrm_handle* h, bool sync) {
@@ -1404,6 +1428,9 @@ static int launch_small(riptrm_handle* h, const SmallParams& P, const DevOpts& o
 }
 
 static int dispatch_small(riptrm_handle* h, int mode, const SmallParams& P, const DevOpts& o, cudaStream_t st) {
+#ifdef RIPTRM_DEV_SPHERE_ONLY   // diagnostic builds (seconds instead of minutes): only the n = 50 TMEM kernels
+    return fail(RIPTRM_E_UNSUPPORTED, "RIPTRM_DEV_SPHERE_ONLY build");
+#else
     if (mode == 3 || mode == 4 || (mode == 0 && exact_repmat(h))) {   // exact trust-region solver (hook / whole solve), Newton hook
         if (h->family == RIPTRM_FAMILY_ROSENBROCK_GRASSMANN)
             return mode == 3 ? launch_small<GrassmannFam, 3, true>(h, P, o, st)
@@ -1424,6 +1451,7 @@ static int dispatch_small(riptrm_handle* h, int mode, const SmallParams& P, cons
         return launch_small<StableIdFam, 2>(h, P, o, st);
     }
     return fail(RIPTRM_E_UNSUPPORTED, "family not built into this library");
+#endif
 }
 
 static SmallParams small_params(const riptrm_handle* h) {
