@@ -226,8 +226,10 @@ int riptrm_set_options(riptrm_handle* h, const riptrm_options* opts);
  * trace [batch][trace_capacity][RIPTRM_TRACE_FIELDS].  `stream` is a cudaStream_t (or NULL).
  * With `where` == RIPTRM_HOST the call returns after the results are in the host buffers;
  * with RIPTRM_DEVICE the batched families (1-3) only enqueue work on `stream`.  The COLUMNS / STIEFEL families (4, 5) are
- * sequenced by the host -- one tCG launch and one post launch per trust-region iteration, with a one-int device-to-host poll
- * of the "all done" flag in between -- so their solve returns when the solve has finished, in either mode. */
+ * sequenced by the host -- one tCG launch and one post launch per trust-region iteration, enqueued four iterations ahead of
+ * the one-int "all done" flag the host polls, so the stream never runs dry; launches behind the last iteration return at
+ * once on the device -- so their solve returns when the solve has finished, in either mode ('maxtime' is tested against
+ * the host clock at enqueue time, i.e. up to four iterations late). */
 int riptrm_solve(riptrm_handle* h, const double* x0, const double* y0, double* x, double* y,
                  double* summary, double* trace, int where, void* stream);
 

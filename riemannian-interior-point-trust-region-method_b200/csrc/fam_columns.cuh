@@ -455,6 +455,9 @@ struct ColState {
 // ------------------------------------------------------------------------------------------------------
 template <int P, int MODE>
 __global__ void __launch_bounds__(NT, 1) columns_kernel(Params prm) {
+    // whole-solve mode: the host enqueues a few trust-region iterations ahead of the "all done" flag it polls; the launches
+    // behind the last iteration find the flag set and return (uniform over the grid: written by the previous launch)
+    if (prm.solve && *reinterpret_cast<const volatile int*>(prm.all_done) != 0) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<P>& sm = *reinterpret_cast<Smem<P>*>(smem_raw);
     __shared__ ColState cs[P];
@@ -1023,6 +1026,7 @@ struct PostState {  // per column, identical in every CTA
 
 template <int P, bool INIT>
 __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
+    if (!INIT && *reinterpret_cast<const volatile int*>(prm.all_done) != 0) return;   // enqueued ahead of the flag (see columns_kernel)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<P>& sm = *reinterpret_cast<Smem<P>*>(smem_raw);
     __shared__ PostState ps[P];

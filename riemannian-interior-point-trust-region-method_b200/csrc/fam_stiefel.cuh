@@ -107,6 +107,7 @@ struct TcgState {
 // ------------------------------------------------------------------------------------------------------
 template <int P, int MODE>
 __global__ void __launch_bounds__(NT, 1) stiefel_kernel(Params prm) {
+    if (prm.solve && *reinterpret_cast<const volatile int*>(prm.all_done) != 0) return;   // enqueued ahead of the flag (columns_kernel)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<P>& sm = *reinterpret_cast<Smem<P>*>(smem_raw);
     __shared__ TcgState ts;
@@ -493,6 +494,7 @@ struct PostState {
 
 template <int P, bool INIT>
 __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
+    if (!INIT && *reinterpret_cast<const volatile int*>(prm.all_done) != 0) return;   // enqueued ahead of the flag (columns_kernel)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<P>& sm = *reinterpret_cast<Smem<P>*>(smem_raw);
     __shared__ PostState ps;

@@ -91,6 +91,10 @@ struct riptrm_handle {
     int colP = 0, n_pad = 0, ld = 0, col_slots = 0, col_R = 0, col_grid = 0;
     unsigned long long last_passes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // COLUMNS / STIEFEL whole solves: the host runs kColLookahead trust-region iterations ahead of the flag it polls
+    int* h_done = nullptr;               // pinned, kColLookahead ints
+    cudaEvent_t done_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool no_launch_events = false;       // inside a whole solve: the launches do not record ev0 / ev1 (the solve does)
     int64_t launches = 0;
     double last_ms = 0.0;
 };
@@ -369,6 +373,10 @@ static void free_any(T*& p) {
 }
 
 extern "C" int riptrm_destroy(riptrm_handle* h) {
+    if (h != nullptr) {
+        if (h->h_done != nullptr) cudaFreeHost(h->h_done);
+        for (auto& e : h->done_ev) if (e != nullptr) cudaEventDestroy(e);
+    }
     if (h == nullptr) return RIPTRM_OK;
     cudaSetDevice(h->device);
     if (h->ownZ) free_dev(h->dZ);
@@ -496,9 +504,9 @@ static int columns_launch(riptrm_handle* h, col::Params& prm, cudaStream_t st) {
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, col::NT, smem));
     if (per_sm < 1) return fail(RIPTRM_E_UNSUPPORTED, "columns kernel does not fit on an SM");
     void* args[] = {&prm};
-    CUDA_TRY(cudaEventRecord(h->ev0, st));
+    if (!h->no_launch_events) CUDA_TRY(cudaEventRecord(h->ev0, st));
     CUDA_TRY(cudaLaunchCooperativeKernel((void*)kern, dim3(h->col_grid), dim3(col::NT), args, smem, st));
-    CUDA_TRY(cudaEventRecord(h->ev1, st));
+    if (!h->no_launch_events) CUDA_TRY(cudaEventRecord(h->ev1, st));
     h->launches += 1;
     return RIPTRM_OK;
 }
@@ -512,9 +520,9 @@ static int stiefel_launch(riptrm_handle* h, col::Params& prm, cudaStream_t st) {
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, col::NT, smem));
     if (per_sm < 1) return fail(RIPTRM_E_UNSUPPORTED, "stiefel kernel does not fit on an SM");
     void* args[] = {&prm};
-    CUDA_TRY(cudaEventRecord(h->ev0, st));
+    if (!h->no_launch_events) CUDA_TRY(cudaEventRecord(h->ev0, st));
     CUDA_TRY(cudaLaunchCooperativeKernel((void*)kern, dim3(h->col_grid), dim3(col::NT), args, smem, st));
-    CUDA_TRY(cudaEventRecord(h->ev1, st));
+    if (!h->no_launch_events) CUDA_TRY(cudaEventRecord(h->ev1, st));
     h->launches += 1;
     return RIPTRM_OK;
 }
@@ -732,26 +740,32 @@ static int columns_solve(riptrm_handle* h, const double* x0, const double* y0, d
     prm.now_s = seconds_since_start();
     if ((rc = columns_dispatch_post<true>(h, prm, st))) return rc;
     const long long max_rounds = (long long)(o.maxiter + 1) * (o.inner_maxiter > 0 ? o.inner_maxiter : 100000);
-    for (long long round = 0; round < max_rounds; ++round) {
-        int done = 0;
-        CUDA_TRY(cudaMemcpyAsync(&done, q.all_done, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        if (done) break;
-        cudaEvent_t keep0 = h->ev0, keep1 = h->ev1;  // columns_dispatch records its own events: keep the solve's start
-        cudaEvent_t t0, t1;
-        CUDA_TRY(cudaEventCreate(&t0));
-        CUDA_TRY(cudaEventCreate(&t1));
-        h->ev0 = t0;
-        h->ev1 = t1;
-        rc = columns_dispatch<2>(h, prm, st);
-        h->ev0 = keep0;
-        h->ev1 = keep1;
-        cudaEventDestroy(t0);
-        cudaEventDestroy(t1);
-        if (rc) return rc;
-        prm.now_s = seconds_since_start();   // as of the last poll: the limits are tested one trust-region iteration late at most
-        if ((rc = columns_dispatch_post<false>(h, prm, st))) return rc;
+    // The host sequences the launches (one tCG launch and one post launch per trust-region iteration) kColLookahead
+    // iterations AHEAD of the "all done" flag: after every iteration the flag is copied to a pinned slot and an event is
+    // recorded; before enqueuing iteration r the host waits for the flag of iteration r - kColLookahead only, so the stream
+    // never runs dry (round 1 synchronised on every iteration: 4-14 % of a config-4 solve).  The few launches enqueued
+    // behind the last iteration see the flag on the device and return at once.
+    constexpr int kColLookahead = 4;
+    if (h->h_done == nullptr) {
+        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h->h_done), kColLookahead * sizeof(int), cudaHostAllocDefault));
+        for (int i = 0; i < kColLookahead; ++i) CUDA_TRY(cudaEventCreateWithFlags(&h->done_ev[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < kColLookahead; ++i) h->h_done[i] = 0;
+    h->no_launch_events = true;
+    for (long long round = 0; round < max_rounds; ++round) {
+        const int slot = (int)(round % kColLookahead);
+        if (round >= kColLookahead) {
+            if (cudaEventSynchronize(h->done_ev[slot]) != cudaSuccess) { rc = fail(RIPTRM_E_CUDA, "columns solve: flag poll failed"); break; }
+            if (h->h_done[slot]) break;
+        }
+        prm.now_s = seconds_since_start();   // as of enqueue time: the time limits are tested a few iterations late at most
+        if ((rc = columns_dispatch<2>(h, prm, st))) break;
+        if ((rc = columns_dispatch_post<false>(h, prm, st))) break;
+        if (cudaMemcpyAsync(&h->h_done[slot], q.all_done, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaEventRecord(h->done_ev[slot], st) != cudaSuccess) { rc = fail(RIPTRM_E_CUDA, "columns solve: flag copy failed"); break; }
+    }
+    h->no_launch_events = false;
+    if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev1, st));
     if (x != nullptr && (rc = columns_export(h, x, prm.X, where, st))) return rc;
     if (y != nullptr && (rc = columns_export(h, y, prm.Y, where, st))) return rc;
