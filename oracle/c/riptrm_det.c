@@ -260,6 +260,80 @@ static TcgResult tcg(const Ctx* c, const det_options* o, const Pt* pt, const Ste
     double inv_zr = 1.0 / z_r;
     for (int e = 0; e < N; ++e) wv[e] = pt->x[e] * st->ys[e];
     const double q = vdot(c, wv, pt->x);
+#ifdef RIPTRM_TCG_FMA
+    /* EXPERIMENT (round 2, not adopted): the same loop with the axpy / update lines written as fused multiply-adds, which
+     * would remove ~29 of the ~225 FP64 instructions of a tCG iteration on the GPU.  Measured against the reference's golden
+     * run (scripts/parity_report.py --engine c with this switch): the discrete trace leaves at outer iteration 19 instead of
+     * 20, the KKT residual agrees to 3.5e-8 / 2.6e-3 instead of 9.5e-9 / 9.5e-7 over outer iterations 1-9 / 10-19 -- the
+     * parity windows SHRINK, so the kernels keep the unfused form. */
+    for (; j < maxinner; ++j) {
+        matvec(c, delta, Sv);
+        const double a = vdot(c, pt->x, Sv), b = vdot(c, pt->x, delta), g1 = vdot(c, wv, delta);
+        const double h1 = vdot(c, delta, Sv), h2 = vdot(c, delta, delta);
+        for (int e = 0; e < N; ++e) tmp[e] = st->ys[e] * delta[e];
+        const double h3 = vdot(c, delta, tmp);
+        const double d = c->embedded ? g1 : fma(-b, q, g1);
+        for (int e = 0; e < N; ++e) {
+            const double ga = c->embedded ? delta[e] : fma(-pt->x[e], b, delta[e]);
+            const double t = st->ys[e] * ga;
+            const double hl = fma(st->kappa, delta[e], fma(a, pt->x[e], -Sv[e]));
+            const double g = fma(-d, pt->x[e], t);
+            Hd[e] = hl + g;
+        }
+        const double dt = c->embedded ? h3 : fma(-b, g1, h3);
+        const double d_Hd = fma(-d, b, fma(st->kappa, h2, fma(a, b, -h1)) + dt);
+        double alpha = 0.0, e_Pe_new = e_Pe;
+        if (d_Hd != 0.0) {
+            alpha = z_r / d_Hd;
+            e_Pe_new = fma(alpha * alpha, d_Pd, fma(2.0 * alpha, e_Pd, e_Pe));
+        }
+        if (d_Hd <= 0.0 || e_Pe_new >= Delta2) {
+            const double tau = (-e_Pd + sqrt(e_Pd * e_Pd + d_Pd * (Delta2 - e_Pe))) / d_Pd;
+            for (int e = 0; e < N; ++e) {
+                eta[e] = fma(tau, delta[e], eta[e]);
+                Heta[e] = fma(tau, Hd[e], Heta[e]);
+            }
+            res.stop = (d_Hd <= 0.0) ? TCG_NEGATIVE_CURVATURE : TCG_EXCEEDED_TR;
+            ++j;
+            break;
+        }
+        e_Pe = e_Pe_new;
+        for (int e = 0; e < N; ++e) {
+            new_eta[e] = fma(alpha, delta[e], eta[e]);
+            new_Heta[e] = fma(alpha, Hd[e], Heta[e]);
+            r_new[e] = fma(alpha, Hd[e], r[e]);
+        }
+        const double new_model = fma(0.5, vdot(c, new_eta, new_Heta), vdot(c, new_eta, st->c));
+        const double rr_new = vdot(c, r_new, r_new), xr = vdot(c, pt->x, r_new);
+        if (new_model >= model_value) {
+            res.stop = TCG_MODEL_INCREASED;
+            ++j;
+            break;
+        }
+        memcpy(eta, new_eta, sizeof(double) * N);
+        memcpy(Heta, new_Heta, sizeof(double) * N);
+        memcpy(r, r_new, sizeof(double) * N);
+        model_value = new_model;
+        r_r = rr_new;
+        /* residual test on squares (||r|| <= target <=> r_r <= target^2): no square root on the critical path */
+        if (j >= o->tcg_mininner && r_r <= target_sq) {
+            res.stop = (o->tcg_kappa < nr_theta) ? TCG_REACHED_TARGET_LINEAR : TCG_REACHED_TARGET_SUPERLINEAR;
+            ++j;
+            break;
+        }
+        /* beta = z_r / z_r_old as a product with the reciprocal formed one iteration earlier (off the critical path) */
+        const double beta = r_r * inv_zr;
+        z_r = r_r;
+        inv_zr = 1.0 / z_r;
+        const double xd = fma(beta, b, -xr); /* <x, -r + beta delta> */
+        for (int e = 0; e < N; ++e) {
+            const double dn = fma(beta, delta[e], -r[e]);
+            delta[e] = fma(-xd, pt->x[e], dn);
+        }
+        e_Pd = beta * fma(alpha, d_Pd, e_Pd);
+        d_Pd = fma(beta * beta, d_Pd, z_r);
+    }
+#else
     for (; j < maxinner; ++j) {
         matvec(c, delta, Sv);
         const double a = vdot(c, pt->x, Sv), b = vdot(c, pt->x, delta), g1 = vdot(c, wv, delta);
@@ -327,6 +401,7 @@ static TcgResult tcg(const Ctx* c, const det_options* o, const Pt* pt, const Ste
         e_Pd = beta * (e_Pd + alpha * d_Pd);
         d_Pd = z_r + (beta * beta) * d_Pd;
     }
+#endif
 #else
     for (; j < maxinner; ++j) {
         Hw(c, pt, st, delta, Hd);
