@@ -593,6 +593,11 @@ def check_user_functions(option, problem, st, log):
     return dropped
 
 
+# rows per pair of the per-inner-iteration log buffer of `run_batch` (None: 12 * maxiter + 64, at least 64, at most 65536);
+# tests set it to exercise the path that re-solves the pairs whose log did not fit
+TRACE_CAPACITY_OVERRIDE = None
+
+
 class RIPTRM:
     """Drop-in for the reference's `RIPTRM` class (src/solver/RIPTRM.py:302-976): both trust-region solvers, 'tCG' and the
     class default 'Exact_RepMat' with the second-order stationarity test."""
@@ -710,23 +715,40 @@ class RIPTRM:
         trace_mode = 1 if save_inner else 2
         maxiter = int(option["maxiter"])
         cap = (maxiter + 1) if not save_inner else min(max(64, 12 * maxiter + 64), 1 << 16)
+        if save_inner and TRACE_CAPACITY_OVERRIDE is not None:
+            cap = int(TRACE_CAPACITY_OVERRIDE)
         bs = BatchSolver(structures, device=self.device)
         try:
-            while True:
-                bs.set_options(option, trace_mode, cap)
-                x, y, summary, trace = bs.solve()
-                need = int(summary[:, _lib.SM["trace_rows"]].max())
-                if need <= cap:
-                    break
-                cap = need  # the solve is deterministic: rerun with room for every row
+            bs.set_options(option, trace_mode, cap)
+            x, y, summary, trace = bs.solve()
             run_time = bs.kernel_ms * 1e-3
         finally:
             bs.close()
+        # A pair whose log needs more rows than the capacity (iterates, multipliers and summary are complete either way; only
+        # its rows beyond `cap` were dropped) is solved again -- the solve is deterministic -- in a batch of just those pairs
+        # with room for every row: the rest of the batch is not re-run.  (The reference's default inner_maxiter = None leaves
+        # the number of rows of an outer iteration unbounded, so no capacity holds by construction.)
+        rows_needed = summary[:, _lib.SM["trace_rows"]].astype(np.int64)
+        over = np.flatnonzero(rows_needed > cap)
+        traces = [trace[i] for i in range(len(structures))]
+        if over.size:
+            sub = BatchSolver([structures[i] for i in over], device=self.device)
+            try:
+                sub.set_options(option, trace_mode, int(rows_needed[over].max()))
+                xs, ys, ss, ts = sub.solve()
+                run_time += sub.kernel_ms * 1e-3
+            finally:
+                sub.close()
+            for j, i in enumerate(over):
+                timed_out = summary[i, _lib.SM["stop_reason"]] == 1 or ss[j, _lib.SM["stop_reason"]] == 1   # 'maxtime' is wall clock
+                if not timed_out and not (np.array_equal(xs[j], x[i]) and np.array_equal(ss[j], summary[i])):
+                    raise _lib.RiptrmError("the re-solve of a pair whose trace overflowed did not reproduce its first solve")
+                traces[i] = ts[j]
         self.last_summary = summary
         outs = []
         for i, st in enumerate(structures):
             nrows = int(summary[i, _lib.SM["trace_rows"]])
-            log = trace_to_log(trace[i, :nrows], save_inner)
+            log = trace_to_log(traces[i][:nrows], save_inner)
             opt = copy.copy(option)
             opt["stoppingcriterion"] = _stop_message(summary[i], option, run_time)
             outs.append(Output(name=self.name, x=st.unpack_x(x[i]), option=opt, log=log,

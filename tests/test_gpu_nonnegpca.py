@@ -329,3 +329,26 @@ def test_two_warps_per_copy_of_S_is_bit_identical(rb, monkeypatch):
     for key, (x, y, sm, _) in res.items():
         assert np.array_equal(x, ref[0]) and np.array_equal(y, ref[1]) and np.array_equal(sm[:, :15], ref[2][:, :15]), key
     assert (ref[2][:, rb._lib.SM["residual"]] < 1e-8).all()
+
+
+@pytest.mark.gpu
+def test_log_that_overflows_its_buffer_resolves_only_those_pairs(rb, datasets, monkeypatch):
+    """run_batch sizes the per-inner-iteration log buffer from maxiter; a pair that needs more rows is solved again (alone, the
+    solve is deterministic) with room for every row, the rest of the batch is not: logs identical to the roomy run."""
+    import riptrm_b200.solver as solver_mod
+    d = datasets["NonnegPCA/1"]
+    rs = np.random.RandomState(3)
+    starts = [d["initx_a"]] + [v / np.linalg.norm(v) for v in (rs.rand(d["initx_a"].size) + 0.05 for _ in range(2))]
+    sts = [rb.NonnegPCAStructure(Z=d["Z"], x0=x0, y0=d["initineqLagmult"]) for x0 in starts]
+    opt = {"TRS_solver": "tCG", "second_order_stationarity": False, "tolresid": 0, "maxtime": 1e9, "maxiter": 12}
+    roomy = rb.RIPTRM(opt).run_batch([None] * 3, structures=sts)
+    rows = sorted(len(o.log["iteration"]) for o in roomy)
+    monkeypatch.setattr(solver_mod, "TRACE_CAPACITY_OVERRIDE", (rows[0] + rows[1]) // 2 if rows[0] < rows[1] else rows[0] - 1)
+    tight = rb.RIPTRM(opt).run_batch([None] * 3, structures=sts)
+    for a, b in zip(roomy, tight):
+        assert len(a.log["iteration"]) == len(b.log["iteration"])
+        for k in a.log:
+            if k == "time":
+                continue
+            assert all((u == v) or (u != u and v != v) for u, v in zip(a.log[k], b.log[k])), k
+        assert np.array_equal(a.x, b.x) and np.array_equal(a.ineqLagmult, b.ineqLagmult)
