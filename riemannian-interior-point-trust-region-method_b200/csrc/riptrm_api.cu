@@ -4,6 +4,7 @@
 // pair per warp at a time, a persistent grid (SM count x resident CTAs per SM) that pulls
 // instances from an atomic queue because per-instance work varies 3-5x.
 // There is no inter-warp synchronisation anywhere on the solve path.
+#include <cuda.h>           // types of the stream memory operations only: the entry point comes from cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -75,6 +76,7 @@ struct riptrm_handle {
     int* d_fast_order = nullptr;  // fast lane: the pairs of the longest units
     int* d_lane_state = nullptr;  // fast lane: election state (2 + 2 * 256 ints) + per-CTA placement records
     unsigned long long* d_lane_times = nullptr;   // entry / exit globaltimer of the recorded CTAs
+    unsigned int* d_lane_arrive = nullptr;        // arrival count of the lane kernel's CTAs (see SphereParams::lane_arrive)
     int lane_debug_len = 0;
     cudaStream_t lane_stream = nullptr;
     cudaEvent_t lane_ev0 = nullptr, lane_ev1 = nullptr;
@@ -125,6 +127,8 @@ struct SphereParams {
     int* lane_state;
     int* lane_debug;
     unsigned long long* lane_times;   // [CTA][2]: globaltimer at entry / exit of the CTAs that write a lane_debug record
+    unsigned int* lane_arrive;        // two-kernel lane: every lane CTA counts itself in when it starts; the main kernel's stream
+                                      // waits on the count (cuStreamWaitValue32), so it cannot start before the lane is resident
     // hooks
     const double* v;
     double mu;
@@ -403,6 +407,7 @@ extern "C" int riptrm_destroy(riptrm_handle* h) {
     free_any(h->d_fast_order);
     free_any(h->d_lane_state);
     free_any(h->d_lane_times);
+    free_any(h->d_lane_arrive);
     if (h->lane_stream) cudaStreamDestroy(h->lane_stream);
     if (h->lane_ev0) cudaEventDestroy(h->lane_ev0);
     if (h->lane_ev1) cudaEventDestroy(h->lane_ev1);
@@ -935,6 +940,10 @@ __global__ void __launch_bounds__(128, 2) sphere_tmem_kernel(SphereParams P, Dev
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         P.lane_debug[blockIdx.x] = (int)(smid << 4) | kLaneLane;
         if (P.lane_times != nullptr) P.lane_times[2 * blockIdx.x] = global_timer_ns();
+    }
+    if (P.lane_arrive != nullptr && threadIdx.x == 0) {   // this CTA is resident: count it in for the main kernel's stream wait
+        atomicAdd(P.lane_arrive, 1u);
+        __threadfence_system();
     }
     if (warp == 0) tmem::alloc(&tmem_base, 256);
     tmem::fence_before_sync();
@@ -1525,7 +1534,19 @@ static int prepare_lane_in_kernel(riptrm_handle* h, SphereParams& P, cudaStream_
     return RIPTRM_OK;
 }
 
-// (legacy form, RIPTRM_FAST_LANE_LEGACY=1: a second kernel on a priority stream, placed by timing)
+typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static WaitValue32Fn lane_wait_value_entry() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return reinterpret_cast<WaitValue32Fn>(fn);
+}
+
+// the two-kernel lane: a second kernel on a priority stream whose CTAs take an SM each (150 KB of shared memory: no main CTA
+// fits beside them); the main kernel's stream waits until they have all started
 static int launch_fast_lane(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
     int fast_units = 16;   // 32 pairs: 8 CTAs of the 4-warp kernel on 8 SMs of their own
     if (const char* e = getenv("RIPTRM_FAST_UNITS")) fast_units = std::max(1, std::min(64, atoi(e)));   // tuning knob
@@ -1541,9 +1562,12 @@ static int launch_fast_lane(riptrm_handle* h, const SphereParams& P, const DevOp
     mark_fast_lane_kernel<<<(fast_units + 31) / 32, 32, 0, st>>>(h->d_order, fast_units, h->d_pause, h->d_fast_order);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemsetAsync(h->d_counter + 1, 0, sizeof(int), st));
+    if (h->d_lane_arrive == nullptr) CUDA_TRY(cudaMalloc(&h->d_lane_arrive, sizeof(unsigned int)));
+    CUDA_TRY(cudaMemsetAsync(h->d_lane_arrive, 0, sizeof(unsigned int), st));
     CUDA_TRY(cudaEventRecord(h->lane_ev0, st));
     CUDA_TRY(cudaStreamWaitEvent(h->lane_stream, h->lane_ev0, 0));
     SphereParams F = P;
+    F.lane_arrive = h->d_lane_arrive;
     F.sibling_units = 0;
     F.order = h->d_fast_order;
     F.queue_len = 2 * fast_units;
@@ -1554,12 +1578,24 @@ static int launch_fast_lane(riptrm_handle* h, const SphereParams& P, const DevOp
     auto kern = sphere_tmem_kernel<0>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    kern<<<(2 * fast_units + 3) / 4, 128, smem, h->lane_stream>>>(F, o, h->d_counter + 1);
+    const int nctas = (2 * fast_units + 3) / 4;
+    kern<<<nctas, 128, smem, h->lane_stream>>>(F, o, h->d_counter + 1);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(h->lane_ev1, h->lane_stream));
-    hold_kernel<<<1, 32, 0, st>>>(30000);   // the main kernel follows on `st` once the lane's CTAs have their SMs
-    CUDA_TRY(cudaGetLastError());
-    h->launches += 3;
+    // The main kernel follows on `st` once the lane's CTAs have their SMs -- BY CONSTRUCTION: `st` waits until the arrival
+    // count the lane CTAs increment at entry has reached their number (a stream memory operation; round 1 slept 30 us in a
+    // one-warp kernel instead).  Driver entry point through the runtime, so the library does not link libcuda; without it
+    // (or with RIPTRM_LANE_HOLD_BY_SLEEP=1, an A/B switch) the sleep kernel is the fall-back.
+    static WaitValue32Fn wait_value = lane_wait_value_entry();
+    if (wait_value != nullptr && getenv("RIPTRM_LANE_HOLD_BY_SLEEP") == nullptr) {
+        const CUresult wr = wait_value((CUstream)st, (CUdeviceptr)(uintptr_t)h->d_lane_arrive, (cuuint32_t)nctas, CU_STREAM_WAIT_VALUE_GEQ);
+        if (wr != CUDA_SUCCESS) return fail(RIPTRM_E_CUDA, "cuStreamWaitValue32 failed");
+        h->launches += 2;
+    } else {
+        hold_kernel<<<1, 32, 0, st>>>(30000);
+        CUDA_TRY(cudaGetLastError());
+        h->launches += 3;
+    }
     return RIPTRM_OK;
 }
 
