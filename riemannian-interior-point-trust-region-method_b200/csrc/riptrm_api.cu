@@ -926,15 +926,19 @@ static int ensure(double*& p, size_t bytes) {
 
 // n = 50 with S in Tensor Memory: 4 independent warps per CTA (one per TMEM sub-partition), 2 CTAs per SM (each
 // allocates 256 of the 512 TMEM columns), every warp pulling pairs from the same atomic queue as sphere_kernel.
+#ifndef RIPTRM_RS1
+#define RIPTRM_RS1 1     // sphere_tmem_kernel (one warp per copy; the fast lane, small batches): tCG reductions through shared memory
+#endif
+constexpr int kTmem1Scratch = 64 + kRedDoubles;   // per warp after the staging copy: broadcast operand + reduction rows
 template <int MODE>
 __global__ void __launch_bounds__(128, 2) sphere_tmem_kernel(SphereParams P, DevOpts o, int* counter) {
-    using F = SphereFam<2, 50, true>;
+    using F = SphereFam<2, 50, true, 64, RIPTRM_RS1 != 0>;
     constexpr int K = 2;
     extern __shared__ __align__(16) double smem[];
     __shared__ uint32_t tmem_base;
     const int n = 50, ns = 50, pad = 64;
     const int warp = threadIdx.x >> 5, lane = lane_id();
-    double* my = smem + (size_t)warp * (n * ns + pad + 64);
+    double* my = smem + (size_t)warp * (n * ns + pad + kTmem1Scratch);
     if (P.lane_debug != nullptr && threadIdx.x == 0) {   // placement record of the two-kernel lane: (smid << 4) | role
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -952,6 +956,7 @@ __global__ void __launch_bounds__(128, 2) sphere_tmem_kernel(SphereParams P, Dev
     typename F::Ctx ctx;
     ctx.S = my;                       // staging copy; S.v reads the TMEM copy
     ctx.vbuf = my + n * ns + pad;
+    ctx.ws.init(ctx.vbuf);
     ctx.n = n;
     ctx.ns = ns;
     ctx.eps = P.eps;
@@ -1197,7 +1202,7 @@ static bool lane_in_kernel_possible(riptrm_handle* h) {
 
 template <int MODE>
 static int launch_sphere_tmem(riptrm_handle* h, const SphereParams& P, const DevOpts& o, cudaStream_t st) {
-    const size_t smem = (size_t)4 * (50 * 50 + 64 + 64) * sizeof(double);
+    const size_t smem = (size_t)4 * (50 * 50 + 64 + kTmem1Scratch) * sizeof(double);
     auto kern = sphere_tmem_kernel<MODE>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
