@@ -183,7 +183,8 @@ enum {
     RIPTRM_SM_DUALVIOLATION = 4, RIPTRM_SM_MANVIOLATION = 5, RIPTRM_SM_MAXVIOLATION = 6,
     RIPTRM_SM_MEANVIOLATION = 7, RIPTRM_SM_MU = 8, RIPTRM_SM_RADIUS = 9, RIPTRM_SM_OUTER_ITERS = 10,
     RIPTRM_SM_INNER_ITERS = 11, RIPTRM_SM_TCG_ITERS = 12, /* sum of (j+1) over tCG calls */
-    RIPTRM_SM_AUX_HESSVECS = 13,                         /* the extra Hw(dx) of RIPTRM.py:659 */
+    RIPTRM_SM_AUX_HESSVECS = 13,                         /* fresh Hw(dx) products formed for RIPTRM.py:659 (0 where the
+                                                            tCG's accumulated Hw[eta] is used: Sphere, TRS_solver='tCG') */
     RIPTRM_SM_STOP_REASON = 14, RIPTRM_SM_TRACE_ROWS = 15 /* rows produced (may exceed capacity) */
 };
 

@@ -26,6 +26,7 @@
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #define LANES 32
@@ -581,8 +582,8 @@ static int inner_step(const Ctx* c, const det_options* o, Pt* pt, double* y, dou
     info->radius = *Delta;
     Step st;
     begin_step(c, pt, y, mu, &st);
-    double dx[MAXN], Hdx_unused[MAXN];
-    const TcgResult tr = tcg(c, o, pt, &st, *Delta, dx, Hdx_unused);
+    double dx[MAXN], Hdx_tcg[MAXN];
+    const TcgResult tr = tcg(c, o, pt, &st, *Delta, dx, Hdx_tcg);
     cnt->tcg += (double)tr.iters;
     info->dxtype = (double)tr.stop;
     info->tcg_iters = (double)tr.iters;
@@ -632,9 +633,15 @@ static int inner_step(const Ctx* c, const det_options* o, Pt* pt, double* y, dou
     const double phi_cur = pt->cost - mu * pl_cur;
     const double phi_new = ptN.cost - mu * pl_new;
     double ared = phi_cur - phi_new;
+    /* the Hw[dx] of RIPTRM.py:659: the product the tCG accumulated beside eta (solver_warp.cuh inner_step), or a fresh one
+     * with RIPTRM_RECOMPUTE_HDX=1 in the environment (the reference's form; the switch the CUDA library reads too) */
     double Hdx[MAXN];
-    Hw(c, pt, &st, dx, Hdx);
-    cnt->aux += 1.0;
+    if (getenv("RIPTRM_RECOMPUTE_HDX") == NULL) {
+        memcpy(Hdx, Hdx_tcg, sizeof(Hdx));
+    } else {
+        Hw(c, pt, &st, dx, Hdx);
+        cnt->aux += 1.0;
+    }
     double pred = (0.0 - 0.5 * vdot(c, Hdx, dx)) - vdot(c, st.c, dx);
     const double reg = (fmax(1.0, fabs(phi_cur)) * 2.220446049250313e-16) * o->reduction_regularization;
     ared = ared + reg;

@@ -32,6 +32,7 @@ struct SphereFam {
     static_assert(!TM || (NFIX == 50 && K_ == 2), "the TMEM layout is built for n = 50");
     static constexpr int K = K_;
     static constexpr int MK = K_;
+    static constexpr bool kTcgReturnsHw = true;   // tcg() returns Hw[eta] accumulated beside eta (solver_warp.cuh inner_step)
     static_assert(K_ == 2 || K_ == 4, "pair layout: K is 2 or 4");
     using Vec = WVec<K>;
     using CVec = WVec<K>;

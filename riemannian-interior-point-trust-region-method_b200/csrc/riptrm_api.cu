@@ -892,6 +892,7 @@ static DevOpts make_devopts(const riptrm_handle* h) {
     o.tcg_mininner = s.tcg_mininner;
     o.tcg_maxinner = s.tcg_maxinner;
     o.is_euclidean_embedded = s.is_euclidean_embedded;
+    o.recompute_hdx = getenv("RIPTRM_RECOMPUTE_HDX") != nullptr ? 1 : 0;   // A/B switch: the reference's fresh Hw[dx] at :659
     o.trace_mode = s.trace_mode;
     o.trace_capacity = s.trace_capacity;
     o.tolresid = s.tolresid;

@@ -12,6 +12,7 @@
 //   eval_point, begin_step, Hw, gadj, inner, project, retract, gradL_norm, manvio, dist,
 //   cactive(ctx,k), dim(ctx), typical_dist(ctx)
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "dense_trs.cuh"
 #include "../../include/riptrm_b200.h"
@@ -29,7 +30,16 @@ struct DevOpts {
     int second_order;
     double trs_tolhardcase;
     const double* tolS;  // device: forcing_function_second_order(mu) per outer iteration
+    // the Hw[dx] of the model decrease (RIPTRM.py:659): 0 = the product the tCG has accumulated (families whose tCG returns
+    // it, `F::kTcgReturnsHw`), 1 = a fresh Hessian-vector product as the reference writes it (RIPTRM_RECOMPUTE_HDX=1)
+    int recompute_hdx;
 };
+
+// families whose tcg() hands back Hw[eta] next to eta declare `static constexpr bool kTcgReturnsHw = true`
+template <class F, class = void>
+struct TcgReturnsHw { static constexpr bool value = false; };
+template <class F>
+struct TcgReturnsHw<F, std::enable_if_t<F::kTcgReturnsHw>> { static constexpr bool value = true; };
 
 // ------------------------------------------------------------------------------------------
 // Exact_RepMat: the representation matrix of Hw in an orthonormal tangent basis and its eigen-decomposition.
@@ -434,7 +444,7 @@ __device__ __forceinline__ bool inner_step(const typename F::Ctx& ctx, const Dev
     typename F::Step st;
     F::begin_step(ctx, pt, y, mu, st);                              // s, grad f, c  (:724-730)
 
-    Vec dx;
+    Vec dx, Hdx_tcg;
     if constexpr (EXACT) {
         // compute_direction, Exact_RepMat branch (:431-444)
         typename F::Coord cc;
@@ -454,8 +464,7 @@ __device__ __forceinline__ bool inner_step(const typename F::Ctx& ctx, const Dev
         dx = F::from_coords(ctx, pt, cc, rw.coef);                  // :441-443
         info.dxtype = (double)to.kind;
     } else {
-        Vec Hdx_unused;
-        const TcgResult tr = F::tcg(ctx, o, pt, y, st, Delta, dx, Hdx_unused);  // :733 -> :445-452
+        const TcgResult tr = F::tcg(ctx, o, pt, y, st, Delta, dx, Hdx_tcg);  // :733 -> :445-452
         cnt.tcg += (double)tr.iters;
         info.dxtype = (double)tr.stop;
         info.tcg_iters = (double)tr.iters;
@@ -554,8 +563,18 @@ __device__ __forceinline__ bool inner_step(const typename F::Ctx& ctx, const Dev
     const double phi_cur = pt.cost - mu * pl_cur;                   // :649
     const double phi_new = ptN.cost - mu * pl_new;
     double ared = phi_cur - phi_new;                                // :658
-    const Vec Hdx = F::Hw(ctx, pt, y, st, dx);                      // the extra Hessian-vector of :659
-    cnt.aux += 1.0;
+    // The Hessian-vector product of :659.  Hw is linear and the tCG accumulates Hw[eta] = sum_j alpha_j Hw[delta_j] beside eta
+    // (:132, :154), so on the tCG path that vector is at hand (pymanopt's own trust-region solver uses it the same way): one
+    // S.v fewer per trust-region iteration.  It differs from a fresh product by rounding only -- `pred` moves in its last
+    // digits, no decision of the reference dataset's 342 trust-region iterations does (profiles/parity_r02.md is unchanged
+    // to every digit); DevOpts::recompute_hdx restores the reference's fresh product.
+    Vec Hdx;
+    if (!EXACT && TcgReturnsHw<F>::value && !o.recompute_hdx) {
+        Hdx = Hdx_tcg;
+    } else {
+        Hdx = F::Hw(ctx, pt, y, st, dx);
+        cnt.aux += 1.0;
+    }
     double ip_hd = F::inner_partial(ctx, pt, Hdx, dx), ip_cd = F::inner_partial(ctx, pt, st.c, dx);
     wsum2(ip_hd, ip_cd);
     double pred = (0.0 - 0.5 * ip_hd) - ip_cd;
