@@ -226,11 +226,12 @@ int riptrm_set_options(riptrm_handle* h, const riptrm_options* opts);
  * Outputs (any may be NULL): x [batch][n*p], y [batch][m], summary [batch][RIPTRM_SUMMARY_FIELDS],
  * trace [batch][trace_capacity][RIPTRM_TRACE_FIELDS].  `stream` is a cudaStream_t (or NULL).
  * With `where` == RIPTRM_HOST the call returns after the results are in the host buffers;
- * with RIPTRM_DEVICE the batched families (1-3) only enqueue work on `stream`.  The COLUMNS / STIEFEL families (4, 5) are
- * sequenced by the host -- one tCG launch and one post launch per trust-region iteration, enqueued four iterations ahead of
- * the one-int "all done" flag the host polls, so the stream never runs dry; launches behind the last iteration return at
- * once on the device -- so their solve returns when the solve has finished, in either mode ('maxtime' is tested against
- * the host clock at enqueue time, i.e. up to four iterations late). */
+ * with RIPTRM_DEVICE every family only enqueues work on `stream`.  The COLUMNS / STIEFEL families (4, 5) run their whole
+ * solve as ONE graph launch: a conditional WHILE node whose body is the tCG launch and the post launch of a trust-region
+ * iteration (cooperative kernels), ended from the device when every run has finished; 'maxtime' / 'inner_maxtime' are tested
+ * against a device clock.  Where conditional graph nodes are missing (or with RIPTRM_COLUMNS_HOST_LOOP=1) the host sequences
+ * the launches, four iterations ahead of the one-int "all done" flag it polls, and the call returns when the solve has
+ * finished. */
 int riptrm_solve(riptrm_handle* h, const double* x0, const double* y0, double* x, double* y,
                  double* summary, double* trace, int where, void* stream);
 

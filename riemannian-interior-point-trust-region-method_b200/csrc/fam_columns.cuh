@@ -87,7 +87,26 @@ struct Params {
     // time limits (RIPTRM.py:822-834, base_solver.py:85-106): the host loop measures the time since the start of the solve
     // when it polls `all_done` and passes it in, so every CTA takes the same branch
     double now_s, maxtime, inner_maxtime;   // inner_maxtime < 0: None (the outer limit applies to the inner loop)
+    // device-side loop (riptrm_api.cu columns_solve_graph): the launches of a whole solve are the body of a conditional WHILE
+    // graph node; seconds since the start come from a device clock stamp written ahead of every iteration, and the post
+    // kernel ends the loop
+    const double* now_ptr;         // nullptr: `now_s` above (host clock at enqueue time)
+    unsigned long long cond;       // cudaGraphConditionalHandle
+    int cond_on;
 };
+
+// seconds since the start of the solve, device clock: written by one thread ahead of every trust-region iteration so that every
+// CTA of the following launches reads the same value
+__global__ void stamp_kernel(double* now_s, unsigned long long* t0, int init) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (init) {
+        *t0 = t;
+        *now_s = 0.0;
+    } else {
+        *now_s = (double)(t - *t0) * 1e-9;
+    }
+}
 
 // per-column solver state kept in global memory between launches
 enum {
@@ -1027,6 +1046,7 @@ struct PostState {  // per column, identical in every CTA
 template <int P, bool INIT>
 __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
     if (!INIT && *reinterpret_cast<const volatile int*>(prm.all_done) != 0) return;   // enqueued ahead of the flag (see columns_kernel)
+    const double now_s = (prm.now_ptr != nullptr) ? *prm.now_ptr : prm.now_s;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<P>& sm = *reinterpret_cast<Smem<P>*>(smem_raw);
     __shared__ PostState ps[P];
@@ -1345,7 +1365,7 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
                 }
             }
             {   // :822-834 (after the step, as the reference)
-                const double rt = (prm.inner_maxtime < 0.0) ? prm.now_s : (prm.now_s - s.t_inner);
+                const double rt = (prm.inner_maxtime < 0.0) ? now_s : (now_s - s.t_inner);
                 const double lim = (prm.inner_maxtime < 0.0) ? prm.maxtime : prm.inner_maxtime;
                 if (rt >= lim) {
                     s.inner_status = (double)RIPTRM_INNER_MAX_TIME;
@@ -1503,13 +1523,13 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
                 row[RIPTRM_TR_MANVIOLATION] = man_v;
                 row[RIPTRM_TR_MAXVIOLATION] = max_v;
                 row[RIPTRM_TR_MEANVIOLATION] = mean_v;
-                row[RIPTRM_TR_TIME] = prm.now_s;
+                row[RIPTRM_TR_TIME] = now_s;
             }
             s.rows += 1.0;
         }
         if (s.boundary) {
             int stop = RIPTRM_STOP_RUNNING;
-            if (prm.now_s >= prm.maxtime) stop = RIPTRM_STOP_MAXTIME;
+            if (now_s >= prm.maxtime) stop = RIPTRM_STOP_MAXTIME;
             else if (it >= prm.maxiter) stop = RIPTRM_STOP_MAXITER;
             if (residual <= prm.tolresid) stop = RIPTRM_STOP_TOLRESID;
             if (g == 0 && prm.summary != nullptr) {
@@ -1541,7 +1561,7 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
                 s.Delta_init = s.Delta;
                 s.xSx_init = s.xSx;
                 s.cost_init = s.cost;
-                s.t_inner = prm.now_s;
+                s.t_inner = now_s;
             }
         }
     }
@@ -1571,6 +1591,13 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
         bool all = true;
         for (int c = 0; c < prm.p; ++c) all = all && (ps[c].finished != 0.0);
         *prm.all_done = all ? 1 : 0;
+        if (prm.cond_on) cudaGraphSetConditional((cudaGraphConditionalHandle)prm.cond, all ? 0u : 1u);
+        if (prm.now_ptr != nullptr) {   // the clock stamp the next iteration's launches read (device-side loop)
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            double* nw = const_cast<double*>(prm.now_ptr);
+            nw[0] = (double)(t - *reinterpret_cast<const unsigned long long*>(nw + 1)) * 1e-9;
+        }
     }
 #undef FOR_ELEMS
 }

@@ -495,6 +495,7 @@ struct PostState {
 template <int P, bool INIT>
 __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
     if (!INIT && *reinterpret_cast<const volatile int*>(prm.all_done) != 0) return;   // enqueued ahead of the flag (columns_kernel)
+    const double now_s = (prm.now_ptr != nullptr) ? *prm.now_ptr : prm.now_s;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<P>& sm = *reinterpret_cast<Smem<P>*>(smem_raw);
     __shared__ PostState ps;
@@ -828,7 +829,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
                 }
             }
             {   // :822-834
-                const double rt = (prm.inner_maxtime < 0.0) ? prm.now_s : (prm.now_s - s.t_inner);
+                const double rt = (prm.inner_maxtime < 0.0) ? now_s : (now_s - s.t_inner);
                 const double lim = (prm.inner_maxtime < 0.0) ? prm.maxtime : prm.inner_maxtime;
                 if (rt >= lim) {
                     s.inner_status = (double)RIPTRM_INNER_MAX_TIME;
@@ -1011,13 +1012,13 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
                     row[RIPTRM_TR_MANVIOLATION] = man_v;
                     row[RIPTRM_TR_MAXVIOLATION] = max_v;
                     row[RIPTRM_TR_MEANVIOLATION] = mean_v;
-                    row[RIPTRM_TR_TIME] = prm.now_s;
+                    row[RIPTRM_TR_TIME] = now_s;
                 }
                 s.rows += 1.0;
             }
             if (s.boundary) {
                 int stop = RIPTRM_STOP_RUNNING;
-                if (prm.now_s >= prm.maxtime) stop = RIPTRM_STOP_MAXTIME;
+                if (now_s >= prm.maxtime) stop = RIPTRM_STOP_MAXTIME;
                 else if (it >= prm.maxiter) stop = RIPTRM_STOP_MAXITER;
                 if (residual <= prm.tolresid) stop = RIPTRM_STOP_TOLRESID;
                 if (g == 0 && prm.summary != nullptr) {
@@ -1048,7 +1049,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
                     s.k = 0.0;
                     s.Delta_init = s.Delta;
                     s.cost_init = s.cost;
-                    s.t_inner = prm.now_s;
+                    s.t_inner = now_s;
                 }
             }
         }
@@ -1071,6 +1072,13 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
         st[CS_DELTA_INIT] = s.Delta_init; st[CS_COST_INIT] = s.cost_init;
         st[CS_T_INNER] = s.t_inner;
         *prm.all_done = (s.finished != 0.0) ? 1 : 0;
+        if (prm.cond_on) cudaGraphSetConditional((cudaGraphConditionalHandle)prm.cond, (s.finished != 0.0) ? 0u : 1u);
+        if (prm.now_ptr != nullptr) {   // the clock stamp the next iteration's launches read (device-side loop)
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            double* nw = const_cast<double*>(prm.now_ptr);
+            nw[0] = (double)(t - *reinterpret_cast<const unsigned long long*>(nw + 1)) * 1e-9;
+        }
     }
 #undef FOR_ROWS
 }

@@ -97,6 +97,11 @@ struct riptrm_handle {
     int* h_done = nullptr;               // pinned, kColLookahead ints
     cudaEvent_t done_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool no_launch_events = false;       // inside a whole solve: the launches do not record ev0 / ev1 (the solve does)
+    // device-side loop of the whole solve (columns_solve_graph): the instantiated graph, the parameter block it was built
+    // for, the device clock stamp
+    cudaGraphExec_t col_graph = nullptr;
+    col::Params col_graph_prm{};
+    double* d_now = nullptr;             // [0] seconds since the start of the solve, [1] (as bits) globaltimer at the start
     int64_t launches = 0;
     double last_ms = 0.0;
 };
@@ -378,6 +383,8 @@ static void free_any(T*& p) {
 
 extern "C" int riptrm_destroy(riptrm_handle* h) {
     if (h != nullptr) {
+        if (h->col_graph != nullptr) cudaGraphExecDestroy(h->col_graph);
+        free_dev(h->d_now);
         if (h->h_done != nullptr) cudaFreeHost(h->h_done);
         for (auto& e : h->done_ev) if (e != nullptr) cudaEventDestroy(e);
     }
@@ -696,8 +703,140 @@ static int columns_dispatch_post(riptrm_handle* h, col::Params& prm, cudaStream_
 #endif
 }
 
-// riptrm_solve on the COLUMNS family: p independent RIPTRM runs sharing S, advanced in lock-step.  The host only
-// sequences launches (tCG for all columns, then the rest of the trust-region iteration) and polls one flag.
+// ---- device-side loop of the whole solve ------------------------------------------------------------------------------
+// kernel entry points by family and column template (what columns_dispatch / columns_dispatch_post launch)
+static void* columns_tcg_entry(const riptrm_handle* h, size_t* smem) {
+#ifdef RIPTRM_DEV_SPHERE_ONLY
+    return nullptr;
+#else
+#define RIPTRM_ENTRY(NS, KERN, PP) case PP: *smem = sizeof(col::Smem<PP>); return (void*)NS::KERN<PP, 2>;
+    if (is_stiefel(h)) {
+        switch (h->colP) { RIPTRM_ENTRY(stf, stiefel_kernel, 4) RIPTRM_ENTRY(stf, stiefel_kernel, 10) RIPTRM_ENTRY(stf, stiefel_kernel, 16) }
+        return nullptr;
+    }
+    switch (h->colP) {
+        RIPTRM_ENTRY(col, columns_kernel, 1) RIPTRM_ENTRY(col, columns_kernel, 2) RIPTRM_ENTRY(col, columns_kernel, 4)
+        RIPTRM_ENTRY(col, columns_kernel, 8) RIPTRM_ENTRY(col, columns_kernel, 10) RIPTRM_ENTRY(col, columns_kernel, 16)
+    }
+    return nullptr;
+#undef RIPTRM_ENTRY
+#endif
+}
+template <bool INIT>
+static void* columns_post_entry(const riptrm_handle* h) {
+#ifdef RIPTRM_DEV_SPHERE_ONLY
+    return nullptr;
+#else
+#define RIPTRM_ENTRY(NS, KERN, PP) case PP: return (void*)NS::KERN<PP, INIT>;
+    if (is_stiefel(h)) {
+        switch (h->colP) { RIPTRM_ENTRY(stf, stiefel_post_kernel, 4) RIPTRM_ENTRY(stf, stiefel_post_kernel, 10) RIPTRM_ENTRY(stf, stiefel_post_kernel, 16) }
+        return nullptr;
+    }
+    switch (h->colP) {
+        RIPTRM_ENTRY(col, columns_post_kernel, 1) RIPTRM_ENTRY(col, columns_post_kernel, 2) RIPTRM_ENTRY(col, columns_post_kernel, 4)
+        RIPTRM_ENTRY(col, columns_post_kernel, 8) RIPTRM_ENTRY(col, columns_post_kernel, 10) RIPTRM_ENTRY(col, columns_post_kernel, 16)
+    }
+    return nullptr;
+#undef RIPTRM_ENTRY
+#endif
+}
+
+// The whole solve as ONE graph launch: [clock stamps, post<INIT>] then a conditional WHILE node whose body is [tCG launch,
+// post launch] -- all cooperative launches; the post kernel ends the loop with cudaGraphSetConditional when every
+// run has finished.  No host involvement between the first launch and the last: `RIPTRM_DEVICE` solves of the COLUMNS /
+// STIEFEL families only enqueue work, and the time limits are tested against a device clock.  The graph is kept with the
+// parameter block it was built for and rebuilt when a pointer or option in it changes.  Returns > 0 when conditional graph
+// nodes are not available (the caller falls back to the host-sequenced loop).
+static int columns_solve_graph(riptrm_handle* h, col::Params prm, cudaStream_t st) {
+    if (getenv("RIPTRM_COLUMNS_HOST_LOOP") != nullptr) return 1;   // A/B switch
+    size_t smem = 0;
+    void* tcg_fn = columns_tcg_entry(h, &smem);
+    void* post0_fn = columns_post_entry<true>(h);
+    void* post_fn = columns_post_entry<false>(h);
+    if (tcg_fn == nullptr || post0_fn == nullptr || post_fn == nullptr) return fail(RIPTRM_E_UNSUPPORTED, "unsupported column count");
+    if (h->d_now == nullptr) CUDA_TRY(cudaMalloc(&h->d_now, 2 * sizeof(double)));
+    prm.now_ptr = h->d_now;
+    prm.now_s = 0.0;
+    prm.cond_on = 1;
+    prm.cond = 0;
+    if (h->col_graph != nullptr) {   // same launches as last time?  (the handle sits inside the block: compare without it)
+        col::Params a = h->col_graph_prm;
+        a.cond = 0;
+        if (memcmp(&a, &prm, sizeof(prm)) != 0) {
+            cudaGraphExecDestroy(h->col_graph);
+            h->col_graph = nullptr;
+        }
+    }
+    if (h->col_graph == nullptr) {
+        for (void* fn : {tcg_fn, post0_fn, post_fn})
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaGraph_t g = nullptr;
+        CUDA_TRY(cudaGraphCreate(&g, 0));
+        cudaGraphConditionalHandle ch;
+        if (cudaGraphConditionalHandleCreate(&ch, g, 1, cudaGraphCondAssignDefault) != cudaSuccess) {
+            cudaGetLastError();
+            cudaGraphDestroy(g);
+            return 1;
+        }
+        col::Params gp = prm;
+        gp.cond = (unsigned long long)ch;
+        double* now = h->d_now;
+        unsigned long long* t0 = reinterpret_cast<unsigned long long*>(h->d_now + 1);
+        int one = 1, zero = 0;
+        auto add_kernel = [&](cudaGraph_t graph, cudaGraphNode_t* dep, void* fn, dim3 grid, dim3 block, size_t sm, void** args,
+                              bool coop, cudaGraphNode_t* out) -> cudaError_t {
+            cudaKernelNodeParams kp = {};
+            kp.func = fn;
+            kp.gridDim = grid;
+            kp.blockDim = block;
+            kp.sharedMemBytes = (unsigned)sm;
+            kp.kernelParams = args;
+            cudaError_t e = cudaGraphAddKernelNode(out, graph, dep, dep ? 1 : 0, &kp);
+            if (e == cudaSuccess && coop) {
+                cudaLaunchAttributeValue v = {};
+                v.cooperative = 1;
+                e = cudaGraphKernelNodeSetAttribute(*out, cudaLaunchAttributeCooperative, &v);
+            }
+            return e;
+        };
+        void* stamp_fn = (void*)col::stamp_kernel;
+        void* a_stamp0[] = {&now, &t0, &one};
+        void* a_stamp[] = {&now, &t0, &zero};
+        void* a_prm[] = {&gp};
+        // start of the clock, then a first reading (> 0: a run whose time budget is already spent must stop at once); every
+        // post launch leaves the reading for the next iteration
+        cudaGraphNode_t n_stamp0, n_stamp1, n_post0, n_while, b_tcg, b_post;
+        cudaError_t e = add_kernel(g, nullptr, stamp_fn, dim3(1), dim3(1), 0, a_stamp0, false, &n_stamp0);
+        if (e == cudaSuccess) e = add_kernel(g, &n_stamp0, stamp_fn, dim3(1), dim3(1), 0, a_stamp, false, &n_stamp1);
+        if (e == cudaSuccess) e = add_kernel(g, &n_stamp1, post0_fn, dim3(h->col_grid), dim3(col::NT), smem, a_prm, true, &n_post0);
+        cudaGraphNodeParams wp = {cudaGraphNodeTypeConditional};
+        wp.conditional.handle = ch;
+        wp.conditional.type = cudaGraphCondTypeWhile;
+        wp.conditional.size = 1;
+        if (e == cudaSuccess) e = cudaGraphAddNode(&n_while, g, &n_post0, 1, &wp);
+        if (e == cudaSuccess) {
+            cudaGraph_t body = wp.conditional.phGraph_out[0];
+            e = add_kernel(body, nullptr, tcg_fn, dim3(h->col_grid), dim3(col::NT), smem, a_prm, true, &b_tcg);
+            if (e == cudaSuccess) e = add_kernel(body, &b_tcg, post_fn, dim3(h->col_grid), dim3(col::NT), smem, a_prm, true, &b_post);
+        }
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&h->col_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            h->col_graph = nullptr;
+            if (getenv("RIPTRM_DEBUG_GRAPH") != nullptr) fprintf(stderr, "[riptrm] columns graph: %s\n", cudaGetErrorString(e));
+            return 1;   // e.g. a driver without conditional nodes: host-sequenced loop
+        }
+        h->col_graph_prm = gp;
+    }
+    CUDA_TRY(cudaGraphLaunch(h->col_graph, st));
+    h->launches += 3;   // the graph launch; the launches inside it are counted on the device (matvec passes, inner iterations)
+    return RIPTRM_OK;
+}
+
+// riptrm_solve on the COLUMNS family: p independent RIPTRM runs sharing S, advanced in lock-step.  One graph launch with a
+// device-side loop (columns_solve_graph); where conditional graph nodes are missing the host sequences the launches (tCG for
+// all columns, then the rest of the trust-region iteration) a few iterations ahead of the flag it polls.
 static int columns_solve(riptrm_handle* h, const double* x0, const double* y0, double* x, double* y, double* summary,
                          double* trace, int where, cudaStream_t st) {
     const riptrm_options& o = h->opts;
@@ -742,8 +881,11 @@ static int columns_solve(riptrm_handle* h, const double* x0, const double* y0, d
     if ((rc = columns_import(h, prm.X, x0, where, st)) || (rc = columns_import(h, prm.Y, y0, where, st))) return rc;
     CUDA_TRY(cudaMemsetAsync(q.colstate, 0, (size_t)col::MAXP * col::CS_FIELDS * sizeof(double), st));
     CUDA_TRY(cudaEventRecord(h->ev0, st));
+    const int grc = columns_solve_graph(h, prm, st);
+    if (grc < 0) return grc;
+    const bool host_loop = grc > 0;
     prm.now_s = seconds_since_start();
-    if ((rc = columns_dispatch_post<true>(h, prm, st))) return rc;
+    if (host_loop && (rc = columns_dispatch_post<true>(h, prm, st))) return rc;
     const long long max_rounds = (long long)(o.maxiter + 1) * (o.inner_maxiter > 0 ? o.inner_maxiter : 100000);
     // The host sequences the launches (one tCG launch and one post launch per trust-region iteration) kColLookahead
     // iterations AHEAD of the "all done" flag: after every iteration the flag is copied to a pinned slot and an event is
@@ -757,7 +899,7 @@ static int columns_solve(riptrm_handle* h, const double* x0, const double* y0, d
     }
     for (int i = 0; i < kColLookahead; ++i) h->h_done[i] = 0;
     h->no_launch_events = true;
-    for (long long round = 0; round < max_rounds; ++round) {
+    for (long long round = 0; host_loop && round < max_rounds; ++round) {
         const int slot = (int)(round % kColLookahead);
         if (round >= kColLookahead) {
             if (cudaEventSynchronize(h->done_ev[slot]) != cudaSuccess) { rc = fail(RIPTRM_E_CUDA, "columns solve: flag poll failed"); break; }
@@ -778,6 +920,7 @@ static int columns_solve(riptrm_handle* h, const double* x0, const double* y0, d
     if (summary != nullptr)
         CUDA_TRY(cudaMemcpyAsync(summary, q.summary, (size_t)nruns * RIPTRM_SUMMARY_FIELDS * sizeof(double), kind, st));
     if (tb != 0 && where != RIPTRM_DEVICE) CUDA_TRY(cudaMemcpyAsync(trace, h->d_trace, tb, cudaMemcpyDeviceToHost, st));
+    if (where == RIPTRM_DEVICE && !host_loop) return RIPTRM_OK;   // enqueue-only, like the batched families
     CUDA_TRY(cudaStreamSynchronize(st));
     return finish_timing(h, true);
 }

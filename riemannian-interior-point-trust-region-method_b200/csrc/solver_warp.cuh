@@ -569,9 +569,14 @@ __device__ __forceinline__ bool inner_step(const typename F::Ctx& ctx, const Dev
     // digits, no decision of the reference dataset's 342 trust-region iterations does (profiles/parity_r02.md is unchanged
     // to every digit); DevOpts::recompute_hdx restores the reference's fresh product.
     Vec Hdx;
-    if (!EXACT && TcgReturnsHw<F>::value && !o.recompute_hdx) {
-        Hdx = Hdx_tcg;
-    } else {
+    bool fresh = true;
+    if constexpr (!EXACT && TcgReturnsHw<F>::value) {
+        if (!o.recompute_hdx) {
+            Hdx = Hdx_tcg;
+            fresh = false;
+        }
+    }
+    if (fresh) {
         Hdx = F::Hw(ctx, pt, y, st, dx);
         cnt.aux += 1.0;
     }
