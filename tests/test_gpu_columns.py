@@ -193,3 +193,35 @@ def test_per_inner_iteration_log_matches_the_c_oracle(rb):
             assert max_rel_diff(o.log, ref, col, rows=m, floor=1e-12) < 1e-6, (c, col)
         assert max_rel_diff(o.log, ref, "residual", rows=m, floor=1e-10) < 1e-5
         assert abs(o.log["cost"][-1] - ref["cost"][-1]) < 1e-7 * abs(ref["cost"][-1])
+
+
+@pytest.mark.parametrize("family", ["columns", "stiefel"])
+def test_device_side_loop_and_host_sequenced_loop_agree_bit_for_bit(rb, family, monkeypatch):
+    """The whole solve runs as one graph launch with a conditional WHILE node (device-side loop); RIPTRM_COLUMNS_HOST_LOOP=1
+    sequences the same launches from the host.  Same launches, same order: identical iterates, multipliers, summaries, logs."""
+    n, p = 100, 4
+    Z, X0, Y0, rs = _instance(n, p, seed=5)
+    Y0 = np.ones((n, p))
+    opt = rb.options.default_option()
+    opt.update(TRS_solver="tCG", second_order_stationarity=False, maxiter=6, tolresid=0, maxtime=1e9, inner_maxiter=50)
+    res = []
+    for host_loop in (False, True):
+        if host_loop:
+            monkeypatch.setenv("RIPTRM_COLUMNS_HOST_LOOP", "1")
+        else:
+            monkeypatch.delenv("RIPTRM_COLUMNS_HOST_LOOP", raising=False)
+        if family == "columns":
+            s = rb.ColumnsSolver(Z, p)
+            x0 = X0
+        else:
+            from helpers import stiefel_start
+            s = rb.StiefelSolver(Z, p, eps=0.01)
+            x0 = stiefel_start(n, p, 5)
+        res.append(s.solve(x0, Y0, opt, per_inner_trace=True, trace_capacity=600))
+        s.close()
+    (Xa, Ya, sa, ta), (Xb, Yb, sb, tb) = res
+    TIME = rb._lib.TR["time"]
+    keep = [i for i in range(ta.shape[2]) if i != TIME]
+    assert np.array_equal(Xa, Xb) and np.array_equal(Ya, Yb) and np.array_equal(sa, sb)
+    assert np.array_equal(np.nan_to_num(ta[:, :, keep], nan=-7.0), np.nan_to_num(tb[:, :, keep], nan=-7.0))
+    assert sa[0, rb._lib.SM["outer_iters"]] >= 1
