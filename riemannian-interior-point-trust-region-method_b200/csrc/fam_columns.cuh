@@ -90,6 +90,9 @@ struct Params {
     // device-side loop (riptrm_api.cu columns_solve_graph): the launches of a whole solve are the body of a conditional WHILE
     // graph node; seconds since the start come from a device clock stamp written ahead of every iteration, and the post
     // kernel ends the loop
+    int reuse_heta;                // COLUMNS whole solve: the Hw[dx] of RIPTRM.py:659 is the Hw[eta] the tCG accumulated (one S.V
+                                   // pass and three reduction rounds fewer per trust-region iteration; solver_warp.cuh
+                                   // inner_step has the argument); 0 = a fresh product (RIPTRM_RECOMPUTE_HDX=1)
     const double* now_ptr;         // nullptr: `now_s` above (host clock at enqueue time)
     unsigned long long cond;       // cudaGraphConditionalHandle
     int cond_on;
@@ -1264,6 +1267,21 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
                 ps[tid].pl_new = sm.scal[P + tid];
             }
             __syncthreads();
+            if (prm.reuse_heta) {
+                // <Hw dx, dx>, <c, dx> with the Hw[eta] the tCG kernel accumulated beside eta
+                double part[2] = {0.0, 0.0};
+                if (ps[myc].path == 3) {
+                    FOR_ELEMS(e) {
+                        const double v = prm.eta[e];
+                        part[0] = fma(prm.Heta[e], v, part[0]);
+                        part[1] = fma(prm.c[e], v, part[1]);
+                    }
+                }
+                block_reduce_store<P, 2>(prm, sm, part, buf);
+                grid.sync();
+                gather_scalars<P, 2>(prm, sm, buf);
+                buf ^= 1;
+            } else {
             stream_pass<P>(prm, sm, pipe);  // S dx
             grid.sync();
             // ---- P7-P9: Hw[dx] as in the tCG kernel, then <Hw dx, dx>, <c, dx> ------------------------------------------
@@ -1325,6 +1343,7 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
             grid.sync();
             gather_scalars<P, 2>(prm, sm, buf);
             buf ^= 1;
+            }
         }
         // ---- P10: rho test, radius update (:660-677), acceptance, inner-loop bookkeeping (:808-842) --------------------
         if (tid < P && ps[tid].path) {
@@ -1340,7 +1359,7 @@ __global__ void __launch_bounds__(NT, 1) columns_post_kernel(Params prm) {
                 s.inner_status = (double)RIPTRM_INNER_PRIMAL_INFEASIBLE;
                 s.DeltaNext = prm.gamma * s.normdx;
             } else {
-                s.cnt_aux += 1.0;
+                if (!prm.reuse_heta) s.cnt_aux += 1.0;
                 const double phi_cur = s.cost - s.mu * s.pl_cur, phi_new = s.costN - s.mu * s.pl_new;
                 double ared = phi_cur - phi_new;
                 double pred = (0.0 - 0.5 * sm.scal[tid]) - sm.scal[P + tid];

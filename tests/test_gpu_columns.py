@@ -118,9 +118,8 @@ def test_whole_solve_matches_the_c_oracle_per_column(rb):
                 # tCG counts hinge on the ulp-level test norm_r <= target (RIPTRM.py:183): a different summation
                 # order may stop one iteration apart
                 assert abs(sm[c, SM["tcg_iters"]] - so[12]) <= 2, (c, sm[c, SM["tcg_iters"]], so[12])
-                # the COLUMNS kernel forms Hw[dx] of RIPTRM.py:659 afresh (one S.V pass per trust-region iteration not taken
-                # in the converged / infeasible branches); the Sphere path and the C oracle reuse the tCG's product
-                assert so[13] == 0 and 0 < sm[c, SM["aux_hessvecs"]] <= sm[c, SM["inner_iters"]]
+                # the Hw[dx] of RIPTRM.py:659 is the product the tCG accumulated, in the kernels and in the C oracle
+                assert so[13] == 0 and sm[c, SM["aux_hessvecs"]] == 0
             assert abs(sm[c, SM["cost"]] - so[0]) < (1e-6 if exact_counts else 1e-8) * abs(so[0])
             if not exact_counts:
                 assert np.max(np.abs(X[:, c] - xo)) < 1e-8
