@@ -753,6 +753,24 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
                 ps.pl_new = colsum<P>(tot, 1);
             }
             __syncthreads();
+            if (prm.reuse_heta) {
+                // <Hw dx, dx>, <c, dx> with the Hw[eta] the tCG kernel accumulated beside eta (fam_columns.cuh Params::reuse_heta)
+                double part[2] = {0.0, 0.0};
+                FOR_ROWS(row, e) {
+                    const double v = prm.eta[e];
+                    part[0] = fma(prm.Heta[e], v, part[0]);
+                    part[1] = fma(prm.c[e], v, part[1]);
+                }
+                breduce<P, 2, 0>(prm, sm, part, buf);
+                grid.sync();
+                gather_tot<P>(prm, sm, tot, buf, 2, 2);
+                buf ^= 1;
+                if (tid == 0) {
+                    ps.hdx = colsum<P>(tot, 0);
+                    ps.cdx = colsum<P>(tot, 1);
+                }
+                __syncthreads();
+            } else {
             stream_pass<P>(prm, sm, pipe);  // S dx
             grid.sync();
             // ---- P7: W of Hw[dx];  X'W, <dx, W>, <c, dx> ---------------------------------------------------------------
@@ -789,6 +807,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
                 ps.cdx = colsum<P>(tot, P + 1);
             }
             __syncthreads();
+            }
         }
         // ---- P10: rho test, radius update (:660-677), acceptance, inner-loop bookkeeping (:808-842) --------------------
         if (tid == 0) {
@@ -804,7 +823,7 @@ __global__ void __launch_bounds__(NT, 1) stiefel_post_kernel(Params prm) {
                 s.inner_status = (double)RIPTRM_INNER_PRIMAL_INFEASIBLE;
                 s.DeltaNext = prm.gamma * s.normdx;
             } else {
-                s.cnt_aux += 1.0;
+                if (!prm.reuse_heta) s.cnt_aux += 1.0;
                 const double phi_cur = s.cost - s.mu * s.pl_cur, phi_new = s.costN - s.mu * s.pl_new;
                 double ared = phi_cur - phi_new;
                 double pred = (0.0 - 0.5 * s.hdx) - s.cdx;

@@ -843,7 +843,7 @@ static int columns_solve(riptrm_handle* h, const double* x0, const double* y0, d
     col::Params prm{};
     const ColPtrs q = columns_fill_params(h, prm);
     prm.solve = 1;
-    prm.reuse_heta = (!is_stiefel(h) && getenv("RIPTRM_RECOMPUTE_HDX") == nullptr) ? 1 : 0;
+    prm.reuse_heta = (getenv("RIPTRM_RECOMPUTE_HDX") == nullptr) ? 1 : 0;
     prm.mu_sched = h->d_sched;
     prm.tolL_sched = h->d_sched + h->sched_len;
     prm.tolC_sched = h->d_sched + 2 * h->sched_len;
