@@ -18,6 +18,7 @@
 namespace riptrm {
 
 struct GrassmannFam {
+    static constexpr bool kTcgReturnsHw = true;   // tcg_generic accumulates Hw[eta] beside eta: solver_warp.cuh inner_step
     static constexpr int K = 1;
     static constexpr int MK = 1;
     static constexpr int PMAX = 5;

@@ -31,6 +31,7 @@ struct StableIdFam {
     static constexpr int DMAX = 5;
     static constexpr int kComponents = 3;
     static constexpr int kSlots = 8;
+    static constexpr bool kTcgReturnsHw = true;   // tcg() returns Hw[eta] (unwhitened) beside eta: solver_warp.cuh inner_step
     using Vec = WVec<3>;
     using CVec = WVec<1>;
     using LM = double;  // "lane matrix": a d x d matrix with one entry per lane
