@@ -33,6 +33,7 @@ struct SphereFam {
     static constexpr int K = K_;
     static constexpr int MK = K_;
     static constexpr bool kTcgReturnsHw = true;   // tcg() returns Hw[eta] accumulated beside eta (solver_warp.cuh inner_step)
+    static constexpr bool kMergedStepDots = true; // step_dots / gadj_given / retract_given below
     static_assert(K_ == 2 || K_ == 4, "pair layout: K is 2 or 4");
     using Vec = WVec<K>;
     using CVec = WVec<K>;
@@ -283,6 +284,35 @@ struct SphereFam {
 #pragma unroll
         for (int k = 0; k < K; ++k) g.v[k] = v.v[k] - pt.x.v[k] * b;
         return g;
+    }
+
+    // The five inner products of a trust-region iteration that depend on dx alone, in one reduction round (inner_step):
+    // <dx,dx>, <x,dx>, <x+dx,x+dx>, <Hdx,dx>, <c,dx>; per value the tree of wdot(), hence the bits of the separate calls.
+    static __device__ __forceinline__ void step_dots(const Ctx&, const Pt& pt, const Step& st, const Vec& dx, const Vec& Hdx,
+                                                     double (&d)[5]) {
+        Vec a;
+#pragma unroll
+        for (int k = 0; k < K; ++k) a.v[k] = pt.x.v[k] + dx.v[k];
+        d[0] = wdot_partial(dx, dx);
+        d[1] = wdot_partial(pt.x, dx);
+        d[2] = wdot_partial(a, a);
+        d[3] = wdot_partial(Hdx, dx);
+        d[4] = wdot_partial(st.c, dx);
+        wsumN<5>(d);
+    }
+    static __device__ __forceinline__ CVec gadj_given(const Ctx& c, const Pt& pt, const Vec& v, double b) {
+        if (c.embedded) return v;
+        CVec g;
+#pragma unroll
+        for (int k = 0; k < K; ++k) g.v[k] = v.v[k] - pt.x.v[k] * b;
+        return g;
+    }
+    static __device__ __forceinline__ Vec retract_given(const Ctx&, const Pt& pt, const Vec& dx, double aa) {
+        Vec a;
+        const double nrm = sqrt(aa);
+#pragma unroll
+        for (int k = 0; k < K; ++k) a.v[k] = (pt.x.v[k] + dx.v[k]) / nrm;
+        return a;
     }
 
     static __device__ __forceinline__ Vec Hw(const Ctx& c, const Pt& pt, const CVec&, const Step& st, const Vec& v) {

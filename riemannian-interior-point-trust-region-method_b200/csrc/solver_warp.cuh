@@ -35,6 +35,15 @@ struct DevOpts {
     int recompute_hdx;
 };
 
+// families that take the inner products a trust-region iteration needs from dx alone -- <dx,dx> (:735), the projection
+// coefficient of G*[dx] (:743), the retraction's norm (:744), <Hw dx, dx> and <c, dx> (:659-660) -- in ONE reduction round
+// instead of four declare `static constexpr bool kMergedStepDots = true` and provide step_dots / gadj_given / retract_given
+// (same summation tree per value, hence the same bits)
+template <class F, class = void>
+struct MergedStepDots { static constexpr bool value = false; };
+template <class F>
+struct MergedStepDots<F, std::enable_if_t<F::kMergedStepDots>> { static constexpr bool value = true; };
+
 // families whose tcg() hands back Hw[eta] next to eta declare `static constexpr bool kTcgReturnsHw = true`
 template <class F, class = void>
 struct TcgReturnsHw { static constexpr bool value = false; };
@@ -469,11 +478,21 @@ __device__ __forceinline__ bool inner_step(const typename F::Ctx& ctx, const Dev
         info.dxtype = (double)tr.stop;
         info.tcg_iters = (double)tr.iters;
     }
-    const double normdx = sqrt(F::inner(ctx, pt, dx, dx));          // :735
+    constexpr bool MERGED = !EXACT && MergedStepDots<F>::value && TcgReturnsHw<F>::value;
+    double dots[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // MERGED: <dx,dx>, <x,dx>, <x+dx,x+dx>, <Hw dx,dx>, <c,dx>
+    double normdx;
+    CVec ga;
+    if constexpr (MERGED) {
+        F::step_dots(ctx, pt, st, dx, Hdx_tcg, dots);
+        normdx = sqrt(dots[0]);                                     // :735
+        ga = F::gadj_given(ctx, pt, dx, dots[1]);
+    } else {
+        normdx = sqrt(F::inner(ctx, pt, dx, dx));                   // :735
+        ga = F::gadj(ctx, pt, dx);
+    }
     info.normdx = normdx;
 
     // dy = -y + mu * (1/s) - y * G*[dx] / s ; yNew = y + dy        (:743, :745)
-    const CVec ga = F::gadj(ctx, pt, dx);
     CVec yNew;
 #pragma unroll
     for (int k = 0; k < MK; ++k) {
@@ -485,7 +504,8 @@ __device__ __forceinline__ bool inner_step(const typename F::Ctx& ctx, const Dev
         }
     }
     typename F::Pt ptN;
-    F::eval_point(ctx, F::retract(ctx, pt, dx), ptN);               // :744 (+ cost, s at xNew)
+    if constexpr (MERGED) F::eval_point(ctx, F::retract_given(ctx, pt, dx, dots[2]), ptN);
+    else F::eval_point(ctx, F::retract(ctx, pt, dx), ptN);          // :744 (+ cost, s at xNew)
 
     // compute_inner_stoppingcriteria (:574-629)
     bool xfe = true, yfe = true;
@@ -576,12 +596,19 @@ __device__ __forceinline__ bool inner_step(const typename F::Ctx& ctx, const Dev
             fresh = false;
         }
     }
-    if (fresh) {
-        Hdx = F::Hw(ctx, pt, y, st, dx);
-        cnt.aux += 1.0;
+    double ip_hd, ip_cd;
+    if (MERGED && !fresh) {
+        ip_hd = dots[3];                                            // taken in the merged round right after the tCG
+        ip_cd = dots[4];
+    } else {
+        if (fresh) {
+            Hdx = F::Hw(ctx, pt, y, st, dx);
+            cnt.aux += 1.0;
+        }
+        ip_hd = F::inner_partial(ctx, pt, Hdx, dx);
+        ip_cd = F::inner_partial(ctx, pt, st.c, dx);
+        wsum2(ip_hd, ip_cd);
     }
-    double ip_hd = F::inner_partial(ctx, pt, Hdx, dx), ip_cd = F::inner_partial(ctx, pt, st.c, dx);
-    wsum2(ip_hd, ip_cd);
     double pred = (0.0 - 0.5 * ip_hd) - ip_cd;
     const double reg = (fmax(1.0, fabs(phi_cur)) * 2.220446049250313e-16) * o.reduction_regularization;  // :660
     ared = ared + reg;
