@@ -171,7 +171,7 @@ def test_fullsize_properties(rb):
 
 @pytest.mark.parametrize("family", ["stiefel", "columns"])
 def test_time_limits_of_the_large_n_solves(rb, family):
-    """`maxtime` (base_solver.py:85-106) and `inner_maxtime` (RIPTRM.py:822-834) on the host-sequenced whole solves: a run
+    """`maxtime` (base_solver.py:85-106) and `inner_maxtime` (RIPTRM.py:822-834) on the whole solves of the large-n families (device clock inside the graph launch): a run
     whose budget is already spent stops at outer iteration 0 with the starting point; an inner budget of zero rolls every
     inner loop back after its first trust-region iteration ('max-time-exceeded') and the run ends on maxiter."""
     n, p = 96, 4
