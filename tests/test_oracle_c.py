@@ -99,3 +99,31 @@ def test_merged_reduction_tcg_matches_reference_operation_order(datasets):
     assert np.max(np.abs(xa - xb)) < 1e-12 and abs(sa[0] - sb[0]) < 1e-12 * abs(sb[0])
     g = load_golden("nonnegpca_1_a_K40")
     assert np.max(np.abs(xb - np.array(g["x"]))) < REL_TOL
+
+
+def test_model_decrease_from_the_tcg_product_moves_no_decision(datasets, monkeypatch):
+    """inner_step evaluates pred = -<c,dx> - <dx,Hw dx>/2 (RIPTRM.py:659-660) with the Hw[eta] the tCG accumulated beside eta;
+    RIPTRM_RECOMPUTE_HDX=1 forms the fresh product the reference writes.  Hw is linear, so the two differ by rounding only:
+    on the reference's dataset every discrete column of the 343-row trace, every radius and every tCG count is the same, the
+    objective agrees to 1e-13 and `ared_pred` to 1e-6 wherever it is not a ratio of two rounding-level numbers."""
+    d = datasets["NonnegPCA/1"]
+    runs = []
+    for fresh in (False, True):
+        if fresh:
+            monkeypatch.setenv("RIPTRM_RECOMPUTE_HDX", "1")
+        else:
+            monkeypatch.delenv("RIPTRM_RECOMPUTE_HDX", raising=False)
+        x, y, sm, tr = detc.solve(d["Z"], d["initx_a"], d["initineqLagmult"], {"maxiter": 40, "tolresid": 0},
+                                  trace_capacity=512)
+        runs.append((x, y, sm, rb.trace_to_log(tr)))
+    (xa, ya, sa, La), (xb, yb, sb, Lb) = runs
+    assert sa[13] == 0 and sb[13] > 0                                # fresh products formed: none / one per rho test
+    assert len(La["iteration"]) == len(Lb["iteration"]) == 343   # row 0 + 342 trust-region iterations
+    assert first_discrete_mismatch(La, Lb, columns=DISCRETE_COLUMNS + ("tcg_iters",)) == len(La["iteration"])
+    assert max_rel_diff(La, Lb, "TR_radius") == 0.0
+    assert max_rel_diff(La, Lb, "cost") < 1e-13
+    assert np.max(np.abs(xa - xb)) < 1e-14 and sa[12] == sb[12]
+    ra = np.array([v if v is not None else np.nan for v in La["ared/pred"]], dtype=float)
+    rbv = np.array([v if v is not None else np.nan for v in Lb["ared/pred"]], dtype=float)
+    ok = np.isfinite(ra) & np.isfinite(rbv) & (np.array(La["iteration"]) <= 30)
+    assert np.nanmax(np.abs(ra[ok] - rbv[ok]) / np.maximum(1.0, np.abs(rbv[ok]))) < 1e-6
