@@ -343,3 +343,26 @@ def test_standin_coordinator_problems_are_recognised(datasets):
     cs = rb.StableIdStructure.conspec_from_constset(datasets["StableIdentification/1"]["constset"])
     assert isinstance(st, rb.StableIdStructure) and np.array_equal(st.conspec, cs) and st.X.shape == (5, 95)
     assert np.array_equal(st.x0[2], datasets["StableIdentification/1"]["initQ_t"])
+
+
+def test_bench_arms_describe_the_same_workload():
+    """The driver compares the `config` of `bench.py` and `bench.py --impl reference`: both come from one function of the
+    arguments, steps in flight included."""
+    import importlib.util
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_bench_mod", os.path.join(root, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(mod)
+        args = mod.parse()
+    finally:
+        sys.argv = argv
+    assert args.in_flight == 2 and args.gpus == 1 and args.scaling == "weak"
+    c1, c8 = mod.config_dict(args, 1), mod.config_dict(args, 8)
+    assert c1["in_flight"] == 2 and c1["pairs_per_gpu"] == 16384 and c8["pairs_total"] == 8 * 16384
+    assert "flushed" in c1["l2"] and mod.UNIT == "pairs/s"
+    args.scaling = "strong"
+    assert mod.config_dict(args, 8)["pairs_per_gpu"] == 2048 and mod.instances_per_rank(args, 8) == 512
