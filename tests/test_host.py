@@ -366,3 +366,43 @@ def test_bench_arms_describe_the_same_workload():
     assert "flushed" in c1["l2"] and mod.UNIT == "pairs/s"
     args.scaling = "strong"
     assert mod.config_dict(args, 8)["pairs_per_gpu"] == 2048 and mod.instances_per_rank(args, 8) == 512
+
+
+def test_recognition_with_the_attribute_layout_of_real_pymanopt(datasets, monkeypatch):
+    """pymanopt 2.2's `Function` keeps the user's function as `_original_function`, a backend object as `_backend` and the
+    backend's `prepare_function(function)` result as `_function` (for the autograd backend the function itself, for others a
+    wrapper).  The closure walk does not depend on attribute names: a Function laid out that way -- with `_function` a
+    functools.wraps wrapper, the harder case -- is recognised like the stand-in's."""
+    import functools
+
+    import dropin_standins as D
+    import pymanopt.function as pf
+
+    class _Backend:
+        def __init__(self):
+            self.name = "Autograd"
+
+        def prepare_function(self, function):
+            @functools.wraps(function)
+            def prepared(*args):
+                return function(*args)
+            return prepared
+
+    class RealLayoutFunction(pf.Function):
+        def __init__(self, function, manifold):
+            super().__init__(function, manifold)
+            self._original_function = function
+            self._backend = _Backend()
+            self._function = self._backend.prepare_function(function)
+            self._gradient = None
+            self._hessian = None
+
+    monkeypatch.setattr(pf, "Function", RealLayoutFunction)
+    pb = D.build_problem("NonnegPCA", datasets)
+    assert type(pb.cost).__name__ == "RealLayoutFunction" and hasattr(pb.cost, "_original_function")
+    st = rb.structure_from_problem(pb)
+    assert isinstance(st, rb.NonnegPCAStructure) and np.array_equal(st.Z, datasets["NonnegPCA/1"]["Z"])
+    st = rb.structure_from_problem(D.build_problem("Rosenbrock", datasets))
+    assert isinstance(st, rb.RosenbrockStructure) and (st.alpha, st.offset, st.shape) == (1e7, 0.01, (5, 3, 15))
+    st = rb.structure_from_problem(D.build_problem("StableIdentification", datasets, "t"))
+    assert isinstance(st, rb.StableIdStructure) and st.X.shape == (5, 95)
